@@ -1,0 +1,262 @@
+"""Drop-in for the reference's pybind module `pointnet2._ext`.
+
+Same nine function names, argument order, return types and precondition errors as
+/root/reference/detection/Votenet/pointnet2/_ext_src/src/bindings.cpp:11-24 (wrappers in
+sampling.cpp, ball_query.cpp, group_points.cpp, interpolate.cpp), but every op runs in
+libb2r.so (hand-written sm_100a CUDA behind the C ABI of include/b2r.h).  The reference's own
+`pointnet2_utils.py` works unchanged on top of this module (the repo-root
+package `pointnet2/` re-exports it under the reference's import path).
+
+Error behaviour mirrors `_ext_src/include/utils.h:10-30`: non-contiguous / wrong dtype / mixed
+device inputs raise RuntimeError with the reference's messages; CPU tensors raise
+"CPU not supported" (sampling.cpp:38-40).  A failing kernel launch raises instead of calling
+exit(-1) (cuda_utils.h:35-44).
+"""
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk_contig(t, name):
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be a contiguous tensor" % name)
+
+
+def _chk_float(t, name):
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be a float tensor" % name)
+
+
+def _chk_int(t, name):
+    if t.dtype != torch.int32:
+        raise RuntimeError("%s must be an int tensor" % name)
+
+
+def _chk_cuda(lead, others):
+    if not lead.is_cuda:
+        raise RuntimeError("CPU not supported")
+    for t, name in others:
+        if not t.is_cuda:
+            raise RuntimeError("%s must be a CUDA tensor" % name)
+        if t.device != lead.device:
+            raise RuntimeError("%s must be on the same device as the first argument" % name)
+
+
+class _on_device:
+    """Make the tensor's device current for the duration of the launch (the reference relies on
+    the caller's current device; nn.DataParallel replicas set it per thread)."""
+
+    def __init__(self, t):
+        self.idx = t.device.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.idx is not None and self.idx != cur:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *a):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+def furthest_point_sampling(points, nsamples):
+    """(B,N,3) f32 -> (B,nsamples) i32.  Replaces sampling.cpp:70-91."""
+    _chk_contig(points, "points")
+    _chk_float(points, "points")
+    _chk_cuda(points, [])
+    B, N = points.size(0), points.size(1)
+    out = torch.empty((B, nsamples), dtype=torch.int32, device=points.device)
+    with _on_device(points):
+        _lib.check(_lib.lib().b2r_fps(points.data_ptr(), B, N, int(nsamples), out.data_ptr(),
+                                      _stream()), "furthest_point_sampling")
+    return out
+
+
+def gather_points(points, idx):
+    """(B,C,N), (B,M) -> (B,C,M).  Replaces sampling.cpp:20-43."""
+    _chk_contig(points, "points")
+    _chk_contig(idx, "idx")
+    _chk_float(points, "points")
+    _chk_int(idx, "idx")
+    _chk_cuda(points, [(idx, "idx")])
+    B, C, N = points.shape
+    M = idx.size(1)
+    out = torch.empty((B, C, M), dtype=torch.float32, device=points.device)
+    with _on_device(points):
+        _lib.check(_lib.lib().b2r_gather_fwd(points.data_ptr(), idx.data_ptr(), B, C, N, M,
+                                             out.data_ptr(), _stream()), "gather_points")
+    return out
+
+
+def gather_points_grad(grad_out, idx, n):
+    """(B,C,M), (B,M), n -> (B,C,n).  Replaces sampling.cpp:45-69."""
+    _chk_contig(grad_out, "grad_out")
+    _chk_contig(idx, "idx")
+    _chk_float(grad_out, "grad_out")
+    _chk_int(idx, "idx")
+    _chk_cuda(grad_out, [(idx, "idx")])
+    B, C, M = grad_out.shape
+    out = torch.empty((B, C, int(n)), dtype=torch.float32, device=grad_out.device)
+    with _on_device(grad_out):
+        _lib.check(_lib.lib().b2r_gather_bwd(grad_out.data_ptr(), idx.data_ptr(), B, C, int(n), M,
+                                             out.data_ptr(), _stream()), "gather_points_grad")
+    return out
+
+
+def ball_query(new_xyz, xyz, radius, nsample):
+    """(B,M,3), (B,N,3) -> (B,M,nsample) i32.  Replaces ball_query.cpp:13-37."""
+    _chk_contig(new_xyz, "new_xyz")
+    _chk_contig(xyz, "xyz")
+    _chk_float(new_xyz, "new_xyz")
+    _chk_float(xyz, "xyz")
+    _chk_cuda(new_xyz, [(xyz, "xyz")])
+    B, M = new_xyz.size(0), new_xyz.size(1)
+    N = xyz.size(1)
+    out = torch.empty((B, M, int(nsample)), dtype=torch.int32, device=new_xyz.device)
+    with _on_device(new_xyz):
+        _lib.check(_lib.lib().b2r_ball_query(new_xyz.data_ptr(), xyz.data_ptr(), B, N, M,
+                                             float(radius), int(nsample), out.data_ptr(),
+                                             _stream()), "ball_query")
+    return out
+
+
+def group_points(points, idx):
+    """(B,C,N), (B,NP,NS) -> (B,C,NP,NS).  Replaces group_points.cpp:17-40."""
+    _chk_contig(points, "points")
+    _chk_contig(idx, "idx")
+    _chk_float(points, "points")
+    _chk_int(idx, "idx")
+    _chk_cuda(points, [(idx, "idx")])
+    B, C, N = points.shape
+    NP, NS = idx.size(1), idx.size(2)
+    out = torch.empty((B, C, NP, NS), dtype=torch.float32, device=points.device)
+    with _on_device(points):
+        _lib.check(_lib.lib().b2r_group_fwd(points.data_ptr(), idx.data_ptr(), B, C, N, NP, NS,
+                                            out.data_ptr(), _stream()), "group_points")
+    return out
+
+
+def group_points_grad(grad_out, idx, n):
+    """(B,C,NP,NS), (B,NP,NS), n -> (B,C,n).  Replaces group_points.cpp:42-65."""
+    _chk_contig(grad_out, "grad_out")
+    _chk_contig(idx, "idx")
+    _chk_float(grad_out, "grad_out")
+    _chk_int(idx, "idx")
+    _chk_cuda(grad_out, [(idx, "idx")])
+    B, C, NP, NS = grad_out.shape
+    out = torch.empty((B, C, int(n)), dtype=torch.float32, device=grad_out.device)
+    with _on_device(grad_out):
+        _lib.check(_lib.lib().b2r_group_bwd(grad_out.data_ptr(), idx.data_ptr(), B, C, int(n), NP,
+                                            NS, out.data_ptr(), _stream()), "group_points_grad")
+    return out
+
+
+def three_nn(unknowns, knows):
+    """(B,n,3), (B,m,3) -> [dist2 (B,n,3) f32, idx (B,n,3) i32].  Replaces interpolate.cpp:19-45."""
+    _chk_contig(unknowns, "unknowns")
+    _chk_contig(knows, "knows")
+    _chk_float(unknowns, "unknowns")
+    _chk_float(knows, "knows")
+    _chk_cuda(unknowns, [(knows, "knows")])
+    B, n = unknowns.size(0), unknowns.size(1)
+    m = knows.size(1)
+    dist2 = torch.empty((B, n, 3), dtype=torch.float32, device=unknowns.device)
+    idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknowns.device)
+    with _on_device(unknowns):
+        _lib.check(_lib.lib().b2r_three_nn(unknowns.data_ptr(), knows.data_ptr(), B, n, m,
+                                           dist2.data_ptr(), idx.data_ptr(), _stream()),
+                   "three_nn")
+    return [dist2, idx]
+
+
+def three_interpolate(points, idx, weight):
+    """(B,C,m), (B,n,3), (B,n,3) -> (B,C,n).  Replaces interpolate.cpp:47-75."""
+    _chk_contig(points, "points")
+    _chk_contig(idx, "idx")
+    _chk_contig(weight, "weight")
+    _chk_float(points, "points")
+    _chk_int(idx, "idx")
+    _chk_float(weight, "weight")
+    _chk_cuda(points, [(idx, "idx"), (weight, "weight")])
+    B, C, m = points.shape
+    n = idx.size(1)
+    out = torch.empty((B, C, n), dtype=torch.float32, device=points.device)
+    with _on_device(points):
+        _lib.check(_lib.lib().b2r_three_interp_fwd(points.data_ptr(), idx.data_ptr(),
+                                                   weight.data_ptr(), B, C, m, n, out.data_ptr(),
+                                                   _stream()), "three_interpolate")
+    return out
+
+
+def three_interpolate_grad(grad_out, idx, weight, m):
+    """(B,C,n), (B,n,3), (B,n,3), m -> (B,C,m).  Replaces interpolate.cpp:76-104."""
+    _chk_contig(grad_out, "grad_out")
+    _chk_contig(idx, "idx")
+    _chk_contig(weight, "weight")
+    _chk_float(grad_out, "grad_out")
+    _chk_int(idx, "idx")
+    _chk_float(weight, "weight")
+    _chk_cuda(grad_out, [(idx, "idx"), (weight, "weight")])
+    B, C, n = grad_out.shape
+    out = torch.empty((B, C, int(m)), dtype=torch.float32, device=grad_out.device)
+    with _on_device(grad_out):
+        _lib.check(_lib.lib().b2r_three_interp_bwd(grad_out.data_ptr(), idx.data_ptr(),
+                                                   weight.data_ptr(), B, C, n, int(m),
+                                                   out.data_ptr(), _stream()),
+                   "three_interpolate_grad")
+    return out
+
+
+# ---- beyond the reference's nine: the fused QueryAndGroup tail (include/b2r.h) -------------
+def query_group(xyz, new_xyz, features, idx, radius, normalize_xyz):
+    """One-pass group(xyz)-new_xyz(/radius) ++ group(features) -> (B,3+C,NP,NS)."""
+    _chk_cuda(xyz, [(new_xyz, "new_xyz"), (idx, "idx")])
+    for t, nme in ((xyz, "xyz"), (new_xyz, "new_xyz")):
+        _chk_contig(t, nme)
+        _chk_float(t, nme)
+    _chk_contig(idx, "idx")
+    _chk_int(idx, "idx")
+    C = 0
+    fptr = None
+    if features is not None:
+        _chk_contig(features, "features")
+        _chk_float(features, "features")
+        _chk_cuda(xyz, [(features, "features")])
+        C = features.size(1)
+        fptr = features.data_ptr()
+    B, N = xyz.size(0), xyz.size(1)
+    NP, NS = idx.size(1), idx.size(2)
+    out = torch.empty((B, 3 + C, NP, NS), dtype=torch.float32, device=xyz.device)
+    with _on_device(xyz):
+        _lib.check(_lib.lib().b2r_query_group_fwd(xyz.data_ptr(), new_xyz.data_ptr(), fptr,
+                                                  idx.data_ptr(), B, C, N, NP, NS, float(radius),
+                                                  1 if normalize_xyz else 0, out.data_ptr(),
+                                                  _stream()), "query_group")
+    return out
+
+
+def query_group_grad(grad_out, idx, N, C, radius, normalize_xyz, need_xyz, need_new_xyz,
+                     need_features):
+    """Backward of query_group: returns (grad_xyz|None, grad_new_xyz|None, grad_features|None)."""
+    _chk_contig(grad_out, "grad_out")
+    _chk_float(grad_out, "grad_out")
+    _chk_cuda(grad_out, [(idx, "idx")])
+    B, _, NP, NS = grad_out.shape
+    dev = grad_out.device
+    gx = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if need_xyz else None
+    gn = torch.empty((B, NP, 3), dtype=torch.float32, device=dev) if need_new_xyz else None
+    gf = torch.empty((B, C, N), dtype=torch.float32, device=dev) if (need_features and C) else None
+    with _on_device(grad_out):
+        _lib.check(_lib.lib().b2r_query_group_bwd(
+            grad_out.data_ptr(), idx.data_ptr(), B, C, int(N), NP, NS, float(radius),
+            1 if normalize_xyz else 0,
+            gx.data_ptr() if gx is not None else None,
+            gn.data_ptr() if gn is not None else None,
+            gf.data_ptr() if gf is not None else None, _stream()), "query_group_grad")
+    return gx, gn, gf

@@ -1,0 +1,67 @@
+"""ctypes binding of libb2r.so (the C ABI declared in include/b2r.h).
+
+There is NO fallback: if the library is missing or a call fails this module raises.  The
+library is built in-tree by `backtoreality_b200.build.build()` (nvcc, sm_100a only).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2r.so")
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_f = ctypes.c_float
+_ip = ctypes.POINTER(ctypes.c_int)
+
+# name -> argtypes; every function returns int (b2r_status) unless listed in _RESTYPES
+SIGNATURES = {
+    "b2r_version": [],
+    "b2r_status_string": [_i],
+    "b2r_last_error": [],
+    "b2r_ref_block_threads": [_i],
+    "b2r_fps": [_vp, _i, _i, _i, _vp, _vp],
+    "b2r_fps_plan": [_i, _i, _ip, _ip, _ip, _ip],
+    "b2r_gather_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "b2r_gather_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "b2r_ball_query": [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp],
+    "b2r_group_fwd": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "b2r_group_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "b2r_three_nn": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "b2r_three_interp_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "b2r_three_interp_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "b2r_query_group_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp],
+    "b2r_query_group_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp],
+}
+_RESTYPES = {"b2r_status_string": ctypes.c_char_p, "b2r_last_error": ctypes.c_char_p}
+
+_lib = None
+
+
+class B2RError(RuntimeError):
+    """A libb2r call returned a negative status."""
+
+
+def lib():
+    """Load libb2r.so once.  Raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise ImportError(
+                "libb2r.so not found at %s -- build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU or PyTorch fallback for these ops)" % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(l, name)  # AttributeError if the .so is stale: loud on purpose
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, ctypes.c_int)
+        _lib = l
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        l = lib()
+        raise B2RError("%s failed: %s (%s)" % (
+            what, l.b2r_status_string(status).decode(), l.b2r_last_error().decode()))

@@ -1,0 +1,75 @@
+"""Pointnet2Backbone (VoteNet and GroupFree3D flavours) on the B200-native ops.
+
+Mirrors /root/reference/detection/Votenet/models/backbone_module.py:21-133 and
+/root/reference/detection/GroupFree3D/models/backbone_module.py:21-138: four
+PointnetSAModuleVotes (npoint 2048/1024/512/256, radius 0.2/0.4/0.8/1.2, nsample 64/32/16/16)
+and two PointnetFPModule; identical hyper-parameters, end_points keys and state-dict layout
+(SURVEY.md appendix B).  The only difference between the two flavours is the width of fp2's last
+layer (256 vs 288), selected with `fp2_out`.
+"""
+import torch
+import torch.nn as nn
+
+from .pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
+
+
+class Pointnet2Backbone(nn.Module):
+    """input_feature_dim: channels per point beyond xyz (1 = height for VoteNet, 0 for GF3D).
+    fp2_out: 256 (VoteNet) or 288 (GroupFree3D)."""
+
+    def __init__(self, input_feature_dim=0, fp2_out=256):
+        super().__init__()
+        self.sa1 = PointnetSAModuleVotes(npoint=2048, radius=0.2, nsample=64,
+                                         mlp=[input_feature_dim, 64, 64, 128],
+                                         use_xyz=True, normalize_xyz=True)
+        self.sa2 = PointnetSAModuleVotes(npoint=1024, radius=0.4, nsample=32,
+                                         mlp=[128, 128, 128, 256],
+                                         use_xyz=True, normalize_xyz=True)
+        self.sa3 = PointnetSAModuleVotes(npoint=512, radius=0.8, nsample=16,
+                                         mlp=[256, 128, 128, 256],
+                                         use_xyz=True, normalize_xyz=True)
+        self.sa4 = PointnetSAModuleVotes(npoint=256, radius=1.2, nsample=16,
+                                         mlp=[256, 128, 128, 256],
+                                         use_xyz=True, normalize_xyz=True)
+        self.fp1 = PointnetFPModule(mlp=[256 + 256, 256, 256])
+        self.fp2 = PointnetFPModule(mlp=[256 + 256, 256, fp2_out])
+
+    def _break_up_pc(self, pc):
+        xyz = pc[..., 0:3].contiguous()
+        features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
+        return xyz, features
+
+    def forward(self, pointcloud: torch.Tensor, end_points=None):
+        """pointcloud (B,N,3+input_feature_dim) -> end_points dict (sa{1..4}_xyz/features,
+        sa1_inds, sa2_inds, fp2_features, fp2_xyz, fp2_inds)."""
+        if not end_points:
+            end_points = {}
+        xyz, features = self._break_up_pc(pointcloud)
+
+        xyz, features, fps_inds = self.sa1(xyz, features)
+        end_points['sa1_inds'] = fps_inds
+        end_points['sa1_xyz'] = xyz
+        end_points['sa1_features'] = features
+
+        xyz, features, fps_inds = self.sa2(xyz, features)
+        end_points['sa2_inds'] = fps_inds
+        end_points['sa2_xyz'] = xyz
+        end_points['sa2_features'] = features
+
+        xyz, features, fps_inds = self.sa3(xyz, features)
+        end_points['sa3_xyz'] = xyz
+        end_points['sa3_features'] = features
+
+        xyz, features, fps_inds = self.sa4(xyz, features)
+        end_points['sa4_xyz'] = xyz
+        end_points['sa4_features'] = features
+
+        features = self.fp1(end_points['sa3_xyz'], end_points['sa4_xyz'],
+                            end_points['sa3_features'], end_points['sa4_features'])
+        features = self.fp2(end_points['sa2_xyz'], end_points['sa3_xyz'],
+                            end_points['sa2_features'], features)
+        end_points['fp2_features'] = features
+        end_points['fp2_xyz'] = end_points['sa2_xyz']
+        num_seed = end_points['fp2_xyz'].shape[1]
+        end_points['fp2_inds'] = end_points['sa1_inds'][:, 0:num_seed]
+        return end_points

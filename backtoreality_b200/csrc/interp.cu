@@ -1,0 +1,195 @@
+// interp.cu -- three_nn and three_interpolate forward/backward (sm_100a).
+//
+// Replaces three_nn_kernel / three_interpolate(_grad)_kernel (reference
+// _ext_src/src/interpolate_gpu.cu:14-64, 77-106, 121-148), which run B CTAs in total.
+//
+// three_nn: one thread per unknown point; the CTA stages the known points in shared memory as
+// structure-of-arrays and every thread walks them with broadcast 128-bit shared loads (4 known
+// points per step).  Bit-exact: d = fma(dz,dz, fma(dx,dx, dy*dy)), d* = unknown - known, top-3
+// kept with strict '<' in ascending index order (earlier index wins ties).  The reference holds
+// its running best in double initialised to 1e40 and stores (float)1e40 = +inf when fewer than
+// three candidates exist; float +inf as the initial value gives the identical result because a
+// float d (finite or +inf) is < 1e40 exactly when it is < +inf.
+//
+// three_interpolate: HBM-bound mover.  grid over (points, channel chunks, scenes), index and
+// weight triplets loaded once per thread and reused over the channel chunk, coalesced stores.
+#include "common.cuh"
+
+namespace b2r {
+namespace {
+
+constexpr int kNnThreads = 128;
+constexpr int kNnTile = 1024;  // known points per shared-memory tile
+
+__global__ void __launch_bounds__(kNnThreads)
+    three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ known, int n,
+                    int m, float *__restrict__ dist2, int *__restrict__ idx) {
+  __shared__ __align__(16) float s_k[3][kNnTile];
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * kNnThreads + threadIdx.x;
+  const bool active = j < n;
+  known += (size_t)b * m * 3;
+
+  float ux = 0.f, uy = 0.f, uz = 0.f;
+  if (active) {
+    const float *u = unknown + ((size_t)b * n + j) * 3;
+    ux = u[0]; uy = u[1]; uz = u[2];
+  }
+  const float inf = __int_as_float(0x7f800000);
+  float b1 = inf, b2 = inf, b3 = inf;
+  int i1 = 0, i2 = 0, i3 = 0;
+
+  for (int base = 0; base < m; base += kNnTile) {
+    const int tile_m = min(kNnTile, m - base);
+    __syncthreads();
+    for (int e = threadIdx.x; e < tile_m * 3; e += kNnThreads) {
+      const int p = e / 3, c = e - p * 3;
+      s_k[c][p] = known[(size_t)base * 3 + e];
+    }
+    if (tile_m & 3) {  // pad to a multiple of 4 with NaN: never '<' anything
+      const int padded = (tile_m + 3) & ~3;
+      if (threadIdx.x < (padded - tile_m) * 3)
+        s_k[threadIdx.x % 3][tile_m + threadIdx.x / 3] = __int_as_float(0x7fc00000);
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int off = 0; off < tile_m; off += 4) {
+      const float4 X = *reinterpret_cast<const float4 *>(&s_k[0][off]);
+      const float4 Y = *reinterpret_cast<const float4 *>(&s_k[1][off]);
+      const float4 Z = *reinterpret_cast<const float4 *>(&s_k[2][off]);
+      const float xs[4] = {X.x, X.y, X.z, X.w};
+      const float ys[4] = {Y.x, Y.y, Y.z, Y.w};
+      const float zs[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float d = sumsq_ref(__fsub_rn(ux, xs[v]), __fsub_rn(uy, ys[v]), __fsub_rn(uz, zs[v]));
+        if (d < b3) {  // b1 <= b2 <= b3, so this is the reference's if / else-if chain
+          const int k = base + off + v;
+          if (d < b2) {
+            b3 = b2; i3 = i2;
+            if (d < b1) {
+              b2 = b1; i2 = i1;
+              b1 = d;  i1 = k;
+            } else {
+              b2 = d;  i2 = k;
+            }
+          } else {
+            b3 = d; i3 = k;
+          }
+        }
+      }
+    }
+  }
+  if (active) {
+    float *od = dist2 + ((size_t)b * n + j) * 3;
+    int *oi = idx + ((size_t)b * n + j) * 3;
+    od[0] = b1; od[1] = b2; od[2] = b3;
+    oi[0] = i1; oi[1] = i2; oi[2] = i3;
+  }
+}
+
+constexpr int kIpThreads = 128;
+
+// out[b,c,j] = fma(p3,w3, fma(p1,w1, p2*w2))
+__global__ void __launch_bounds__(kIpThreads)
+    interp_fwd_kernel(const float *__restrict__ f, const int *__restrict__ idx,
+                      const float *__restrict__ w, int C, int m, int n, int cpb,
+                      float *__restrict__ out) {
+  const int j = blockIdx.x * kIpThreads + threadIdx.x;
+  if (j >= n) return;
+  const int b = blockIdx.z;
+  const int *ip = idx + ((size_t)b * n + j) * 3;
+  const float *wp = w + ((size_t)b * n + j) * 3;
+  const int a1 = ip[0], a2 = ip[1], a3 = ip[2];
+  const float w1 = wp[0], w2 = wp[1], w3 = wp[2];
+  const int c0 = blockIdx.y * cpb, c1 = min(C, c0 + cpb);
+  const float *src = f + ((size_t)b * C + c0) * m;
+  float *dst = out + ((size_t)b * C + c0) * n + j;
+#pragma unroll 4
+  for (int c = c0; c < c1; ++c, src += m, dst += n) {
+    const float p1 = __ldg(src + a1), p2 = __ldg(src + a2), p3 = __ldg(src + a3);
+    *dst = __fmaf_rn(p3, w3, __fmaf_rn(p1, w1, __fmul_rn(p2, w2)));
+  }
+}
+
+__global__ void __launch_bounds__(kIpThreads)
+    interp_bwd_kernel(const float *__restrict__ g, const int *__restrict__ idx,
+                      const float *__restrict__ w, int C, int n, int m, int cpb,
+                      float *__restrict__ gf) {
+  const int j = blockIdx.x * kIpThreads + threadIdx.x;
+  if (j >= n) return;
+  const int b = blockIdx.z;
+  const int *ip = idx + ((size_t)b * n + j) * 3;
+  const float *wp = w + ((size_t)b * n + j) * 3;
+  const int a1 = ip[0], a2 = ip[1], a3 = ip[2];
+  const float w1 = wp[0], w2 = wp[1], w3 = wp[2];
+  const int c0 = blockIdx.y * cpb, c1 = min(C, c0 + cpb);
+  const float *src = g + ((size_t)b * C + c0) * n + j;
+  float *dst = gf + ((size_t)b * C + c0) * m;
+#pragma unroll 4
+  for (int c = c0; c < c1; ++c, src += n, dst += m) {
+    const float v = *src;
+    atomicAdd(dst + a1, __fmul_rn(v, w1));
+    atomicAdd(dst + a2, __fmul_rn(v, w2));
+    atomicAdd(dst + a3, __fmul_rn(v, w3));
+  }
+}
+
+int pick_cpb(long long pos_blocks, int C, int B) {
+  int cpb = 16;
+  while (cpb > 1 && pos_blocks * ((C + cpb - 1) / cpb) * B < 4LL * kNumSMs) cpb >>= 1;
+  return cpb;
+}
+
+}  // namespace
+}  // namespace b2r
+
+using namespace b2r;
+
+extern "C" int b2r_three_nn(const float *unknown, const float *known, int B, int n, int m,
+                            float *dist2, int *idx, void *stream) {
+  B2R_REQUIRE(B >= 0 && n >= 0 && m >= 0, "b2r_three_nn: negative size");
+  if (B == 0 || n == 0) return B2R_OK;
+  B2R_REQUIRE(unknown && dist2 && idx && (known || m == 0), "b2r_three_nn: null pointer");
+  B2R_REQUIRE(B <= 65535, "b2r_three_nn: B too large");
+  dim3 grid(ceil_div(n, kNnThreads), B, 1);
+  three_nn_kernel<<<grid, kNnThreads, 0, static_cast<cudaStream_t>(stream)>>>(unknown, known, n, m,
+                                                                              dist2, idx);
+  B2R_CHECK_LAUNCH();
+  return B2R_OK;
+}
+
+extern "C" int b2r_three_interp_fwd(const float *features, const int *idx, const float *weight,
+                                    int B, int C, int m, int n, float *out, void *stream) {
+  B2R_REQUIRE(B >= 0 && C >= 0 && m >= 0 && n >= 0, "b2r_three_interp_fwd: negative size");
+  if (B == 0 || C == 0 || n == 0) return B2R_OK;
+  B2R_REQUIRE(features && idx && weight && out, "b2r_three_interp_fwd: null pointer");
+  B2R_REQUIRE(B <= 65535, "b2r_three_interp_fwd: B too large");
+  const int xb = ceil_div(n, kIpThreads);
+  const int cpb = pick_cpb(xb, C, B);
+  dim3 grid(xb, ceil_div(C, cpb), B);
+  interp_fwd_kernel<<<grid, kIpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      features, idx, weight, C, m, n, cpb, out);
+  B2R_CHECK_LAUNCH();
+  return B2R_OK;
+}
+
+extern "C" int b2r_three_interp_bwd(const float *grad_out, const int *idx, const float *weight,
+                                    int B, int C, int n, int m, float *grad_features,
+                                    void *stream) {
+  B2R_REQUIRE(B >= 0 && C >= 0 && m >= 0 && n >= 0, "b2r_three_interp_bwd: negative size");
+  if (B == 0 || C == 0 || m == 0) return B2R_OK;
+  B2R_REQUIRE(grad_features, "b2r_three_interp_bwd: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  B2R_CUDA(cudaMemsetAsync(grad_features, 0, sizeof(float) * (size_t)B * C * m, st));
+  if (n == 0) return B2R_OK;
+  B2R_REQUIRE(grad_out && idx && weight, "b2r_three_interp_bwd: null pointer");
+  B2R_REQUIRE(B <= 65535, "b2r_three_interp_bwd: B too large");
+  const int xb = ceil_div(n, kIpThreads);
+  const int cpb = pick_cpb(xb, C, B);
+  dim3 grid(xb, ceil_div(C, cpb), B);
+  interp_bwd_kernel<<<grid, kIpThreads, 0, st>>>(grad_out, idx, weight, C, n, m, cpb,
+                                                 grad_features);
+  B2R_CHECK_LAUNCH();
+  return B2R_OK;
+}

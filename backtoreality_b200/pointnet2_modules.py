@@ -1,0 +1,133 @@
+"""PointNet++ set-abstraction / feature-propagation modules on the B200-native ops.
+
+Mirrors the call surface of /root/reference/detection/Votenet/pointnet2/pointnet2_modules.py that
+the detectors instantiate:
+
+    PointnetSAModuleVotes    (:164-272)   used by Pointnet2Backbone and ProposalModule
+    PointnetFPModule         (:454-514)   used by Pointnet2Backbone
+    PointnetSAModuleCenters  (:357-451)   used by the CenterRefine backbones
+
+Constructor keyword arguments, forward signatures, return tuples, sub-module names
+(`grouper`, `mlp_module`, `mlp`) and therefore state-dict keys are the reference's.  The
+reference's quirk of mutating the caller's `mlp` list (`mlp_spec[0] += 3`, :204-206) is kept.
+MSG / LFP / Rlt variants are never instantiated by any training script and are not carried
+(SURVEY.md 2a row 3).
+"""
+from typing import List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import pointnet2_utils
+from . import pytorch_utils as pt_utils
+
+
+def _pool(new_features, grouped_xyz, pooling, sigma, nsample):
+    """(B,C,npoint,nsample) -> (B,C,npoint): the reference's three pooling modes (:254-267)."""
+    if pooling == 'max':
+        new_features = F.max_pool2d(new_features, kernel_size=[1, new_features.size(3)])
+    elif pooling == 'avg':
+        new_features = F.avg_pool2d(new_features, kernel_size=[1, new_features.size(3)])
+    elif pooling == 'rbf':
+        rbf = torch.exp(-1 * grouped_xyz.pow(2).sum(1, keepdim=False) / (sigma ** 2) / 2)
+        new_features = torch.sum(new_features * rbf.unsqueeze(1), -1, keepdim=True) / float(nsample)
+    return new_features.squeeze(-1)
+
+
+class _SAVotesBase(nn.Module):
+    def __init__(self, *, mlp: List[int], npoint: int = None, radius: float = None,
+                 nsample: int = None, bn: bool = True, use_xyz: bool = True,
+                 pooling: str = 'max', sigma: float = None, normalize_xyz: bool = False,
+                 sample_uniformly: bool = False, ret_unique_cnt: bool = False):
+        super().__init__()
+        self.npoint = npoint
+        self.radius = radius
+        self.nsample = nsample
+        self.pooling = pooling
+        self.mlp_module = None
+        self.use_xyz = use_xyz
+        self.sigma = sigma
+        if self.sigma is None:
+            self.sigma = self.radius / 2
+        self.normalize_xyz = normalize_xyz
+        self.ret_unique_cnt = ret_unique_cnt
+
+        if npoint is not None:
+            self.grouper = pointnet2_utils.QueryAndGroup(
+                radius, nsample, use_xyz=use_xyz, ret_grouped_xyz=True,
+                normalize_xyz=normalize_xyz, sample_uniformly=sample_uniformly,
+                ret_unique_cnt=ret_unique_cnt)
+        else:
+            self.grouper = pointnet2_utils.GroupAll(use_xyz, ret_grouped_xyz=True)
+
+        mlp_spec = mlp
+        if use_xyz and len(mlp_spec) > 0:
+            mlp_spec[0] += 3  # mutates the caller's list, exactly like the reference
+        self.mlp_module = pt_utils.SharedMLP(mlp_spec, bn=bn)
+
+    def _abstract(self, xyz, new_xyz, features):
+        grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features)
+        new_features = self.mlp_module(grouped_features)  # (B, mlp[-1], npoint, nsample)
+        return _pool(new_features, grouped_xyz, self.pooling, self.sigma, self.nsample)
+
+
+class PointnetSAModuleVotes(_SAVotesBase):
+    """Set abstraction that also returns the sampled indices (reference :164-272).
+
+    forward(xyz (B,N,3), features (B,C,N) | None, inds (B,npoint) int32 | None)
+        -> new_xyz (B,npoint,3), new_features (B,mlp[-1],npoint), inds (B,npoint)
+    """
+
+    def forward(self, xyz: torch.Tensor, features: torch.Tensor = None,
+                inds: torch.Tensor = None):
+        xyz_flipped = xyz.transpose(1, 2).contiguous()
+        if inds is None:
+            inds = pointnet2_utils.furthest_point_sample(xyz, self.npoint)
+        else:
+            assert (inds.shape[1] == self.npoint)
+        new_xyz = pointnet2_utils.gather_operation(
+            xyz_flipped, inds
+        ).transpose(1, 2).contiguous() if self.npoint is not None else None
+        new_features = self._abstract(xyz, new_xyz, features)
+        return new_xyz, new_features, inds
+
+
+class PointnetSAModuleCenters(_SAVotesBase):
+    """Set abstraction around externally supplied centres (reference :357-451).
+
+    forward(xyz (B,N,3), features (B,C,N), centers (B,npoint,3)) -> new_features (B,mlp[-1],npoint)
+    """
+
+    def forward(self, xyz: torch.Tensor, features: torch.Tensor, centers: torch.Tensor):
+        return self._abstract(xyz, centers, features)
+
+
+class PointnetFPModule(nn.Module):
+    """Feature propagation: inverse-distance 3-NN interpolation + SharedMLP (reference :454-514).
+
+    forward(unknown (B,n,3), known (B,m,3), unknow_feats (B,C1,n), known_feats (B,C2,m))
+        -> (B, mlp[-1], n)
+    """
+
+    def __init__(self, *, mlp: List[int], bn: bool = True):
+        super().__init__()
+        self.mlp = pt_utils.SharedMLP(mlp, bn=bn)
+
+    def forward(self, unknown, known, unknow_feats, known_feats):
+        if known is not None:
+            dist, idx = pointnet2_utils.three_nn(unknown, known)
+            dist_recip = 1.0 / (dist + 1e-8)
+            norm = torch.sum(dist_recip, dim=2, keepdim=True)
+            weight = dist_recip / norm
+            interpolated_feats = pointnet2_utils.three_interpolate(known_feats, idx, weight)
+        else:
+            interpolated_feats = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
+
+        if unknow_feats is not None:
+            new_features = torch.cat([interpolated_feats, unknow_feats], dim=1)
+        else:
+            new_features = interpolated_feats
+
+        new_features = self.mlp(new_features.unsqueeze(-1))
+        return new_features.squeeze(-1)

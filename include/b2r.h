@@ -1,0 +1,152 @@
+/*
+ * b2r.h -- C ABI of libb2r.so: the B200-native (sm_100a) PointNet++ set-abstraction ops.
+ *
+ * This is the drop-in boundary for the reference's pybind module `pointnet2._ext`
+ * (/root/reference/detection/Votenet/pointnet2/_ext_src/src/bindings.cpp:11-24).  Every entry
+ * point below replaces one `at::Tensor`-level function of that module; the file:line it
+ * replaces is cited on each declaration (paths relative to .../pointnet2/_ext_src/).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  All data pointers are DEVICE pointers on the
+ *     current CUDA device, contiguous, float32 / int32 -- exactly what the reference's
+ *     CHECK_CONTIGUOUS / CHECK_IS_FLOAT / CHECK_IS_INT macros (include/utils.h:10-30) demand.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Launches are
+ *     asynchronous on that stream, no host synchronisation, re-entrant, no global state
+ *     (the reference launches on at::cuda::getCurrentCUDAStream(), e.g. sampling_gpu.cu:30-31).
+ *   - Outputs are fully written by the callee (including the zero fill the reference gets from
+ *     torch::zeros, e.g. ball_query.cpp:24-26, sampling.cpp:57-59): callers may pass
+ *     uninitialised memory.
+ *   - Return value: B2R_OK (0) or a negative b2r_status.  Never exit()s -- unlike the
+ *     reference's CUDA_CHECK_ERRORS (include/cuda_utils.h:35-44).  b2r_last_error() gives a
+ *     thread-local human-readable detail string for the last failing call.
+ *   - 64-bit offset arithmetic throughout (the reference uses 32-bit int offsets,
+ *     group_points_gpu.cu:19-21); every single dimension must still fit in int32.
+ */
+#ifndef B2R_H_
+#define B2R_H_
+
+#if defined(__GNUC__)
+#define B2R_API __attribute__((visibility("default")))
+#else
+#define B2R_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum b2r_status {
+  B2R_OK = 0,
+  B2R_ERR_INVALID_ARG = -1, /* null pointer, negative size, misaligned buffer */
+  B2R_ERR_CUDA = -2,        /* a CUDA runtime call / kernel launch failed */
+  B2R_ERR_UNSUPPORTED = -3  /* size outside what the kernels support */
+} b2r_status;
+
+/* library version (major*10000 + minor*100 + patch) and error helpers */
+B2R_API int b2r_version(void);
+B2R_API const char *b2r_status_string(int status);
+B2R_API const char *b2r_last_error(void);
+
+/* The reference's power-of-two thread-count rule (include/cuda_utils.h:20-24).  Exposed because
+ * it fixes the FPS tie order (see b2r_fps) and callers/tests may want to inspect it. */
+B2R_API int b2r_ref_block_threads(int work_size);
+
+/* ------------------------------------------------------------------------------------------
+ * furthest_point_sampling(points, nsamples)            src/sampling.cpp:70-91,
+ *                                                       kernel src/sampling_gpu.cu:74-178
+ * xyz (B,N,3) f32  ->  idx (B,npoint) i32.  idx[b,0] = 0; bit-exact with the reference,
+ * including the |p|^2 <= 1e-3 exclusion (sampling_gpu.cu:105-106) and the winner among exactly
+ * equal distances (which in the reference is decided by its 512-lane strided scan + shared-memory
+ * tree, sampling_gpu.cu:64-70,113-173).  No global scratch is needed: the running min-distances
+ * live in registers across a thread-block cluster.
+ */
+B2R_API int b2r_fps(const float *xyz, int B, int N, int npoint, int *idx, void *stream);
+
+/* Launch geometry b2r_fps would use for (B,N): cluster size, threads per CTA, points per thread
+ * and dynamic shared memory bytes.  Any out pointer may be NULL. */
+B2R_API int b2r_fps_plan(int B, int N, int *cluster_size, int *threads, int *points_per_thread,
+                 int *smem_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * gather_points(points, idx)                            src/sampling.cpp:20-43,
+ *                                                       kernel src/sampling_gpu.cu:13-25
+ * features (B,C,N) f32, idx (B,M) i32  ->  out (B,C,M):  out[b,c,j] = features[b,c,idx[b,j]]
+ */
+B2R_API int b2r_gather_fwd(const float *features, const int *idx, int B, int C, int N, int M, float *out,
+                   void *stream);
+
+/* gather_points_grad(grad_out, idx, n)                  src/sampling.cpp:45-69,
+ *                                                       kernel src/sampling_gpu.cu:39-52
+ * grad_out (B,C,M), idx (B,M)  ->  grad_features (B,C,N) = scatter-add into zeros */
+B2R_API int b2r_gather_bwd(const float *grad_out, const int *idx, int B, int C, int N, int M,
+                   float *grad_features, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ball_query(new_xyz, xyz, radius, nsample)             src/ball_query.cpp:13-37,
+ *                                                       kernel src/ball_query_gpu.cu:14-49
+ * new_xyz (B,M,3), xyz (B,N,3)  ->  idx (B,M,nsample) i32: the first `nsample` point indices k
+ * (ascending) with fma(dz,dz,fma(dx,dx,dy*dy)) < radius*radius; slots past the count repeat the
+ * first hit; an empty ball yields zeros.  Bit-exact with the reference.
+ */
+B2R_API int b2r_ball_query(const float *new_xyz, const float *xyz, int B, int N, int M, float radius,
+                   int nsample, int *idx, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * group_points(points, idx)                             src/group_points.cpp:17-40,
+ *                                                       kernel src/group_points_gpu.cu:13-33
+ * features (B,C,N), idx (B,NP,NS)  ->  out (B,C,NP,NS)
+ */
+B2R_API int b2r_group_fwd(const float *features, const int *idx, int B, int C, int N, int NP, int NS,
+                  float *out, void *stream);
+
+/* group_points_grad(grad_out, idx, n)                   src/group_points.cpp:42-65,
+ *                                                       kernel src/group_points_gpu.cu:48-69
+ * grad_out (B,C,NP,NS), idx (B,NP,NS)  ->  grad_features (B,C,N) */
+B2R_API int b2r_group_bwd(const float *grad_out, const int *idx, int B, int C, int N, int NP, int NS,
+                  float *grad_features, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * three_nn(unknowns, knows)                             src/interpolate.cpp:19-45,
+ *                                                       kernel src/interpolate_gpu.cu:14-64
+ * unknown (B,n,3), known (B,m,3)  ->  dist2 (B,n,3) f32 (SQUARED distances, ascending),
+ * idx (B,n,3) i32.  Strict '<' insertion: the earlier index wins ties.  m<3 leaves +inf / 0.
+ */
+B2R_API int b2r_three_nn(const float *unknown, const float *known, int B, int n, int m, float *dist2,
+                 int *idx, void *stream);
+
+/* three_interpolate(points, idx, weight)                src/interpolate.cpp:47-75,
+ *                                                       kernel src/interpolate_gpu.cu:77-106
+ * features (B,C,m), idx (B,n,3), weight (B,n,3)  ->  out (B,C,n) */
+B2R_API int b2r_three_interp_fwd(const float *features, const int *idx, const float *weight, int B, int C,
+                         int m, int n, float *out, void *stream);
+
+/* three_interpolate_grad(grad_out, idx, weight, m)      src/interpolate.cpp:76-104,
+ *                                                       kernel src/interpolate_gpu.cu:121-148
+ * grad_out (B,C,n)  ->  grad_features (B,C,m) */
+B2R_API int b2r_three_interp_bwd(const float *grad_out, const int *idx, const float *weight, int B, int C,
+                         int n, int m, float *grad_features, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused QueryAndGroup tail (reference Python: pointnet2_utils.py:347-366, i.e. two
+ * grouping_operation calls + in-place `-= new_xyz` + `/= radius` + torch.cat, five HBM passes)
+ * in ONE pass:
+ *   out[b, 0:3,  j, s] = (xyz[b, idx[b,j,s], :] - new_xyz[b, j, :]) (/ radius if normalize)
+ *   out[b, 3:3+C,j, s] = features[b, :, idx[b,j,s]]            (C may be 0, features NULL)
+ * xyz (B,N,3), new_xyz (B,NP,3), features (B,C,N) or NULL, idx (B,NP,NS) -> out (B,3+C,NP,NS).
+ * The division is a true IEEE division by `radius` as in the reference.
+ */
+B2R_API int b2r_query_group_fwd(const float *xyz, const float *new_xyz, const float *features,
+                        const int *idx, int B, int C, int N, int NP, int NS, float radius,
+                        int normalize_xyz, float *out, void *stream);
+
+/* Backward of the above.  grad_out (B,3+C,NP,NS).  Any of the three outputs may be NULL
+ * (= that input needs no gradient).  grad_xyz (B,N,3), grad_new_xyz (B,NP,3),
+ * grad_features (B,C,N); all fully written (zero-filled then accumulated). */
+B2R_API int b2r_query_group_bwd(const float *grad_out, const int *idx, int B, int C, int N, int NP, int NS,
+                        float radius, int normalize_xyz, float *grad_xyz, float *grad_new_xyz,
+                        float *grad_features, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2R_H_ */

@@ -1,0 +1,77 @@
+"""Import the reference's UNMODIFIED Python stack on CPU, over the oracle `_ext` facade.
+
+TEST INFRASTRUCTURE ONLY, and BUILD-CONTAINER ONLY: /root/reference does not exist on the
+GPU box, so nothing in the `-m gpu` tests, smoke() or bench.py may call this.  It is used by
+tests/golden/make_golden.py (fixture generation) and by `-m "not gpu"` tests that skip when the
+reference tree is absent.
+
+The reference does `import pointnet2._ext as _ext` (pointnet2_utils.py:25-33) and bare
+`import pointnet2_utils`, `import pytorch_utils` (pointnet2_modules.py:16-22), so we inject a
+synthetic `pointnet2` package whose `_ext` attribute is oracle.fake_ext, and load the reference
+files under private module names (so they never shadow this repo's own modules).
+"""
+import importlib.util
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("B2R_REFERENCE_ROOT", "/root/reference")
+_V = os.path.join(REF_ROOT, "detection", "Votenet")
+_G = os.path.join(REF_ROOT, "detection", "GroupFree3D")
+
+
+def available():
+    return os.path.isfile(os.path.join(_V, "pointnet2", "pointnet2_utils.py"))
+
+
+def _load(name, path, aliases=()):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    for a in aliases:
+        sys.modules[a] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class RefStack:
+    """Holds the reference modules for one flavour ('votenet' or 'groupfree3d')."""
+
+    def __init__(self, flavour="votenet"):
+        from . import fake_ext
+
+        if not available():
+            raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+        root = _V if flavour == "votenet" else _G
+        saved = {k: sys.modules.get(k) for k in
+                 ("pointnet2", "pointnet2._ext", "pointnet2_utils", "pytorch_utils",
+                  "pointnet2_modules")}
+        saved_path = list(sys.path)
+        try:
+            pkg = types.ModuleType("pointnet2")
+            pkg.__path__ = []
+            pkg._ext = fake_ext
+            sys.modules["pointnet2"] = pkg
+            sys.modules["pointnet2._ext"] = fake_ext
+            tag = "_b2r_ref_%s_" % flavour
+            self.pytorch_utils = _load(tag + "pytorch_utils",
+                                       os.path.join(root, "pointnet2", "pytorch_utils.py"),
+                                       aliases=("pytorch_utils",))
+            self.pointnet2_utils = _load(tag + "pointnet2_utils",
+                                         os.path.join(root, "pointnet2", "pointnet2_utils.py"),
+                                         aliases=("pointnet2_utils",))
+            self.pointnet2_modules = _load(tag + "pointnet2_modules",
+                                           os.path.join(root, "pointnet2", "pointnet2_modules.py"),
+                                           aliases=("pointnet2_modules",))
+            self.backbone_module = _load(tag + "backbone_module",
+                                         os.path.join(root, "models", "backbone_module.py"))
+            if flavour == "votenet":
+                self.voting_module = _load(tag + "voting_module",
+                                           os.path.join(root, "models", "voting_module.py"))
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    sys.modules.pop(k, None)
+                else:
+                    sys.modules[k] = v
+            sys.path[:] = saved_path
