@@ -21,6 +21,33 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- instrumentation used by bench.py (never changes what runs) ------------------------------
+LAUNCHES = 0   # number of libb2r kernel launches issued through this module
+TIMED = {}     # op name -> list of (start_event, stop_event); filled only for names in TIME_OPS
+TIME_OPS = set()
+
+
+class _timed:
+    """Counts the launch and, for ops listed in TIME_OPS, brackets it with CUDA events recorded
+    on the launching (current) stream."""
+
+    def __init__(self, name):
+        self.name = name
+        self.ev = None
+
+    def __enter__(self):
+        global LAUNCHES
+        LAUNCHES += 1
+        if self.name in TIME_OPS:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+
+    def __exit__(self, *a):
+        if self.ev is not None:
+            self.ev[1].record()
+            TIMED.setdefault(self.name, []).append(self.ev)
+
+
 def _chk_contig(t, name):
     if not t.is_contiguous():
         raise RuntimeError("%s must be a contiguous tensor" % name)
@@ -72,7 +99,7 @@ def furthest_point_sampling(points, nsamples):
     _chk_cuda(points, [])
     B, N = points.size(0), points.size(1)
     out = torch.empty((B, nsamples), dtype=torch.int32, device=points.device)
-    with _on_device(points):
+    with _on_device(points), _timed("furthest_point_sampling"):
         _lib.check(_lib.lib().b2r_fps(points.data_ptr(), B, N, int(nsamples), out.data_ptr(),
                                       _stream()), "furthest_point_sampling")
     return out
@@ -88,7 +115,7 @@ def gather_points(points, idx):
     B, C, N = points.shape
     M = idx.size(1)
     out = torch.empty((B, C, M), dtype=torch.float32, device=points.device)
-    with _on_device(points):
+    with _on_device(points), _timed("gather_points"):
         _lib.check(_lib.lib().b2r_gather_fwd(points.data_ptr(), idx.data_ptr(), B, C, N, M,
                                              out.data_ptr(), _stream()), "gather_points")
     return out
@@ -103,7 +130,7 @@ def gather_points_grad(grad_out, idx, n):
     _chk_cuda(grad_out, [(idx, "idx")])
     B, C, M = grad_out.shape
     out = torch.empty((B, C, int(n)), dtype=torch.float32, device=grad_out.device)
-    with _on_device(grad_out):
+    with _on_device(grad_out), _timed("gather_points_grad"):
         _lib.check(_lib.lib().b2r_gather_bwd(grad_out.data_ptr(), idx.data_ptr(), B, C, int(n), M,
                                              out.data_ptr(), _stream()), "gather_points_grad")
     return out
@@ -119,7 +146,7 @@ def ball_query(new_xyz, xyz, radius, nsample):
     B, M = new_xyz.size(0), new_xyz.size(1)
     N = xyz.size(1)
     out = torch.empty((B, M, int(nsample)), dtype=torch.int32, device=new_xyz.device)
-    with _on_device(new_xyz):
+    with _on_device(new_xyz), _timed("ball_query"):
         _lib.check(_lib.lib().b2r_ball_query(new_xyz.data_ptr(), xyz.data_ptr(), B, N, M,
                                              float(radius), int(nsample), out.data_ptr(),
                                              _stream()), "ball_query")
@@ -136,7 +163,7 @@ def group_points(points, idx):
     B, C, N = points.shape
     NP, NS = idx.size(1), idx.size(2)
     out = torch.empty((B, C, NP, NS), dtype=torch.float32, device=points.device)
-    with _on_device(points):
+    with _on_device(points), _timed("group_points"):
         _lib.check(_lib.lib().b2r_group_fwd(points.data_ptr(), idx.data_ptr(), B, C, N, NP, NS,
                                             out.data_ptr(), _stream()), "group_points")
     return out
@@ -151,7 +178,7 @@ def group_points_grad(grad_out, idx, n):
     _chk_cuda(grad_out, [(idx, "idx")])
     B, C, NP, NS = grad_out.shape
     out = torch.empty((B, C, int(n)), dtype=torch.float32, device=grad_out.device)
-    with _on_device(grad_out):
+    with _on_device(grad_out), _timed("group_points_grad"):
         _lib.check(_lib.lib().b2r_group_bwd(grad_out.data_ptr(), idx.data_ptr(), B, C, int(n), NP,
                                             NS, out.data_ptr(), _stream()), "group_points_grad")
     return out
@@ -168,7 +195,7 @@ def three_nn(unknowns, knows):
     m = knows.size(1)
     dist2 = torch.empty((B, n, 3), dtype=torch.float32, device=unknowns.device)
     idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknowns.device)
-    with _on_device(unknowns):
+    with _on_device(unknowns), _timed("three_nn"):
         _lib.check(_lib.lib().b2r_three_nn(unknowns.data_ptr(), knows.data_ptr(), B, n, m,
                                            dist2.data_ptr(), idx.data_ptr(), _stream()),
                    "three_nn")
@@ -187,7 +214,7 @@ def three_interpolate(points, idx, weight):
     B, C, m = points.shape
     n = idx.size(1)
     out = torch.empty((B, C, n), dtype=torch.float32, device=points.device)
-    with _on_device(points):
+    with _on_device(points), _timed("three_interpolate"):
         _lib.check(_lib.lib().b2r_three_interp_fwd(points.data_ptr(), idx.data_ptr(),
                                                    weight.data_ptr(), B, C, m, n, out.data_ptr(),
                                                    _stream()), "three_interpolate")
@@ -205,7 +232,7 @@ def three_interpolate_grad(grad_out, idx, weight, m):
     _chk_cuda(grad_out, [(idx, "idx"), (weight, "weight")])
     B, C, n = grad_out.shape
     out = torch.empty((B, C, int(m)), dtype=torch.float32, device=grad_out.device)
-    with _on_device(grad_out):
+    with _on_device(grad_out), _timed("three_interpolate_grad"):
         _lib.check(_lib.lib().b2r_three_interp_bwd(grad_out.data_ptr(), idx.data_ptr(),
                                                    weight.data_ptr(), B, C, n, int(m),
                                                    out.data_ptr(), _stream()),
@@ -233,7 +260,7 @@ def query_group(xyz, new_xyz, features, idx, radius, normalize_xyz):
     B, N = xyz.size(0), xyz.size(1)
     NP, NS = idx.size(1), idx.size(2)
     out = torch.empty((B, 3 + C, NP, NS), dtype=torch.float32, device=xyz.device)
-    with _on_device(xyz):
+    with _on_device(xyz), _timed("query_group"):
         _lib.check(_lib.lib().b2r_query_group_fwd(xyz.data_ptr(), new_xyz.data_ptr(), fptr,
                                                   idx.data_ptr(), B, C, N, NP, NS, float(radius),
                                                   1 if normalize_xyz else 0, out.data_ptr(),
@@ -252,7 +279,7 @@ def query_group_grad(grad_out, idx, N, C, radius, normalize_xyz, need_xyz, need_
     gx = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if need_xyz else None
     gn = torch.empty((B, NP, 3), dtype=torch.float32, device=dev) if need_new_xyz else None
     gf = torch.empty((B, C, N), dtype=torch.float32, device=dev) if (need_features and C) else None
-    with _on_device(grad_out):
+    with _on_device(grad_out), _timed("query_group_grad"):
         _lib.check(_lib.lib().b2r_query_group_bwd(
             grad_out.data_ptr(), idx.data_ptr(), B, C, int(N), NP, NS, float(radius),
             1 if normalize_xyz else 0,

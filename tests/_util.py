@@ -1,0 +1,31 @@
+"""Shared helpers for the parity tests."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name)))
+
+
+def weight_checksum(module):
+    return float(sum(p.detach().double().abs().sum().cpu() for p in module.parameters()))
+
+
+def sub(t, n=4096):
+    f = t.detach().reshape(-1)
+    step = max(1, f.numel() // n)
+    return f[::step].cpu().numpy().copy()
+
+
+def rel_l2(got, want):
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    return float(np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-30))
+
+
+def pattern_like(t):
+    return torch.linspace(-1, 1, t.numel(), device="cpu").reshape(t.shape).to(t.device)

@@ -1,0 +1,72 @@
+"""The oracle's module-level port (oracle/cpu_modules.py) against the golden fixtures that were
+generated from the reference's own Python stack (tests/golden/make_golden.py).  No GPU."""
+import numpy as np
+import pytest
+import torch
+
+from _util import golden, pattern_like, rel_l2, sub, weight_checksum
+from backtoreality_b200 import scenes
+from oracle import cpu_modules
+
+TOL = 1e-5  # same torch CPU fp32 kernels, same op order: differences are thread-sum noise only
+
+
+@pytest.mark.parametrize("fixture", ["backbone_votenet_eval.npz", "backbone_votenet_train.npz",
+                                     "backbone_gf3d_train.npz"])
+def test_backbone_port_matches_reference_python(fixture):
+    g = golden(fixture)
+    torch.manual_seed(int(g["seed"]))
+    net = cpu_modules.Backbone(input_feature_dim=int(g["C"]), fp2_out=int(g["fp2_out"]))
+    assert abs(weight_checksum(net) - float(g["wsum"])) < 1e-6 * float(g["wsum"])
+    net.train(bool(g["train"]))
+    pc = torch.from_numpy(scenes.batch(50, int(g["B"]), int(g["N"]), C=int(g["C"]), kind="room",
+                                       dup=0.2))
+    ep = net(pc)
+    assert np.array_equal(ep["sa1_inds"].numpy(), g["sa1_inds"])
+    assert np.array_equal(ep["sa2_inds"].numpy(), g["sa2_inds"])
+    for k in ("sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features"):
+        assert rel_l2(sub(ep[k]), g[k]) < TOL, k
+    (ep["fp2_features"] * pattern_like(ep["fp2_features"])).sum().backward()
+    assert rel_l2(sub(net.sa1.mlp_module.layer0.conv.weight.grad), g["g_sa1_l0"]) < 1e-4
+    assert rel_l2(sub(net.sa2.mlp_module.layer0.conv.weight.grad), g["g_sa2_l0"]) < 1e-4
+    assert rel_l2(sub(net.fp1.mlp.layer0.conv.weight.grad), g["g_fp1_l0"]) < 1e-4
+    if g["train"]:
+        bn = net.sa1.mlp_module.layer0.bn.bn
+        assert rel_l2(bn.running_mean.numpy(), g["rm_sa1_l0"]) < TOL
+        assert rel_l2(bn.running_var.numpy(), g["rv_sa1_l0"]) < TOL
+
+
+def test_vote_aggregation_port():
+    g = golden("vote_aggregation.npz")
+    torch.manual_seed(int(g["seed"]))
+    sa = cpu_modules.SAModuleVotes(npoint=64, radius=0.3, nsample=16, mlp=[32, 32, 32, 32],
+                                   normalize_xyz=True)
+    assert abs(weight_checksum(sa) - float(g["wsum"])) < 1e-6 * float(g["wsum"])
+    gen = torch.Generator().manual_seed(int(g["seed"]) + 1)
+    xyz = (torch.rand(2, 256, 3, generator=gen) * 2.0 + 0.5).requires_grad_(True)
+    feats = torch.randn(2, 32, 256, generator=gen).requires_grad_(True)
+    new_xyz, new_feats, inds = sa(xyz, feats)
+    assert np.array_equal(inds.numpy(), g["inds"])
+    assert np.array_equal(new_xyz.detach().numpy(), g["new_xyz"])
+    assert rel_l2(new_feats.detach().numpy(), g["new_feats"]) < TOL
+    ((new_feats * pattern_like(new_feats)).sum() + (new_xyz * 0.37).sum()).backward()
+    assert rel_l2(xyz.grad.numpy(), g["g_xyz"]) < 1e-4
+    assert rel_l2(sub(feats.grad), g["g_feats"]) < 1e-4
+
+
+def test_fp_module_port():
+    g = golden("fp_module.npz")
+    torch.manual_seed(int(g["seed"]))
+    fp = cpu_modules.FPModule(mlp=[64, 32, 24])
+    assert abs(weight_checksum(fp) - float(g["wsum"])) < 1e-6 * float(g["wsum"])
+    gen = torch.Generator().manual_seed(int(g["seed"]) + 1)
+    unknown = torch.rand(2, 100, 3, generator=gen)
+    known = torch.rand(2, 37, 3, generator=gen)
+    known[:, 5] = known[:, 2]
+    uf = torch.randn(2, 16, 100, generator=gen).requires_grad_(True)
+    kf = torch.randn(2, 48, 37, generator=gen).requires_grad_(True)
+    y = fp(unknown, known, uf, kf)
+    assert rel_l2(y.detach().numpy(), g["y"]) < TOL
+    (y * pattern_like(y)).sum().backward()
+    assert rel_l2(kf.grad.numpy(), g["g_kf"]) < 1e-4
+    assert rel_l2(sub(uf.grad), g["g_uf"]) < 1e-4

@@ -1,0 +1,155 @@
+"""Module / backbone parity on the GPU: the product's drop-in API (pointnet2_utils autograd
+functions, PointnetSAModuleVotes, PointnetFPModule, Pointnet2Backbone) against
+  * the golden fixtures generated from the reference's own Python stack, and
+  * the oracle's CPU port (oracle/cpu_modules.py) at BASELINE.json's full 40k-point size.
+
+Tolerances: indices bit-exact; features / gradients rel-L2 <= 1e-4 with TF32
+disabled (pure fp32 MLP), <= 5e-3 in the default TF32 MLP mode the reference itself runs in.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _util import golden, pattern_like, rel_l2, sub, weight_checksum
+from backtoreality_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+TF32_TOL = 5e-3
+
+
+@pytest.fixture()
+def fp32_mlp():
+    """Run the SharedMLP convs in true fp32 so tolerances can be tight."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("fixture", ["backbone_votenet_eval.npz", "backbone_votenet_train.npz",
+                                     "backbone_gf3d_train.npz"])
+def test_backbone_vs_reference_python_golden(cuda, fp32_mlp, fixture):
+    from backtoreality_b200.backbone_module import Pointnet2Backbone
+    g = golden(fixture)
+    torch.manual_seed(int(g["seed"]))
+    net = Pointnet2Backbone(input_feature_dim=int(g["C"]), fp2_out=int(g["fp2_out"]))
+    assert abs(weight_checksum(net) - float(g["wsum"])) < 1e-6 * float(g["wsum"])
+    net = net.to(cuda).train(bool(g["train"]))
+    pc = torch.from_numpy(scenes.batch(50, int(g["B"]), int(g["N"]), C=int(g["C"]), kind="room",
+                                       dup=0.2)).to(cuda)
+    ep = net(pc)
+    assert np.array_equal(ep["sa1_inds"].cpu().numpy(), g["sa1_inds"])
+    assert np.array_equal(ep["sa2_inds"].cpu().numpy(), g["sa2_inds"])
+    for k in ("sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features"):
+        assert rel_l2(sub(ep[k]), g[k]) < FP32_TOL, k
+    (ep["fp2_features"] * pattern_like(ep["fp2_features"])).sum().backward()
+    assert rel_l2(sub(net.sa1.mlp_module.layer0.conv.weight.grad), g["g_sa1_l0"]) < 1e-3
+    assert rel_l2(sub(net.sa2.mlp_module.layer0.conv.weight.grad), g["g_sa2_l0"]) < 1e-3
+    assert rel_l2(sub(net.sa4.mlp_module.layer2.conv.weight.grad), g["g_sa4_l2"]) < 1e-3
+    assert rel_l2(sub(net.fp1.mlp.layer0.conv.weight.grad), g["g_fp1_l0"]) < 1e-3
+    assert rel_l2(sub(net.fp2.mlp.layer1.bn.bn.weight.grad), g["g_fp2_l1_bn"]) < 1e-3
+    if g["train"]:
+        bn = net.sa1.mlp_module.layer0.bn.bn
+        assert rel_l2(bn.running_mean.cpu().numpy(), g["rm_sa1_l0"]) < FP32_TOL
+        assert rel_l2(bn.running_var.cpu().numpy(), g["rv_sa1_l0"]) < FP32_TOL
+
+
+def test_vote_aggregation_golden_xyz_gradients_and_given_inds(cuda, fp32_mlp):
+    from backtoreality_b200.pointnet2_modules import PointnetSAModuleVotes
+    g = golden("vote_aggregation.npz")
+    torch.manual_seed(int(g["seed"]))
+    mlp = [32, 32, 32, 32]
+    sa = PointnetSAModuleVotes(npoint=64, radius=0.3, nsample=16, mlp=mlp, use_xyz=True,
+                               normalize_xyz=True)
+    assert mlp[0] == 35  # the reference mutates the caller's list (pointnet2_modules.py:204-206)
+    assert abs(weight_checksum(sa) - float(g["wsum"])) < 1e-6 * float(g["wsum"])
+    sa = sa.to(cuda)
+    gen = torch.Generator().manual_seed(int(g["seed"]) + 1)
+    xyz = (torch.rand(2, 256, 3, generator=gen) * 2.0 + 0.5).to(cuda).requires_grad_(True)
+    feats = torch.randn(2, 32, 256, generator=gen).to(cuda).requires_grad_(True)
+    new_xyz, new_feats, inds = sa(xyz, feats)
+    assert np.array_equal(inds.cpu().numpy(), g["inds"])
+    assert np.array_equal(new_xyz.detach().cpu().numpy(), g["new_xyz"])
+    assert rel_l2(new_feats.detach().cpu().numpy(), g["new_feats"]) < FP32_TOL
+    ((new_feats * pattern_like(new_feats)).sum() + (new_xyz * 0.37).sum()).backward()
+    assert rel_l2(xyz.grad.cpu().numpy(), g["g_xyz"]) < 1e-3
+    assert rel_l2(sub(feats.grad), g["g_feats"]) < 1e-3
+    # explicit inds + features=None (GroupFree3D SA1 style, proposal_module.py:97-100)
+    torch.manual_seed(int(g["seed"]))
+    sa2 = PointnetSAModuleVotes(npoint=64, radius=0.4, nsample=8, mlp=[0, 16, 16], use_xyz=True,
+                                normalize_xyz=True)
+    assert abs(weight_checksum(sa2) - float(g["wsum2"])) < 1e-6 * float(g["wsum2"])
+    sa2 = sa2.to(cuda)
+    given = torch.from_numpy(g["given"]).to(cuda)
+    nx, nf, gi = sa2(xyz.detach(), None, given)
+    assert torch.equal(gi, given)
+    assert np.array_equal(nx.cpu().numpy(), g["nx2"])
+    assert rel_l2(nf.detach().cpu().numpy(), g["nf2"]) < FP32_TOL
+
+
+def test_fp_module_golden(cuda, fp32_mlp):
+    from backtoreality_b200.pointnet2_modules import PointnetFPModule
+    g = golden("fp_module.npz")
+    torch.manual_seed(int(g["seed"]))
+    fp = PointnetFPModule(mlp=[48 + 16, 32, 24])
+    assert abs(weight_checksum(fp) - float(g["wsum"])) < 1e-6 * float(g["wsum"])
+    fp = fp.to(cuda)
+    gen = torch.Generator().manual_seed(int(g["seed"]) + 1)
+    unknown = torch.rand(2, 100, 3, generator=gen)
+    known = torch.rand(2, 37, 3, generator=gen)
+    known[:, 5] = known[:, 2]
+    uf = torch.randn(2, 16, 100, generator=gen).to(cuda).requires_grad_(True)
+    kf = torch.randn(2, 48, 37, generator=gen).to(cuda).requires_grad_(True)
+    y = fp(unknown.to(cuda), known.to(cuda), uf, kf)
+    assert rel_l2(y.detach().cpu().numpy(), g["y"]) < FP32_TOL
+    (y * pattern_like(y)).sum().backward()
+    assert rel_l2(kf.grad.cpu().numpy(), g["g_kf"]) < 1e-3
+    assert rel_l2(sub(uf.grad), g["g_uf"]) < 1e-3
+
+
+def test_reference_gradcheck_of_three_interpolate(cuda):
+    """The reference's only test (pointnet2_test.py:18-30), against the product op."""
+    from backtoreality_b200 import pointnet2_utils
+    feats = torch.randn(1, 2, 4, requires_grad=True).float().cuda()
+
+    def interpolate_func(inputs):
+        idx = torch.from_numpy(np.array([[[0, 1, 2], [1, 2, 3]]])).int().cuda()
+        weight = torch.from_numpy(np.array([[[1, 1, 1], [2, 2, 2]]])).float().cuda()
+        return pointnet2_utils.three_interpolate(inputs, idx, weight)
+
+    assert torch.autograd.gradcheck(interpolate_func, feats, atol=1e-1, rtol=1e-1)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_backbone_full_size_40k_vs_oracle_port(cuda, mode):
+    """BASELINE.json config: 40k-point ScanNet-shaped scenes, train-mode BN, fwd + bwd."""
+    from backtoreality_b200.backbone_module import Pointnet2Backbone
+    from oracle import cpu_modules
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = (mode == "tf32")
+    tol = FP32_TOL if mode == "fp32" else TF32_TOL
+    try:
+        torch.manual_seed(3)
+        port = cpu_modules.Backbone(input_feature_dim=1).train()
+        net = Pointnet2Backbone(input_feature_dim=1)
+        net.load_state_dict(port.state_dict())
+        net = net.to(cuda).train()
+        pc = torch.from_numpy(scenes.batch(20, 2, 40000, C=1, kind="room", dup=0.2))
+        want = port(pc)
+        got = net(pc.to(cuda))
+        for k in ("sa1_inds", "sa2_inds", "fp2_inds"):
+            assert torch.equal(got[k].cpu(), want[k]), k
+        for k in ("sa1_xyz", "sa2_xyz", "sa3_xyz", "sa4_xyz"):
+            assert torch.equal(got[k].cpu(), want[k]), k
+        for k in ("sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features"):
+            assert rel_l2(got[k].detach().cpu().numpy(), want[k].detach().numpy()) < tol, k
+        (want["fp2_features"] * pattern_like(want["fp2_features"])).sum().backward()
+        (got["fp2_features"] * pattern_like(got["fp2_features"])).sum().backward()
+        for (n1, p1), (n2, p2) in zip(port.named_parameters(), net.named_parameters()):
+            assert n1 == n2
+            assert rel_l2(p2.grad.cpu().numpy(), p1.grad.numpy()) < 20 * tol, n1
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old

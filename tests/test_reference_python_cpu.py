@@ -1,0 +1,64 @@
+"""Checks that need the reference tree (/root/reference): skipped on the GPU box.
+
+* the reference's ONLY test, pointnet2_test.py:18-30 (gradcheck of three_interpolate), run
+  verbatim in spirit on CPU over the oracle `_ext` (double perturbation is applied by gradcheck
+  to a float32 op, hence the reference's own loose atol=rtol=1e-1);
+* the oracle's module port equals the reference Python modules with IDENTICAL weights
+  (state_dict interchange), forward and backward;
+* this repo's product modules expose the reference's state-dict layout.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _util import pattern_like, rel_l2
+from backtoreality_b200 import scenes
+from oracle import cpu_modules, ref_python
+
+pytestmark = pytest.mark.skipif(not ref_python.available(), reason="reference tree not present")
+
+
+def test_reference_interpolation_gradcheck_on_oracle_ext():
+    rs = ref_python.RefStack("votenet")
+    torch.manual_seed(0)
+    feats = torch.randn(1, 2, 4).float().requires_grad_(True)
+
+    def interpolate_func(inputs):
+        idx = torch.from_numpy(np.array([[[0, 1, 2], [1, 2, 3]]])).int()
+        weight = torch.from_numpy(np.array([[[1, 1, 1], [2, 2, 2]]])).float()
+        return rs.pointnet2_utils.three_interpolate(inputs, idx, weight)
+
+    assert torch.autograd.gradcheck(interpolate_func, feats, atol=1e-1, rtol=1e-1)
+
+
+@pytest.mark.parametrize("flavour,C,fp2_out", [("votenet", 1, 256), ("groupfree3d", 0, 288)])
+def test_oracle_port_equals_reference_modules(flavour, C, fp2_out):
+    rs = ref_python.RefStack(flavour)
+    torch.manual_seed(5)
+    ref = rs.backbone_module.Pointnet2Backbone(input_feature_dim=C).train()
+    port = cpu_modules.Backbone(input_feature_dim=C, fp2_out=fp2_out).train()
+    port.load_state_dict(ref.state_dict())
+    pc = torch.from_numpy(scenes.batch(9, 2, 2500, C=C, kind="room", dup=0.2))
+    a, b = ref(pc), port(pc)
+    for k in a:
+        if a[k].dtype == torch.int32:
+            assert torch.equal(a[k], b[k]), k
+        else:
+            assert rel_l2(b[k].detach().numpy(), a[k].detach().numpy()) < 1e-6, k
+    (a["fp2_features"] * pattern_like(a["fp2_features"])).sum().backward()
+    (b["fp2_features"] * pattern_like(b["fp2_features"])).sum().backward()
+    for (n1, p1), (n2, p2) in zip(ref.named_parameters(), port.named_parameters()):
+        assert n1 == n2
+        assert rel_l2(p2.grad.numpy(), p1.grad.numpy()) < 1e-4, n1
+
+
+def test_product_modules_have_the_reference_state_dict_layout():
+    from backtoreality_b200.backbone_module import Pointnet2Backbone
+    for flavour, C, fp2_out in [("votenet", 1, 256), ("groupfree3d", 0, 288)]:
+        ref = ref_python.RefStack(flavour).backbone_module.Pointnet2Backbone(input_feature_dim=C)
+        mine = Pointnet2Backbone(input_feature_dim=C, fp2_out=fp2_out)
+        sd_r, sd_m = ref.state_dict(), mine.state_dict()
+        assert list(sd_r.keys()) == list(sd_m.keys())
+        for k in sd_r:
+            assert sd_r[k].shape == sd_m[k].shape, k
+        mine.load_state_dict(sd_r)
