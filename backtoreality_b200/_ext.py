@@ -23,7 +23,7 @@ def _stream():
 
 # ---- instrumentation used by bench.py (never changes what runs) ------------------------------
 LAUNCHES = 0   # number of libb2r kernel launches issued through this module
-TIMED = {}     # op name -> list of (start_event, stop_event); filled only for names in TIME_OPS
+TIMED = {}     # op name -> list of (start_event, stop_event, algorithmic_bytes); only TIME_OPS
 TIME_OPS = set()
 
 
@@ -31,8 +31,9 @@ class _timed:
     """Counts the launch and, for ops listed in TIME_OPS, brackets it with CUDA events recorded
     on the launching (current) stream."""
 
-    def __init__(self, name):
+    def __init__(self, name, algo_bytes=0):
         self.name = name
+        self.bytes = algo_bytes
         self.ev = None
 
     def __enter__(self):
@@ -45,7 +46,7 @@ class _timed:
     def __exit__(self, *a):
         if self.ev is not None:
             self.ev[1].record()
-            TIMED.setdefault(self.name, []).append(self.ev)
+            TIMED.setdefault(self.name, []).append((self.ev[0], self.ev[1], self.bytes))
 
 
 def _chk_contig(t, name):
@@ -260,7 +261,10 @@ def query_group(xyz, new_xyz, features, idx, radius, normalize_xyz):
     B, N = xyz.size(0), xyz.size(1)
     NP, NS = idx.size(1), idx.size(2)
     out = torch.empty((B, 3 + C, NP, NS), dtype=torch.float32, device=xyz.device)
-    with _on_device(xyz), _timed("query_group"):
+    # algorithmic bytes: output write + compulsory reads of features / xyz / centres / idx
+    L = NP * NS
+    algo = B * (4 * (3 + C) * L + min(4 * C * N, 4 * C * L) + min(12 * N, 12 * L) + 12 * NP + 4 * L)
+    with _on_device(xyz), _timed("query_group", algo):
         _lib.check(_lib.lib().b2r_query_group_fwd(xyz.data_ptr(), new_xyz.data_ptr(), fptr,
                                                   idx.data_ptr(), B, C, N, NP, NS, float(radius),
                                                   1 if normalize_xyz else 0, out.data_ptr(),

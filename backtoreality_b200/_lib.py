@@ -33,7 +33,32 @@ SIGNATURES = {
     "b2r_query_group_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp],
     "b2r_query_group_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp],
 }
-_RESTYPES = {"b2r_status_string": ctypes.c_char_p, "b2r_last_error": ctypes.c_char_p}
+_RESTYPES = {"b2r_status_string": ctypes.c_char_p, "b2r_last_error": ctypes.c_char_p,
+             "b2r_mlp_weight_image_bytes": ctypes.c_longlong}
+
+
+class SaLayer(ctypes.Structure):
+    """struct b2r_sa_layer (include/b2r.h)."""
+    _fields_ = [
+        ("B", _i), ("N", _i), ("NP", _i), ("NS", _i), ("Cin", _i), ("Cout", _i),
+        ("mode", _i), ("epilogue", _i),
+        ("xyz", _vp), ("new_xyz", _vp), ("feat_t", _vp), ("idx", _vp),
+        ("radius", _f), ("normalize_xyz", _i),
+        ("z_prev", _vp), ("scale_prev", _vp), ("shift_prev", _vp),
+        ("w_image", _vp), ("z", _vp), ("stats", _vp),
+        ("zmax", _vp), ("zmin", _vp), ("amax", _vp), ("amin", _vp),
+    ]
+
+
+SIGNATURES.update({
+    "b2r_mlp_weight_image_bytes": [_i, _i, _i],
+    "b2r_mlp_pack_weight": [_vp, _i, _i, _i, _vp, _vp],
+    "b2r_sa_layer_fwd": [ctypes.POINTER(SaLayer), _vp],
+    "b2r_bn_finalize": [_vp, _i, ctypes.c_double, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp,
+                        _vp],
+    "b2r_pool_finalize": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "b2r_to_point_major": [_vp, _i, _i, _i, _vp, _vp],
+})
 
 _lib = None
 

@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: Pointnet2Backbone(+vote head) fwd+bwd scenes/sec @40k pts.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b2r|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch of synthetic ScanNet-shaped scenes:
+VoteNet FSB (Pointnet2Backbone -> VotingModule -> vote aggregation + proposal head), batch 8 per
+GPU, 40k points + height feature, train-mode BatchNorm, forward + backward + (N>1) one NCCL
+all-reduce of the flat fp32 gradient + Adam step.  Scenes are sharded across ranks (weak
+scaling, no data-path collective).  Prints ONE JSON line on rank 0 (see the task contract):
+  value     scenes/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       the same with the step's input copied from PINNED HOST memory and the loss read back
+  roofline  the dominant HBM-bound libb2r kernel (fused QueryAndGroup) timed live with CUDA events
+  fps       the FPS cluster kernel (bound by the serial fp32 chain, not by HBM or tensor cores)
+  cpu_baseline  the oracle's CPU port of the same step on this box's host cores (N=1 only)
+`--impl reference` times that CPU port alone (the reference has no CPU path and is CUDA-only:
+"CPU not supported", _ext_src/src/sampling.cpp:38-40; its GPU kernels are timed separately by
+scripts/microbench.py).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "Pointnet2Backbone fwd+bwd scenes/sec @40k pts"
+UNIT = "scenes/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b2r", choices=["b2r", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="scenes per GPU per step")
+    ap.add_argument("--npoints", type=int, default=40000)
+    ap.add_argument("--cpu-scenes", type=int, default=2, help="scenes per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {
+        "workload": "VoteNet FSB backbone+vote head fwd/bwd (BASELINE.json configs[1]): "
+                    "Pointnet2Backbone(input_feature_dim=1) + VotingModule + ProposalModule("
+                    "vote_aggregation, 256 proposals), train-mode BN, Adam step",
+        "scenes_per_gpu": a.batch, "global_batch": a.batch * world, "points_per_scene": a.npoints,
+        "scene_kind": "room (ScanNet-shaped surfaces, 20% duplicate points), seeds 1000+i",
+        "loss": "synthetic scalar: mean(proposal_scores^2) + mean((vote_xyz-seed_xyz)^2)",
+        "parallelism": "dp%d (scenes sharded, flat-gradient NCCL all-reduce)" % world,
+        "l2": "256 MB buffer written between steps (flush) + 4 rotating input batches",
+        "mlp_math": "cuDNN fp32 with TF32 allowed (torch default, as the reference runs)",
+    }
+
+
+def synthetic_loss(ep):
+    return (ep["proposal_scores_raw"] ** 2).mean() + ((ep["vote_xyz"] - ep["seed_xyz"]) ** 2).mean()
+
+
+# ------------------------------------------------------------------------- CPU baseline ----
+def cpu_steps(a, steps, warmup, scenes_per_step):
+    """The oracle's CPU port of the same training step.  Returns (scenes/s, ms/step, cores)."""
+    from backtoreality_b200 import scenes
+    from oracle import cpu_modules, cpu_ops
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    net = cpu_modules.VoteNetCPU(input_feature_dim=1, num_proposal=256).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    pool = [torch.from_numpy(scenes.batch(100 + i * scenes_per_step, scenes_per_step, a.npoints,
+                                          C=1, kind="room", dup=0.2)) for i in range(2)]
+
+    def one(i):
+        ep = net({"point_clouds": pool[i % len(pool)]})
+        ep["seed_xyz"] = ep["fp2_xyz"]
+        loss = synthetic_loss(ep)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        return float(loss.detach())
+
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(i)
+    dt = time.perf_counter() - t0
+    return scenes_per_step * steps / dt, 1e3 * dt / steps, max(cores, cpu_ops.num_threads())
+
+
+def run_reference(a):
+    """`--impl reference`: the CPU arm.  Rank 0 only; other ranks exit without work."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    per = a.cpu_scenes if (a.steps + a.warmup) <= 30 else 1
+    val, ms, cores = cpu_steps(a, a.steps, a.warmup, per)
+    cfg = workload_config(a, 1)
+    cfg["parallelism"] = "host CPU, %d threads" % cores
+    cfg["l2"] = "n/a (CPU)"
+    sample = "%d scenes of %d points per step, %d steps" % (per, a.npoints, a.steps)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------- clocks ----------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.rows = []
+        self.proc = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(dev).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", uuid, "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception as e:  # nvidia-smi missing: report that instead of clocks
+            log("clock sampler unavailable:", e)
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if t < t0 or t > t1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+
+# ------------------------------------------------------------------------- GPU arm ---------
+def run_b2r(a):
+    import torch.distributed as dist
+    from backtoreality_b200 import _ext, _lib, scenes
+    from backtoreality_b200.votenet import VoteNet
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b2r needs a CUDA device (no CPU fallback exists)")
+    _lib.lib()  # loud failure when libb2r.so is missing
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_IB_DISABLE", "1")      # NVLink / NVSwitch only
+        os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == a.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % a.gpus
+
+    torch.manual_seed(0)  # identical replicas
+    net = VoteNet(22, 1, 22, np.ones((22, 3), np.float32), input_feature_dim=1, num_proposal=256,
+                  vote_factor=1, sampling="vote_fps").to(dev).train()
+    params = [p for p in net.parameters()]
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+    off = 0
+    for p in params:  # gradients live in one flat buffer: a single all-reduce per step
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    opt = torch.optim.Adam(params, lr=1e-3, fused=True)
+
+    pool_n = 4
+    host = [torch.from_numpy(scenes.batch((rank * pool_n + i) * a.batch, a.batch, a.npoints, C=1,
+                                          kind="room", dup=0.2)).pin_memory()
+            for i in range(pool_n)]
+    resident = [h.to(dev) for h in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(pc):
+        ep = net({"point_clouds": pc})
+        loss = synthetic_loss(ep)
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(flat)
+            flat.mul_(1.0 / world)
+        opt.step()
+        flat.zero_()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(a.steps):
+            flush.zero_()  # L2 flush between steps
+            fn(i)
+        e1.record()
+        barrier()
+        t1 = time.perf_counter()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), t0, t1
+
+    for i in range(max(a.warmup, 3)):
+        step(resident[i % pool_n])
+    sampler = ClockSampler(dev) if rank == 0 else None
+    time.sleep(0.3)
+
+    # (1) inputs resident in HBM
+    _ext.TIME_OPS.update(["query_group", "furthest_point_sampling"])
+    _ext.TIMED.clear()
+    l0 = _ext.LAUNCHES
+    ms_dev, t0, t1 = timed_loop(lambda i: step(resident[i % pool_n]))
+    launches = _ext.LAUNCHES - l0
+    timed = {k: list(v) for k, v in _ext.TIMED.items()}
+    _ext.TIME_OPS.clear()
+    clocks = sampler.window(t0, t1) if sampler else None
+
+    # (2) end to end: pinned host input -> device each step, loss read back each step
+    def e2e_step(i):
+        pc = host[i % pool_n].to(dev, non_blocking=True)
+        return float(step(pc).item())
+
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e, _, _ = timed_loop(e2e_step)
+    if sampler:
+        sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    scenes_total = a.batch * world * a.steps
+    out = {
+        "metric": METRIC, "value": scenes_total / (ms_dev * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, world),
+        "e2e": {"value": scenes_total / (ms_e2e * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": int(host[0].numel() * 4), "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+
+    # roofline of the dominant HBM-bound libb2r kernel, from events recorded in the timed loop
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    qg = timed.get("query_group", [])
+    if qg:
+        tot_ms = sum(s.elapsed_time(e) for s, e, _ in qg)
+        tot_b = sum(b for _, _, b in qg)
+        ach = tot_b / (tot_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[
+                "query_group_fwd_kernel"]["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        out["roofline"] = {"kernel": "query_group_fwd_kernel (fused QueryAndGroup, 5 launches/step)",
+                           "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                           "algorithmic_bytes_per_launch": tot_b / len(qg),
+                           "avg_launch_us": 1e3 * tot_ms / len(qg), "launches_timed": len(qg)}
+    fp = timed.get("furthest_point_sampling", [])
+    if fp:
+        per_step = len(fp) // a.steps
+        ms_step = sum(s.elapsed_time(e) for s, e, _ in fp) / a.steps
+        # SA1 is the first FPS launch of every step: N points -> 2048 samples
+        sa1 = [fp[i] for i in range(0, len(fp), per_step)]
+        sa1_ms = float(np.mean([s.elapsed_time(e) for s, e, _ in sa1]))
+        upd = a.batch * (2048 - 1) * a.npoints  # point-updates per launch, 8 flop each
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6
+        out["fps"] = {"kernel": "fps_cluster_kernel", "bound": "serial fp32 chain (not hbm/tensor)",
+                      "launches_per_step": per_step, "ms_per_step_all_levels": ms_step,
+                      "sa1_ms_per_batch": sa1_ms, "sa1_ms_per_scene": sa1_ms / a.batch,
+                      "sa1_point_updates_per_s": upd / (sa1_ms * 1e-3),
+                      "sa1_frac_of_fp32_issue_peak": 8 * upd / (sa1_ms * 1e-3) / fp32_peak}
+
+    if world == 1 and not a.no_cpu_baseline:
+        log("timing the CPU port (oracle) on the host cores ...")
+        val, ms, cores = cpu_steps(a, 3, 1, a.cpu_scenes)
+        out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                               "ms_per_step": ms,
+                               "sample": "%d scenes of %d points per step, 3 timed steps after 1 "
+                                         "warm-up (same model, loss, optimizer)" % (a.cpu_scenes,
+                                                                                     a.npoints)}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b2r(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -146,6 +146,70 @@ B2R_API int b2r_query_group_bwd(const float *grad_out, const int *idx, int B, in
                         float radius, int normalize_xyz, float *grad_xyz, float *grad_new_xyz,
                         float *grad_features, void *stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Fused SharedMLP layer of a set-abstraction block on tcgen05 tensor cores (csrc/mlp.cu).
+ *
+ * Replaces, inside PointnetSAModuleVotes.forward (reference pointnet2_modules.py:245-267), the
+ * library chain  QueryAndGroup -> [cuDNN 1x1 Conv2d -> BatchNorm2d -> ReLU] x3 -> max_pool2d
+ * (reference pytorch_utils.py:11-36,67-120).  ONE call runs ONE conv layer as a TF32 GEMM
+ *     z[position, co] = sum_k W[co, k] * x[position, k]          positions = B*NP*NS
+ * with the memory-bound neighbours fused in:
+ *   mode 0      x rows are gathered on the fly: [features(idx) ..., (xyz(idx)-new_xyz)/radius]
+ *               (the grouped (B,3+C,NP,NS) tensor is never materialised)
+ *   mode 1      x = relu(scale_prev * z_prev + shift_prev)  (previous layer's BatchNorm+ReLU)
+ *   epilogue 0  store raw z (M,Cout) position-major + accumulate per-channel sum / sum of squares
+ *   epilogue 1  statistics + max AND min of raw z over each centre's NS samples (+ arg indices);
+ *               b2r_pool_finalize turns them into max_pool(relu(bn(z))) exactly
+ * Weights are passed as the packed image produced by b2r_mlp_pack_weight (TF32-rounded,
+ * 128-byte-swizzled K-major shared-memory layout, staged by one TMA bulk copy).
+ * Limits: Cout <= 256, B*NP*NS % 128 == 0, NS in {16,32,64} for epilogue 1; otherwise
+ * B2R_ERR_UNSUPPORTED (callers then use the unfused path).
+ */
+typedef struct b2r_sa_layer {
+  int B, N, NP, NS;   /* scenes, source points per scene, centres per scene, samples per centre */
+  int Cin, Cout;      /* mode 0: Cin = 3 + feature channels (reference order [xyz, features]) */
+  int mode, epilogue;
+  const float *xyz;      /* mode 0: (B,N,3) */
+  const float *new_xyz;  /* mode 0: (B,NP,3) */
+  const float *feat_t;   /* mode 0: (B,N,Cin-3) POINT-major features, NULL when Cin == 3 */
+  const int *idx;        /* mode 0: (B,NP,NS) ball-query indices */
+  float radius;
+  int normalize_xyz;
+  const float *z_prev;      /* mode 1: (M,Cin) raw conv output of the previous layer */
+  const float *scale_prev;  /* mode 1: (Cin) */
+  const float *shift_prev;  /* mode 1: (Cin) */
+  const float *w_image;     /* from b2r_mlp_pack_weight(w, Cout, Cin, mode == 0) */
+  float *z;                 /* epilogue 0: (M,Cout) */
+  double *stats;            /* (2,Cout) sum, sum of squares; ACCUMULATED (caller zeroes); may be NULL */
+  float *zmax, *zmin;       /* epilogue 1: (B*NP,Cout) */
+  int *amax, *amin;         /* epilogue 1: (B*NP,Cout) sample index in [0,NS) */
+} b2r_sa_layer;
+
+B2R_API long long b2r_mlp_weight_image_bytes(int Cout, int Cin, int gather);
+/* w (Cout,Cin) row-major fp32 = nn.Conv2d(Cin,Cout,1).weight; gather != 0 for mode-0 layers */
+B2R_API int b2r_mlp_pack_weight(const float *w, int Cout, int Cin, int gather, float *image,
+                                void *stream);
+B2R_API int b2r_sa_layer_fwd(const b2r_sa_layer *desc, void *stream);
+
+/* BatchNorm bookkeeping from accumulated statistics (replaces the statistics half of
+ * nn.BatchNorm2d in training mode, reference pytorch_utils.py:55-58): scale = gamma*invstd,
+ * shift = beta - mean*scale; running stats updated with `momentum` (unbiased variance) when
+ * running_mean/var are non-NULL.  mean_out / invstd_out (C) are optional (saved for backward). */
+B2R_API int b2r_bn_finalize(const double *stats, int C, double count, const float *gamma,
+                            const float *beta, float eps, float momentum, float *running_mean,
+                            float *running_var, float *scale, float *shift, float *mean_out,
+                            float *invstd_out, void *stream);
+
+/* out = relu(scale*(scale>=0 ? zmax : zmin) + shift): (B,C,NP) channel-major (reference layout)
+ * and/or (B,NP,C) point-major (the next layer's gather source).  Either output may be NULL. */
+B2R_API int b2r_pool_finalize(const float *zmax, const float *zmin, const float *scale,
+                              const float *shift, int B, int NP, int C, float *out_cm,
+                              float *out_pm, void *stream);
+
+/* (B,C,N) channel-major -> (B,N,C) point-major */
+B2R_API int b2r_to_point_major(const float *in, int B, int C, int N, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,178 @@
+"""The tcgen05 fused SharedMLP layer (csrc/mlp.cu) against fp64 / fp32 torch references.
+
+Tolerance: operands are rounded to TF32 (10-bit mantissa, round-to-nearest), accumulation is
+FP32, so one layer carries a relative error of ~2^-11 per operand; rel-L2 <= 2e-3 per layer and
+<= 5e-3 through the 3-layer block with BatchNorm (the reference itself runs cuDNN TF32 by
+default).  Statistics, pooling indices and BN bookkeeping are checked exactly
+against the kernel's own z where they are integer / order questions.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from _util import rel_l2
+
+pytestmark = pytest.mark.gpu
+TF32_TOL = 2e-3
+
+
+def _run_layer(dev, **kw):
+    from backtoreality_b200 import _ext, _lib
+    d = _lib.SaLayer()
+    keep = []
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            keep.append(v)
+            v = ctypes.c_void_p(v.data_ptr())
+        setattr(d, k, v)
+    _lib.check(_lib.lib().b2r_sa_layer_fwd(ctypes.byref(d), _ext._stream()), "sa_layer_fwd")
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("Cin,Cout,NS,M", [(64, 64, 64, 4096), (64, 128, 64, 8192),
+                                          (128, 128, 32, 4096), (128, 256, 16, 2048),
+                                          (128, 256, 32, 128 * 301), (256, 128, 16, 1024)])
+def test_dense_layer_store_and_stats(cuda, Cin, Cout, NS, M):
+    from backtoreality_b200 import fused_sa
+    g = torch.Generator(device="cpu").manual_seed(Cin * 7 + Cout)
+    zp = torch.randn(M, Cin, generator=g).to(cuda)
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5).to(cuda)
+    sc = (torch.rand(Cin, generator=g) + 0.5).to(cuda)
+    sh = (torch.randn(Cin, generator=g) * 0.3).to(cuda)
+    image = fused_sa.pack_weight(w, gather=False)
+    z = torch.full((M, Cout), float("nan"), device=cuda)
+    stats = torch.zeros(2, Cout, dtype=torch.float64, device=cuda)
+    _run_layer(cuda, B=1, N=1, NP=M // NS, NS=NS, Cin=Cin, Cout=Cout, mode=1, epilogue=0,
+               z_prev=zp, scale_prev=sc, shift_prev=sh, w_image=image, z=z, stats=stats)
+    x = torch.relu(zp.double() * sc.double() + sh.double())
+    want = x @ w.double().reshape(Cout, Cin).t()
+    assert rel_l2(z.cpu().numpy(), want.cpu().numpy()) < TF32_TOL
+    # the statistics are sums of the kernel's own fp32 z
+    np.testing.assert_allclose(stats[0].cpu().numpy(), z.double().sum(0).cpu().numpy(),
+                               rtol=1e-6, atol=1e-3)
+    np.testing.assert_allclose(stats[1].cpu().numpy(), (z.double() ** 2).sum(0).cpu().numpy(),
+                               rtol=1e-6, atol=1e-3)
+
+
+@pytest.mark.parametrize("C,Cout,N,NP,NS,norm", [(1, 64, 5000, 64, 64, True), (0, 64, 3000, 128, 32, True),
+                                                 (128, 128, 2048, 256, 32, True),
+                                                 (256, 128, 1024, 128, 16, False),
+                                                 (6, 32, 777, 64, 16, True)])
+def test_gather_layer_matches_query_group_then_matmul(cuda, C, Cout, N, NP, NS, norm):
+    from backtoreality_b200 import _ext, fused_sa
+    B = 2
+    g = torch.Generator(device="cpu").manual_seed(C + Cout + N)
+    xyz = torch.rand(B, N, 3, generator=g).to(cuda)
+    new_xyz = torch.rand(B, NP, 3, generator=g).to(cuda)
+    feats = torch.randn(B, C, N, generator=g).to(cuda) if C else None
+    idx = torch.randint(0, N, (B, NP, NS), generator=g, dtype=torch.int32).to(cuda)
+    w = (torch.randn(Cout, 3 + C, 1, 1, generator=g) / (3 + C) ** 0.5).to(cuda)
+    r = 0.37
+    feat_t = fused_sa.to_point_major(feats) if C else None
+    if C:
+        assert torch.equal(feat_t, feats.transpose(1, 2).contiguous())
+    image = fused_sa.pack_weight(w, gather=True)
+    M = B * NP * NS
+    z = torch.full((M, Cout), float("nan"), device=cuda)
+    stats = torch.zeros(2, Cout, dtype=torch.float64, device=cuda)
+    kw = dict(B=B, N=N, NP=NP, NS=NS, Cin=3 + C, Cout=Cout, mode=0, epilogue=0, xyz=xyz,
+              new_xyz=new_xyz, idx=idx, radius=r, normalize_xyz=int(norm), w_image=image, z=z,
+              stats=stats)
+    if C:
+        kw["feat_t"] = feat_t
+    _run_layer(cuda, **kw)
+    grouped = _ext.query_group(xyz, new_xyz, feats, idx, r, norm)          # (B,3+C,NP,NS)
+    x = grouped.permute(0, 2, 3, 1).reshape(M, 3 + C).double()
+    want = x @ w.double().reshape(Cout, 3 + C).t()
+    assert rel_l2(z.cpu().numpy(), want.cpu().numpy()) < TF32_TOL
+
+
+@pytest.mark.parametrize("Cin,Cout,NS", [(64, 128, 64), (128, 256, 32), (128, 256, 16), (128, 128, 16)])
+def test_pool_epilogue_matches_dense_epilogue(cuda, Cin, Cout, NS):
+    from backtoreality_b200 import fused_sa
+    M = 128 * 37
+    g = torch.Generator(device="cpu").manual_seed(NS + Cout)
+    zp = torch.randn(M, Cin, generator=g).to(cuda)
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5).to(cuda)
+    sc = torch.ones(Cin, device=cuda)
+    sh = torch.zeros(Cin, device=cuda)
+    image = fused_sa.pack_weight(w, gather=False)
+    z = torch.empty(M, Cout, device=cuda)
+    st0 = torch.zeros(2, Cout, dtype=torch.float64, device=cuda)
+    base = dict(B=1, N=1, NP=M // NS, NS=NS, Cin=Cin, Cout=Cout, mode=1, z_prev=zp, scale_prev=sc,
+                shift_prev=sh, w_image=image)
+    _run_layer(cuda, epilogue=0, z=z, stats=st0, **base)
+    zmax = torch.empty(M // NS, Cout, device=cuda)
+    zmin = torch.empty_like(zmax)
+    amax = torch.empty(M // NS, Cout, dtype=torch.int32, device=cuda)
+    amin = torch.empty_like(amax)
+    st1 = torch.zeros(2, Cout, dtype=torch.float64, device=cuda)
+    _run_layer(cuda, epilogue=1, zmax=zmax, zmin=zmin, amax=amax, amin=amin, stats=st1, **base)
+    zz = z.view(M // NS, NS, Cout)
+    assert torch.equal(zmax, zz.max(1).values) and torch.equal(zmin, zz.min(1).values)
+    assert torch.equal(torch.gather(zz, 1, amax.long()[:, None, :])[:, 0], zmax)
+    assert torch.equal(torch.gather(zz, 1, amin.long()[:, None, :])[:, 0], zmin)
+    assert torch.allclose(st0, st1, rtol=1e-9, atol=1e-6)
+
+
+def _unfused(sa, xyz, new_xyz, feats):
+    """The unfused module path: QueryAndGroup + cuDNN SharedMLP + max_pool2d (fp32)."""
+    import torch.nn.functional as F
+    grouped, _ = sa.grouper(xyz, new_xyz, feats)
+    y = sa.mlp_module(grouped)
+    return F.max_pool2d(y, kernel_size=[1, y.size(3)]).squeeze(-1)
+
+
+@pytest.mark.parametrize("cfg", [dict(N=6000, C=1, npoint=512, radius=0.2, nsample=64, mlp=[1, 64, 64, 128]),
+                                 dict(N=2048, C=128, npoint=1024, radius=0.4, nsample=32, mlp=[128, 128, 128, 256]),
+                                 dict(N=1024, C=256, npoint=256, radius=0.3, nsample=16, mlp=[256, 128, 128, 128]),
+                                 dict(N=3000, C=0, npoint=256, radius=0.3, nsample=16, mlp=[0, 64, 64, 128])])
+@pytest.mark.parametrize("training", [False, True])
+def test_fused_block_vs_unfused_module(cuda, cfg, training):
+    import copy
+    from backtoreality_b200 import fused_sa, pointnet2_utils, scenes
+    from backtoreality_b200.pointnet2_modules import PointnetSAModuleVotes
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(11)
+        sa = PointnetSAModuleVotes(npoint=cfg["npoint"], radius=cfg["radius"],
+                                   nsample=cfg["nsample"], mlp=list(cfg["mlp"]), use_xyz=True,
+                                   normalize_xyz=True).to(cuda)
+        for blk in sa.mlp_module:   # non-trivial BN parameters / running stats, some negative gammas
+            bn = blk.bn.bn
+            bn.weight.data = torch.randn_like(bn.weight) * 0.5 + 0.8
+            bn.bias.data = torch.randn_like(bn.bias) * 0.2
+            bn.running_mean.data = torch.randn_like(bn.running_mean) * 0.1
+            bn.running_var.data = torch.rand_like(bn.running_var) + 0.5
+            bn.momentum = 0.3
+        sa.train(training)
+        ref = copy.deepcopy(sa)
+        B = 2
+        pc = torch.from_numpy(scenes.batch(70, B, cfg["N"], C=max(cfg["C"], 1), kind="room",
+                                           dup=0.2)).to(cuda)
+        xyz = pc[..., :3].contiguous()
+        feats = torch.randn(B, cfg["C"], cfg["N"], device=cuda) if cfg["C"] else None
+        inds = pointnet2_utils.furthest_point_sample(xyz, cfg["npoint"])
+        new_xyz = torch.gather(xyz, 1, inds.long()[..., None].expand(-1, -1, 3)).contiguous()
+        idx = pointnet2_utils.ball_query(cfg["radius"], cfg["nsample"], xyz, new_xyz)
+        assert fused_sa.supported(sa.mlp_module, xyz, feats, idx)
+        with torch.no_grad():
+            want = _unfused(ref, xyz, new_xyz, feats)
+            feat_t = fused_sa.to_point_major(feats) if feats is not None else None
+            got, got_pm = fused_sa.sa_mlp_forward(xyz, new_xyz, feat_t, idx, cfg["radius"], True,
+                                                  sa.mlp_module, training)
+        assert got.shape == want.shape
+        assert rel_l2(got.cpu().numpy(), want.cpu().numpy()) < 5e-3
+        assert torch.equal(got_pm, got.transpose(1, 2).contiguous())
+        if training:
+            for a, b in zip(sa.mlp_module, ref.mlp_module):
+                assert int(a.bn.bn.num_batches_tracked) == int(b.bn.bn.num_batches_tracked) == 1
+                assert rel_l2(a.bn.bn.running_mean.cpu().numpy(),
+                              b.bn.bn.running_mean.cpu().numpy()) < 5e-3
+                assert rel_l2(a.bn.bn.running_var.cpu().numpy(),
+                              b.bn.bn.running_var.cpu().numpy()) < 5e-3
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
