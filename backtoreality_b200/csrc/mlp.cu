@@ -27,119 +27,10 @@
 // with tcgen05.ld.32x32b.x32, MMA completion signalled through tcgen05.commit -> mbarrier.
 // The weight operand is staged by the TMA unit: one cp.async.bulk (UBLKCP) of a pre-swizzled
 // weight image built by `pack_weight_kernel`.
-#include <cuda/ptx>
-
-#include "common.cuh"
+#include "mlp_common.cuh"
 
 namespace b2r {
-namespace {
-
-constexpr int kMlpThreads = 256;  // 8 warps: all load, thread 0 issues MMAs, all run the epilogue
-
-// ----------------------------------------------------------------------------- PTX helpers --
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "MLP_WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra MLP_DONE_%=;\n\t"
-      "bra MLP_WAIT_%=;\n\t"
-      "MLP_DONE_%=:\n\t"
-      "}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes,
-                                         uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(dst),
-      "l"(src), "r"(bytes), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
-               "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
-               : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, TF32 operands, FP32 accumulate
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   bar)
-               : "memory");
-}
-
-// Shared-memory matrix descriptor, K-major, 128-byte swizzle (canonical layout: 8-row x 128-byte
-// atoms, 16-byte chunk index XOR (row & 7); consecutive 8-row groups 1024 B apart = SBO).
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3fffu);        // start address
-  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for SW128 K-major)
-  d |= (uint64_t)(1024u >> 4) << 32;              // stride byte offset: 8 rows x 128 B
-  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                         // layout type: SWIZZLE_128B
-  return d;
-}
-// kind::tf32 instruction descriptor: F32 accumulate, TF32 A/B, both K-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
-}
-
-// byte offset of 16-byte chunk `chunk` (4 consecutive K elements) of row `row` inside a K-major
-// SW128 operand with `rows` rows: K-atom (32 elements) major, then 8-row group, then row, chunk
-__device__ __forceinline__ uint32_t sw128_off(int row, int chunk, int rows) {
-  const int a = chunk >> 3, c = chunk & 7, g = row >> 3, r8 = row & 7;
-  return (uint32_t)(((a * (rows >> 3) + g) << 10) + (r8 << 7) + ((c ^ r8) << 4));
-}
-
-}  // namespace
-
-// packed K extent of a layer: gather mode puts the C feature channels first (padded to a multiple
-// of 4 so the xyz chunk is 16-byte aligned), then dx,dy,dz,0; dense mode is K itself (mult. of 4)
-static inline int packed_k(int Cin, int gather) {
-  if (!gather) return (Cin + 3) & ~3;
-  const int C = Cin - 3;
-  return ((C + 3) & ~3) + 4;
-}
-
+using namespace mlp;
 namespace {
 
 // W (Cout, Cin) row-major fp32 (a 1x1 conv weight) -> TF32-rounded shared-memory image of the A
@@ -180,6 +71,11 @@ struct LayerArgs {
   double *stats;
   float *zmax, *zmin;
   int *amax, *amin;
+  // epilogue 2 (backward helper): dz of the pooled top layer
+  const float *dysel;
+  const int *asel;
+  const float *bw_k1, *bw_k2, *bw_mean, *bw_invstd, *bw_gs;
+  float *dz;
   int Kp, Cout_pad, num_tiles;
 };
 
@@ -201,6 +97,30 @@ __device__ __forceinline__ void pool_groups(const float (&v)[64], long long pos0
     const long long centre = (pos0 + g * NS) / NS;
     const size_t o = (size_t)centre * Cout + c;
     zmax[o] = mx; zmin[o] = mn; amax[o] = ax; amin[o] = an;
+  }
+}
+
+// Backward helper (epilogue 2): with z of the pooled top layer back in registers, emit
+//   dz = gamma*invstd * (dy - mean(dy) - xhat * mean(dy*xhat)),   xhat = (z - mean) * invstd
+// where dy is the max-pool / ReLU routed output gradient: non-zero only at the selected sample.
+template <int NS>
+__device__ __forceinline__ void dz_groups(const float (&v)[64], long long pos0, int c, int Cout,
+                                          const float *__restrict__ dysel,
+                                          const int *__restrict__ asel, float k1, float k2,
+                                          float mean, float invstd, float gs,
+                                          float *__restrict__ dz) {
+#pragma unroll
+  for (int g = 0; g < 64 / NS; ++g) {
+    const long long centre = (pos0 + g * NS) / NS;
+    const float dyv = dysel[(size_t)centre * Cout + c];
+    const int as = asel[(size_t)centre * Cout + c];
+    float *o = dz + (size_t)(pos0 + g * NS) * Cout + c;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const float dy = (s == as) ? dyv : 0.f;
+      const float xh = (v[g * NS + s] - mean) * invstd;
+      o[(size_t)s * Cout] = gs * (dy - k1 - xh * k2);
+    }
   }
 }
 
@@ -264,6 +184,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) sa_layer_fwd_kernel(const Laye
   const bool c_ok = c < a.Cout;
   double acc_s = 0.0, acc_ss = 0.0;
   (void)kColsMax;
+  float e2_k1 = 0.f, e2_k2 = 0.f, e2_mean = 0.f, e2_invstd = 0.f, e2_gs = 0.f;
+  if (a.epilogue == 2 && c_ok) {
+    e2_k1 = a.bw_k1[c]; e2_k2 = a.bw_k2[c]; e2_mean = a.bw_mean[c];
+    e2_invstd = a.bw_invstd[c]; e2_gs = a.bw_gs[c];
+  }
 
   const int KS = (a.Kp + 7) >> 3;  // K = 8 slices actually issued
   const uint32_t idesc = idesc_tf32(NT);
@@ -393,11 +318,19 @@ __global__ void __launch_bounds__(kMlpThreads, 1) sa_layer_fwd_kernel(const Laye
 #pragma unroll
         for (int i = 0; i < 64; ++i)
           if (i < ncols) zp[(size_t)i * a.Cout] = v[i];  // a warp writes 32 channels = 128 B
-      } else {
+      } else if (a.epilogue == 1) {
         const long long p0 = pos0 + col0;
         if (a.NS == 16) pool_groups<16>(v, p0, c, a.Cout, a.zmax, a.zmin, a.amax, a.amin);
         else if (a.NS == 32) pool_groups<32>(v, p0, c, a.Cout, a.zmax, a.zmin, a.amax, a.amin);
         else pool_groups<64>(v, p0, c, a.Cout, a.zmax, a.zmin, a.amax, a.amin);
+      } else {
+        const long long p0 = pos0 + col0;
+        if (a.NS == 16)
+          dz_groups<16>(v, p0, c, a.Cout, a.dysel, a.asel, e2_k1, e2_k2, e2_mean, e2_invstd, e2_gs, a.dz);
+        else if (a.NS == 32)
+          dz_groups<32>(v, p0, c, a.Cout, a.dysel, a.asel, e2_k1, e2_k2, e2_mean, e2_invstd, e2_gs, a.dz);
+        else
+          dz_groups<64>(v, p0, c, a.Cout, a.dysel, a.asel, e2_k1, e2_k2, e2_mean, e2_invstd, e2_gs, a.dz);
       }
     }
     // the next iteration's prologue __syncthreads orders these TMEM loads before its MMAs and
@@ -519,7 +452,7 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
   B2R_REQUIRE(d->B > 0 && d->NP > 0 && d->NS > 0 && d->Cin > 0 && d->Cout > 0,
               "b2r_sa_layer_fwd: non-positive size");
   B2R_REQUIRE(d->mode == 0 || d->mode == 1, "b2r_sa_layer_fwd: mode must be 0 or 1");
-  B2R_REQUIRE(d->epilogue == 0 || d->epilogue == 1, "b2r_sa_layer_fwd: epilogue must be 0 or 1");
+  B2R_REQUIRE(d->epilogue >= 0 && d->epilogue <= 2, "b2r_sa_layer_fwd: epilogue must be 0, 1 or 2");
   B2R_REQUIRE(d->w_image != nullptr, "b2r_sa_layer_fwd: null weight image");
   LayerArgs a;
   a.B = d->B; a.N = d->N; a.NP = d->NP; a.NS = d->NS; a.Cin = d->Cin; a.Cout = d->Cout;
@@ -529,6 +462,8 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
   a.z_prev = d->z_prev; a.scale_prev = d->scale_prev; a.shift_prev = d->shift_prev;
   a.w_image = d->w_image; a.z = d->z; a.stats = d->stats;
   a.zmax = d->zmax; a.zmin = d->zmin; a.amax = d->amax; a.amin = d->amin;
+  a.dysel = d->dysel; a.asel = d->asel; a.bw_k1 = d->bw_k1; a.bw_k2 = d->bw_k2;
+  a.bw_mean = d->bw_mean; a.bw_invstd = d->bw_invstd; a.bw_gs = d->bw_gs; a.dz = d->dz;
   a.Kp = packed_k(d->Cin, d->mode == 0);
   a.Cout_pad = (d->Cout + 127) & ~127;
   const long long M = (long long)d->B * d->NP * d->NS;
@@ -544,7 +479,13 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
   if (d->epilogue == 0) {
     B2R_REQUIRE(d->z != nullptr, "b2r_sa_layer_fwd: epilogue 0 needs z");
   } else {
-    B2R_REQUIRE(d->zmax && d->zmin && d->amax && d->amin, "b2r_sa_layer_fwd: epilogue 1 needs pool outputs");
+    if (d->epilogue == 1)
+      B2R_REQUIRE(d->zmax && d->zmin && d->amax && d->amin,
+                  "b2r_sa_layer_fwd: epilogue 1 needs pool outputs");
+    else
+      B2R_REQUIRE(d->dysel && d->asel && d->bw_k1 && d->bw_k2 && d->bw_mean && d->bw_invstd &&
+                      d->bw_gs && d->dz,
+                  "b2r_sa_layer_fwd: epilogue 2 needs dysel/asel/k1/k2/mean/invstd/gs/dz");
     if (!(d->NS == 16 || d->NS == 32 || d->NS == 64)) {
       set_error("b2r_sa_layer_fwd: pooling supports nsample 16/32/64 (got %d)", d->NS);
       return B2R_ERR_UNSUPPORTED;
@@ -560,7 +501,7 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
   // tile width: 128 positions when one M tile and the operands fit, else 64
   int NT = 64;
   if (MT == 1 && layer_smem_bytes(a.Kp, a.Cout_pad, 128) <= 227 * 1024) NT = 128;
-  if (MT == 1 && NT == 64 && d->epilogue == 1) {
+  if (MT == 1 && NT == 64 && d->epilogue >= 1) {
     set_error("b2r_sa_layer_fwd: pooling layer with Cout<=128 needs K small enough for 128-wide tiles");
     return B2R_ERR_UNSUPPORTED;
   }

@@ -1,0 +1,135 @@
+// mlp_common.cuh -- device helpers shared by the tcgen05 SharedMLP kernels (mlp.cu, mlp_bwd.cu):
+// inline PTX for mbarrier / TMA bulk copy / tcgen05 alloc-mma-commit-fence, shared-memory matrix
+// descriptors for the 128-byte-swizzled canonical layouts (K-major and MN-major views of the SAME
+// bytes), and the address function of that layout.
+#pragma once
+#include <cuda/ptx>
+
+#include "common.cuh"
+
+namespace b2r {
+namespace mlp {
+
+constexpr int kMlpThreads = 256;  // 8 warps: all load, thread 0 issues MMAs, all run the epilogue
+
+// ----------------------------------------------------------------------------- PTX helpers --
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "MLP_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra MLP_DONE_%=;\n\t"
+      "bra MLP_WAIT_%=;\n\t"
+      "MLP_DONE_%=:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 operands, FP32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, 128-byte swizzle (canonical layout: 8-row x 128-byte
+// atoms, 16-byte chunk index XOR (row & 7); consecutive 8-row groups 1024 B apart = SBO).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fffu);        // start address
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for SW128 K-major)
+  d |= (uint64_t)(1024u >> 4) << 32;              // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                         // layout type: SWIZZLE_128B
+  return d;
+}
+// kind::tf32 instruction descriptor: F32 accumulate, TF32 A/B, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// The same swizzled bytes seen MN-major (the "transposed" operand view): groups of 32 contiguous
+// MN elements (128 B) are `lbo` bytes apart, consecutive 8-deep K groups `sbo` bytes apart.
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// general kind::tf32 instruction descriptor: a_mn / b_mn = 1 selects the MN-major operand view
+__host__ __device__ constexpr uint32_t idesc_tf32_ex(int n, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// byte offset of 16-byte chunk `chunk` (4 consecutive K elements) of row `row` inside a K-major
+// SW128 operand with `rows` rows: K-atom (32 elements) major, then 8-row group, then row, chunk
+__device__ __forceinline__ uint32_t sw128_off(int row, int chunk, int rows) {
+  const int a = chunk >> 3, c = chunk & 7, g = row >> 3, r8 = row & 7;
+  return (uint32_t)(((a * (rows >> 3) + g) << 10) + (r8 << 7) + ((c ^ r8) << 4));
+}
+
+// packed K extent of a layer: gather mode puts the C feature channels first (padded to a multiple
+// of 4 so the xyz chunk is 16-byte aligned), then dx,dy,dz,0; dense mode is K itself (mult. of 4)
+__host__ __device__ inline int packed_k(int Cin, int gather) {
+  if (!gather) return (Cin + 3) & ~3;
+  const int C = Cin - 3;
+  return ((C + 3) & ~3) + 4;
+}
+
+}  // namespace mlp
+}  // namespace b2r

@@ -27,6 +27,12 @@ def weight_checksum(module):
     return float(sum(p.detach().double().abs().sum() for p in module.parameters()))
 
 
+def pattern_like(t):
+    """same fixed pseudo-random loss weights as tests/_util.py:pattern_like"""
+    i = torch.arange(t.numel(), dtype=torch.float64)
+    return torch.sin(i * 12.9898 + 0.5 * torch.cos(i * 0.618)).float().reshape(t.shape)
+
+
 def sub(t, n=4096):
     """deterministic subsample of a tensor (keeps fixtures small)"""
     f = t.detach().reshape(-1)
@@ -47,7 +53,7 @@ def backbone_case(flavour, C, fp2_out, N, B, seed, train):
     for k in ("sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features"):
         out[k] = sub(ep[k])
     # one backward through everything: loss = sum(fp2_features * fixed pattern)
-    patt = torch.linspace(-1, 1, ep["fp2_features"].numel()).reshape(ep["fp2_features"].shape)
+    patt = pattern_like(ep["fp2_features"])
     (ep["fp2_features"] * patt).sum().backward()
     out["g_sa1_l0"] = sub(net.sa1.mlp_module.layer0.conv.weight.grad)
     out["g_sa2_l0"] = sub(net.sa2.mlp_module.layer0.conv.weight.grad)
@@ -72,7 +78,7 @@ def vote_aggregation_case(seed):
     xyz = (torch.rand(2, 256, 3, generator=g) * 2.0 + 0.5).requires_grad_(True)
     feats = torch.randn(2, 32, 256, generator=g).requires_grad_(True)
     new_xyz, new_feats, inds = sa(xyz, feats)
-    patt = torch.linspace(-1, 1, new_feats.numel()).reshape(new_feats.shape)
+    patt = pattern_like(new_feats)
     ((new_feats * patt).sum() + (new_xyz * 0.37).sum()).backward()
     out = {"seed": seed, "wsum": weight_checksum(sa), "inds": inds.numpy(),
            "new_xyz": new_xyz.detach().numpy(), "new_feats": new_feats.detach().numpy(),
@@ -100,7 +106,7 @@ def fp_case(seed):
     uf = torch.randn(2, 16, 100, generator=g).requires_grad_(True)
     kf = torch.randn(2, 48, 37, generator=g).requires_grad_(True)
     y = fp(unknown, known, uf, kf)
-    patt = torch.linspace(-1, 1, y.numel()).reshape(y.shape)
+    patt = pattern_like(y)
     (y * patt).sum().backward()
     return {"seed": seed, "wsum": weight_checksum(fp), "y": y.detach().numpy(),
             "g_uf": sub(uf.grad), "g_kf": kf.grad.numpy().copy()}

@@ -3,8 +3,14 @@ functions, PointnetSAModuleVotes, PointnetFPModule, Pointnet2Backbone) against
   * the golden fixtures generated from the reference's own Python stack, and
   * the oracle's CPU port (oracle/cpu_modules.py) at BASELINE.json's full 40k-point size.
 
-Tolerances: indices bit-exact; features / gradients rel-L2 <= 1e-4 with TF32
-disabled (pure fp32 MLP), <= 5e-3 in the default TF32 MLP mode the reference itself runs in.
+Tolerances: indices bit-exact; features rel-L2 <= 1e-4 with TF32 disabled (pure
+fp32 MLP), <= 5e-3 in the default TF32 MLP mode the reference itself runs in.
+Gradients through the whole backbone: rel-L2 <= 1e-2 (fp32) / 5e-2 (TF32).  That is not slack
+for the kernels -- it is the reference's own noise floor: the fp32 CPU reference stack run with
+1 and with 8 threads (different summation order only) disagrees with itself by 1e-3 .. 3e-3 on
+every SA-layer weight gradient of these fixtures (train-mode BatchNorm backward amplifies forward
+rounding differences of ~1e-6; measured with oracle/cpu_modules.py, see DESIGN.md "Tolerances").
+Per-block gradient parity at tight tolerance is in test_fused_sa_gpu.py against fp64.
 """
 import numpy as np
 import pytest
@@ -17,6 +23,8 @@ pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-4
 TF32_TOL = 5e-3
+GRAD_TOL = 1e-2        # fp32 mode, see the module docstring
+GRAD_TOL_TF32 = 5e-2
 
 
 @pytest.fixture()
@@ -46,11 +54,11 @@ def test_backbone_vs_reference_python_golden(cuda, fp32_mlp, fixture):
     for k in ("sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features"):
         assert rel_l2(sub(ep[k]), g[k]) < FP32_TOL, k
     (ep["fp2_features"] * pattern_like(ep["fp2_features"])).sum().backward()
-    assert rel_l2(sub(net.sa1.mlp_module.layer0.conv.weight.grad), g["g_sa1_l0"]) < 1e-3
-    assert rel_l2(sub(net.sa2.mlp_module.layer0.conv.weight.grad), g["g_sa2_l0"]) < 1e-3
-    assert rel_l2(sub(net.sa4.mlp_module.layer2.conv.weight.grad), g["g_sa4_l2"]) < 1e-3
-    assert rel_l2(sub(net.fp1.mlp.layer0.conv.weight.grad), g["g_fp1_l0"]) < 1e-3
-    assert rel_l2(sub(net.fp2.mlp.layer1.bn.bn.weight.grad), g["g_fp2_l1_bn"]) < 1e-3
+    assert rel_l2(sub(net.sa1.mlp_module.layer0.conv.weight.grad), g["g_sa1_l0"]) < GRAD_TOL
+    assert rel_l2(sub(net.sa2.mlp_module.layer0.conv.weight.grad), g["g_sa2_l0"]) < GRAD_TOL
+    assert rel_l2(sub(net.sa4.mlp_module.layer2.conv.weight.grad), g["g_sa4_l2"]) < GRAD_TOL
+    assert rel_l2(sub(net.fp1.mlp.layer0.conv.weight.grad), g["g_fp1_l0"]) < GRAD_TOL
+    assert rel_l2(sub(net.fp2.mlp.layer1.bn.bn.weight.grad), g["g_fp2_l1_bn"]) < GRAD_TOL
     if g["train"]:
         bn = net.sa1.mlp_module.layer0.bn.bn
         assert rel_l2(bn.running_mean.cpu().numpy(), g["rm_sa1_l0"]) < FP32_TOL
@@ -75,8 +83,8 @@ def test_vote_aggregation_golden_xyz_gradients_and_given_inds(cuda, fp32_mlp):
     assert np.array_equal(new_xyz.detach().cpu().numpy(), g["new_xyz"])
     assert rel_l2(new_feats.detach().cpu().numpy(), g["new_feats"]) < FP32_TOL
     ((new_feats * pattern_like(new_feats)).sum() + (new_xyz * 0.37).sum()).backward()
-    assert rel_l2(xyz.grad.cpu().numpy(), g["g_xyz"]) < 1e-3
-    assert rel_l2(sub(feats.grad), g["g_feats"]) < 1e-3
+    assert rel_l2(xyz.grad.cpu().numpy(), g["g_xyz"]) < GRAD_TOL
+    assert rel_l2(sub(feats.grad), g["g_feats"]) < GRAD_TOL
     # explicit inds + features=None (GroupFree3D SA1 style, proposal_module.py:97-100)
     torch.manual_seed(int(g["seed"]))
     sa2 = PointnetSAModuleVotes(npoint=64, radius=0.4, nsample=8, mlp=[0, 16, 16], use_xyz=True,
@@ -106,8 +114,8 @@ def test_fp_module_golden(cuda, fp32_mlp):
     y = fp(unknown.to(cuda), known.to(cuda), uf, kf)
     assert rel_l2(y.detach().cpu().numpy(), g["y"]) < FP32_TOL
     (y * pattern_like(y)).sum().backward()
-    assert rel_l2(kf.grad.cpu().numpy(), g["g_kf"]) < 1e-3
-    assert rel_l2(sub(uf.grad), g["g_uf"]) < 1e-3
+    assert rel_l2(kf.grad.cpu().numpy(), g["g_kf"]) < GRAD_TOL
+    assert rel_l2(sub(uf.grad), g["g_uf"]) < GRAD_TOL
 
 
 def test_reference_gradcheck_of_three_interpolate(cuda):
@@ -131,6 +139,7 @@ def test_backbone_full_size_40k_vs_oracle_port(cuda, mode):
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = (mode == "tf32")
     tol = FP32_TOL if mode == "fp32" else TF32_TOL
+    gtol = GRAD_TOL if mode == "fp32" else GRAD_TOL_TF32
     try:
         torch.manual_seed(3)
         port = cpu_modules.Backbone(input_feature_dim=1).train()
@@ -150,6 +159,6 @@ def test_backbone_full_size_40k_vs_oracle_port(cuda, mode):
         (got["fp2_features"] * pattern_like(got["fp2_features"])).sum().backward()
         for (n1, p1), (n2, p2) in zip(port.named_parameters(), net.named_parameters()):
             assert n1 == n2
-            assert rel_l2(p2.grad.cpu().numpy(), p1.grad.numpy()) < 20 * tol, n1
+            assert rel_l2(p2.grad.cpu().numpy(), p1.grad.numpy()) < gtol, n1
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
