@@ -68,7 +68,7 @@ def supported(mlp_module, xyz, features, idx, pooling="max"):
         if bn.momentum is None or not bn.track_running_stats or not bn.affine:
             return False
         cout, cin = blk.conv.out_channels, blk.conv.in_channels
-        if cout > 256 or (i > 0 and cin % 4 != 0):
+        if cout > 256 or cout % 8 != 0 or cin > 380 or (i > 0 and cin % 4 != 0):
             return False
         smem = _layer_smem(cin, cout, gather=(i == 0), nt=64)
         if smem > 227 * 1024:
@@ -103,13 +103,14 @@ def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
     blocks = list(mlp_module)
     L = len(blocks)
     z_prev = scale = shift = None
-    zs, bn_saved = [], []
+    zs, bn_saved, images = [], [], []
     zmax = zmin = amax = amin = None
     for i, blk in enumerate(blocks):
         conv, bn = blk.conv, blk.bn.bn
         Cin, Cout = conv.in_channels, conv.out_channels
         last = i == L - 1
         image = pack_weight(conv.weight, gather=(i == 0))
+        images.append(image)
         stats = torch.zeros((2, Cout), dtype=torch.float64, device=dev) if training else None
         d = _lib.SaLayer()
         d.B, d.N, d.NP, d.NS, d.Cin, d.Cout = B, N, NP, NS, Cin, Cout
@@ -162,5 +163,172 @@ def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
                                      _ptr(out_cm), _ptr(out_pm), st), "pool_finalize")
     _ext.LAUNCHES += 1
     if save is not None:
-        save.update(zs=zs, bn=bn_saved, zmax=zmax, zmin=zmin, amax=amax, amin=amin)
+        save.update(zs=zs, bn=bn_saved, zmax=zmax, zmin=zmin, amax=amax, amin=amin, images=images)
     return out_cm, out_pm
+
+
+def pack_weight_t(weight, gather):
+    """Conv weight (Cout,Cin,1,1) -> packed TF32 image of W^T (the dgrad A operand)."""
+    Cout, Cin = weight.shape[0], weight.shape[1]
+    w = weight.detach().reshape(Cout, Cin).contiguous()
+    nbytes = _lib.lib().b2r_mlp_weight_t_image_bytes(Cout, Cin, 1 if gather else 0)
+    image = torch.empty(nbytes // 4, dtype=torch.float32, device=weight.device)
+    _lib.check(_lib.lib().b2r_mlp_pack_weight_t(_ptr(w), Cout, Cin, 1 if gather else 0,
+                                                _ptr(image), _ext._stream()), "mlp_pack_weight_t")
+    _ext.LAUNCHES += 1
+    return image
+
+
+def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, weights, gammas,
+                    training, saved, need_feat, need_xyz, need_new_xyz):
+    """Backward of sa_mlp_forward through csrc/mlp_bwd.cu.
+
+    g_out_cm (B,Cl,NP) gradient of the pooled output.  Returns
+    (g_feat_t (B,N,C) | None, g_xyz (B,N,3) | None, g_new_xyz (B,NP,3) | None,
+     [dW_i (Cout,Cin)], [dgamma_i], [dbeta_i]).
+    """
+    lib = _lib.lib()
+    st = _ext._stream()
+    dev = xyz.device
+    B, N = xyz.shape[0], xyz.shape[1]
+    NP, NS = idx.shape[1], idx.shape[2]
+    M = B * NP * NS
+    L = len(weights)
+    zs, bn, images = saved["zs"], saved["bn"], saved["images"]
+    f32 = dict(dtype=torch.float32, device=dev)
+    dWs, dgammas, dbetas = [None] * L, [None] * L, [None] * L
+    tr = 1 if training else 0
+
+    # --- pooled top layer: route the output gradient to its one sample per (centre, channel)
+    top = L - 1
+    Ct = weights[top].shape[0]
+    mean, invstd, scale, shift = bn[top]
+    stats = torch.zeros((2, Ct), dtype=torch.float64, device=dev)
+    dysel = torch.empty((B * NP, Ct), **f32)
+    asel = torch.empty((B * NP, Ct), dtype=torch.int32, device=dev)
+    _lib.check(lib.b2r_pool_bwd_prep(_ptr(g_out_cm), None, _ptr(saved["zmax"]), _ptr(saved["zmin"]),
+                                     _ptr(saved["amax"]), _ptr(saved["amin"]), _ptr(scale),
+                                     _ptr(shift), B, NP, Ct, _ptr(dysel), _ptr(asel), _ptr(stats),
+                                     st), "pool_bwd_prep")
+    k1, k2, gs = torch.empty(Ct, **f32), torch.empty(Ct, **f32), torch.empty(Ct, **f32)
+    dgammas[top], dbetas[top] = torch.empty(Ct, **f32), torch.empty(Ct, **f32)
+    _lib.check(lib.b2r_bn_bwd_finalize(_ptr(stats), Ct, float(M), _ptr(gammas[top]), _ptr(mean),
+                                       _ptr(invstd), tr, None, None, None, _ptr(k1), _ptr(k2),
+                                       _ptr(gs), _ptr(dgammas[top]), _ptr(dbetas[top]), st),
+               "bn_bwd_finalize")
+    # recompute z of the top layer on the tensor cores and emit its dz
+    dz_top = torch.empty((M, Ct), **f32)
+    d = _lib.SaLayer()
+    d.B, d.N, d.NP, d.NS = B, N, NP, NS
+    d.Cin, d.Cout = weights[top].shape[1], Ct
+    d.mode, d.epilogue = (0 if top == 0 else 1), 2
+    if top == 0:
+        d.xyz, d.new_xyz, d.feat_t, d.idx = _ptr(xyz), _ptr(new_xyz), _ptr(feat_t), _ptr(idx)
+        d.radius, d.normalize_xyz = float(radius), 1 if normalize_xyz else 0
+    else:
+        d.z_prev, d.scale_prev, d.shift_prev = _ptr(zs[top - 1]), _ptr(bn[top - 1][2]), _ptr(bn[top - 1][3])
+    d.w_image = _ptr(images[top])
+    d.dysel, d.asel = _ptr(dysel), _ptr(asel)
+    d.bw_k1, d.bw_k2, d.bw_mean, d.bw_invstd, d.bw_gs = _ptr(k1), _ptr(k2), _ptr(mean), _ptr(invstd), _ptr(gs)
+    d.dz = _ptr(dz_top)
+    _lib.check(lib.b2r_sa_layer_fwd(ctypes.byref(d), st), "sa_layer_fwd(epilogue 2)")
+    _ext.LAUNCHES += 3
+
+    g_feat_t = g_xyz = g_new_xyz = None
+    gr = coef = None
+    for l in range(L - 1, -1, -1):
+        Cout, Cin = weights[l].shape[0], weights[l].shape[1]
+        b = _lib.SaLayerBwd()
+        b.B, b.N, b.NP, b.NS, b.Cin, b.Cout = B, N, NP, NS, Cin, Cout
+        b.mode = 0 if l == 0 else 1
+        if l == top:
+            b.dz = _ptr(dz_top)
+        else:
+            b.gr, b.z = _ptr(gr), _ptr(zs[l])
+            b.coef_a, b.coef_b, b.coef_c = _ptr(coef[0]), _ptr(coef[1]), _ptr(coef[2])
+        dWs[l] = torch.zeros((Cout, Cin), **f32)
+        b.dW = _ptr(dWs[l])
+        need_dgrad = True
+        gr_prev = stats_prev = None
+        if l == 0:
+            b.xyz, b.new_xyz, b.feat_t, b.idx = _ptr(xyz), _ptr(new_xyz), _ptr(feat_t), _ptr(idx)
+            b.radius, b.normalize_xyz = float(radius), 1 if normalize_xyz else 0
+            if need_feat and feat_t is not None:
+                g_feat_t = torch.zeros_like(feat_t)
+                b.g_feat_t = _ptr(g_feat_t)
+            if need_xyz:
+                g_xyz = torch.zeros_like(xyz)
+                b.g_xyz = _ptr(g_xyz)
+            if need_new_xyz:
+                g_new_xyz = torch.zeros_like(new_xyz)
+                b.g_new_xyz = _ptr(g_new_xyz)
+            need_dgrad = g_feat_t is not None or need_xyz or need_new_xyz
+        else:
+            b.z_prev, b.scale_prev, b.shift_prev = _ptr(zs[l - 1]), _ptr(bn[l - 1][2]), _ptr(bn[l - 1][3])
+            gr_prev = torch.empty((M, Cin), **f32)
+            stats_prev = torch.zeros((2, Cin), dtype=torch.float64, device=dev)
+            b.gr_prev, b.stats_prev = _ptr(gr_prev), _ptr(stats_prev)
+        image_t = pack_weight_t(weights[l], gather=(l == 0)) if need_dgrad else None
+        b.w_image_t = _ptr(image_t)
+        _lib.check(lib.b2r_sa_layer_bwd(ctypes.byref(b), st), "sa_layer_bwd")
+        _ext.LAUNCHES += 1
+        if l > 0:
+            mean, invstd, _, _ = bn[l - 1]
+            coef = [torch.empty(Cin, **f32) for _ in range(3)]
+            dgammas[l - 1], dbetas[l - 1] = torch.empty(Cin, **f32), torch.empty(Cin, **f32)
+            _lib.check(lib.b2r_bn_bwd_finalize(_ptr(stats_prev), Cin, float(M), _ptr(gammas[l - 1]),
+                                               _ptr(mean), _ptr(invstd), tr, _ptr(coef[0]),
+                                               _ptr(coef[1]), _ptr(coef[2]), None, None, None,
+                                               _ptr(dgammas[l - 1]), _ptr(dbetas[l - 1]), st),
+                       "bn_bwd_finalize")
+            _ext.LAUNCHES += 1
+            gr = gr_prev
+    return g_feat_t, g_xyz, g_new_xyz, dWs, dgammas, dbetas
+
+
+class _FusedSABlock(torch.autograd.Function):
+    """autograd node of the fused block: QueryAndGroup tail + SharedMLP + max-pool in, one
+    (B,C,npoint) tensor out.  Parameters are passed flat as (W0, gamma0, beta0, W1, ...)."""
+
+    @staticmethod
+    def forward(ctx, xyz, new_xyz, features, idx, radius, normalize_xyz, mlp_module, training,
+                *params):
+        feat_t = to_point_major(features.contiguous()) if features is not None else None
+        need = any(ctx.needs_input_grad)
+        save = {} if need else None
+        out_cm, _ = sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
+                                   training, want_point_major=False, save=save)
+        if need:
+            ctx.saved = (xyz, new_xyz, feat_t, idx, float(radius), bool(normalize_xyz),
+                         bool(training), save, params)
+        return out_cm
+
+    @staticmethod
+    def backward(ctx, g_out):
+        xyz, new_xyz, feat_t, idx, radius, normalize_xyz, training, save, params = ctx.saved
+        L = len(params) // 3
+        weights = [params[3 * i].detach().reshape(params[3 * i].shape[0], -1) for i in range(L)]
+        gammas = [params[3 * i + 1].detach() for i in range(L)]
+        nig = ctx.needs_input_grad
+        g_feat_t, g_xyz, g_new_xyz, dWs, dgs, dbs = sa_mlp_backward(
+            g_out.contiguous(), xyz, new_xyz, feat_t, idx, radius, normalize_xyz, weights, gammas,
+            training, save, need_feat=nig[2], need_xyz=nig[0], need_new_xyz=nig[1])
+        g_features = g_feat_t.transpose(1, 2).contiguous() if g_feat_t is not None else None
+        out = [g_xyz, g_new_xyz, g_features, None, None, None, None, None]
+        for i in range(L):
+            out += [dWs[i].view_as(params[3 * i]), dgs[i], dbs[i]]
+        return tuple(out)
+
+
+def sa_block(xyz, new_xyz, features, idx, radius, normalize_xyz, mlp_module, training):
+    """Differentiable fused SA block: returns new_features (B, mlp[-1], npoint)."""
+    params = []
+    for blk in mlp_module:
+        params += [blk.conv.weight, blk.bn.bn.weight, blk.bn.bn.bias]
+    return _FusedSABlock.apply(xyz, new_xyz, features, idx, radius, normalize_xyz, mlp_module,
+                               training, *params)
+
+
+# Set to False to route PointnetSAModuleVotes through the unfused path (QueryAndGroup kernel +
+# cuDNN SharedMLP + max_pool2d) -- used by the parity tests as the fp32 comparison arm.
+ENABLED = True

@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import fused_sa
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
 
@@ -67,6 +68,16 @@ class _SAVotesBase(nn.Module):
         self.mlp_module = pt_utils.SharedMLP(mlp_spec, bn=bn)
 
     def _abstract(self, xyz, new_xyz, features):
+        g = self.grouper
+        if (fused_sa.ENABLED and xyz.is_cuda and self.pooling == 'max'
+                and isinstance(g, pointnet2_utils.QueryAndGroup) and g.use_xyz
+                and not g.sample_uniformly and not g.ret_unique_cnt):
+            # fused path: ball query, then ONE tcgen05 block for group -> relative xyz -> MLP ->
+            # BN/ReLU -> max-pool (csrc/mlp.cu, csrc/mlp_bwd.cu); no (B,C,npoint,nsample) tensor
+            idx = pointnet2_utils.ball_query(self.radius, self.nsample, xyz, new_xyz)
+            if fused_sa.supported(self.mlp_module, xyz, features, idx, self.pooling):
+                return fused_sa.sa_block(xyz, new_xyz, features, idx, self.radius,
+                                         self.normalize_xyz, self.mlp_module, self.training)
         grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features)
         new_features = self.mlp_module(grouped_features)  # (B, mlp[-1], npoint, nsample)
         return _pool(new_features, grouped_xyz, self.pooling, self.sigma, self.nsample)

@@ -218,6 +218,65 @@ B2R_API int b2r_pool_finalize(const float *zmax, const float *zmin, const float 
 /* (B,C,N) channel-major -> (B,N,C) point-major */
 B2R_API int b2r_to_point_major(const float *in, int B, int C, int N, float *out, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Backward of the fused SharedMLP block (csrc/mlp_bwd.cu).  Replaces what autograd runs for
+ * PointnetSAModuleVotes' MLP + pooling (reference pointnet2_modules.py:245-267): max_pool2d
+ * backward, 3 x [ReLU backward, cuDNN BatchNorm backward, cuDNN dgrad + wgrad], torch.cat /
+ * div / sub backward and two group_points_grad scatters (src/group_points_gpu.cu:48-69).
+ *
+ *   b2r_pool_bwd_prep      grad of the pooled output -> the ONE sample per (centre, channel) it
+ *                          reaches (dysel, asel) + BatchNorm-backward sums of the top layer
+ *   b2r_bn_bwd_finalize    sums -> per-channel coefficients of dz = a*gr + b*z + c, dgamma, dbeta
+ *   b2r_sa_layer_fwd (epilogue 2)   recompute z of the top layer, emit its dz
+ *   b2r_sa_layer_bwd       ONE layer: dW (+)= dz^T x  and  gr_prev = (dz W) * relu-mask with the
+ *                          next BatchNorm-backward sums (dense layers), or the scatter-add of
+ *                          dz W into the point-major feature / xyz gradients (gather layer)
+ */
+typedef struct b2r_sa_layer_bwd_desc {
+  int B, N, NP, NS;
+  int Cin, Cout;            /* of THIS layer (mode 0: Cin = 3 + feature channels) */
+  int mode;                 /* 0: gather layer (layer 0), 1: dense layer */
+  /* the layer's input, recomputed exactly like the forward prologue */
+  const float *xyz, *new_xyz, *feat_t;
+  const int *idx;
+  float radius;
+  int normalize_xyz;
+  const float *z_prev, *scale_prev, *shift_prev; /* mode 1 */
+  const float *w_image_t;   /* b2r_mlp_pack_weight_t image; may be NULL when no dgrad is needed */
+  /* the layer's output gradient: either dz directly ... */
+  const float *dz;          /* (M,Cout) or NULL */
+  /* ... or gr = dL/d(bn output, ReLU-masked) with z and the b2r_bn_bwd_finalize coefficients */
+  const float *gr, *z;      /* (M,Cout) */
+  const float *coef_a, *coef_b, *coef_c; /* (Cout) */
+  /* outputs */
+  float *dW;                /* (Cout,Cin) nn.Conv2d layout; ACCUMULATED (caller zeroes) */
+  float *gr_prev;           /* mode 1: (M,Cin) ReLU-masked gradient of the layer below */
+  double *stats_prev;       /* mode 1: (2,Cin) sum(gr_prev), sum(gr_prev*z_prev); ACCUMULATED */
+  float *g_feat_t;          /* mode 0: (B,N,Cin-3) point-major, ACCUMULATED; NULL = not needed */
+  float *g_xyz;             /* mode 0: (B,N,3) ACCUMULATED; NULL = not needed */
+  float *g_new_xyz;         /* mode 0: (B,NP,3) ACCUMULATED; NULL = not needed */
+} b2r_sa_layer_bwd_desc;
+
+B2R_API long long b2r_mlp_weight_t_image_bytes(int Cout, int Cin, int gather);
+B2R_API int b2r_mlp_pack_weight_t(const float *w, int Cout, int Cin, int gather, float *image,
+                                  void *stream);
+B2R_API int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *desc, void *stream);
+
+/* dout_cm (B,C,NP) and/or dout_pm (B,NP,C) (summed; either may be NULL) -> dysel (B*NP,C),
+ * asel (B*NP,C), stats (2,C) double ACCUMULATED: sum(dysel), sum(dysel * zsel). */
+B2R_API int b2r_pool_bwd_prep(const float *dout_cm, const float *dout_pm, const float *zmax,
+                              const float *zmin, const int *amax, const int *amin,
+                              const float *scale, const float *shift, int B, int NP, int C,
+                              float *dysel, int *asel, double *stats, void *stream);
+
+/* stats (2,C) = sum(gr), sum(gr*z) over `count` positions -> coefficients of
+ * dz = coef_a*gr + coef_b*z + coef_c (training != 0: batch statistics; 0: running statistics),
+ * the epilogue-2 form (k1,k2,gs), and dgamma / dbeta.  Any output may be NULL. */
+B2R_API int b2r_bn_bwd_finalize(const double *stats, int C, double count, const float *gamma,
+                                const float *mean, const float *invstd, int training,
+                                float *coef_a, float *coef_b, float *coef_c, float *k1, float *k2,
+                                float *gs, float *dgamma, float *dbeta, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

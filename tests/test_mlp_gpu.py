@@ -176,3 +176,185 @@ def test_fused_block_vs_unfused_module(cuda, cfg, training):
                               b.bn.bn.running_var.cpu().numpy()) < 5e-3
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+# ------------------------------------------------------------------------------- backward ----
+def _run_bwd(**kw):
+    from backtoreality_b200 import _ext, _lib
+    d = _lib.SaLayerBwd()
+    keep = []
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            keep.append(v)
+            v = ctypes.c_void_p(v.data_ptr())
+        setattr(d, k, v)
+    _lib.check(_lib.lib().b2r_sa_layer_bwd(ctypes.byref(d), _ext._stream()), "sa_layer_bwd")
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("Cin,Cout,M,direct", [(64, 64, 4096, False), (64, 128, 8192, True),
+                                              (128, 128, 64 * 301, False), (128, 256, 4096, True),
+                                              (128, 256, 32 * 77, False), (256, 128, 2048, False),
+                                              (64, 24, 1024, False)])
+def test_dense_layer_backward(cuda, Cin, Cout, M, direct):
+    """dW, masked input gradient and the fused BatchNorm-backward sums against fp64."""
+    from backtoreality_b200 import fused_sa
+    g = torch.Generator(device="cpu").manual_seed(Cin * 3 + Cout + M)
+    zp = torch.randn(M, Cin, generator=g).to(cuda)
+    sc = (torch.rand(Cin, generator=g) + 0.5).to(cuda)
+    sc[::5] *= -1.0
+    sh = (torch.randn(Cin, generator=g) * 0.3).to(cuda)
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5).to(cuda)
+    gr = torch.randn(M, Cout, generator=g).to(cuda)
+    z = torch.randn(M, Cout, generator=g).to(cuda)
+    ca = (torch.rand(Cout, generator=g) + 0.5).to(cuda)
+    cb = (torch.randn(Cout, generator=g) * 0.2).to(cuda)
+    cc = (torch.randn(Cout, generator=g) * 0.1).to(cuda)
+    dz = (ca.double() * gr.double() + cb.double() * z.double() + cc.double())
+    image_t = fused_sa.pack_weight_t(w, gather=False)
+    dW = torch.zeros(Cout, Cin, device=cuda)
+    gprev = torch.full((M, Cin), float("nan"), device=cuda)
+    stats = torch.zeros(2, Cin, dtype=torch.float64, device=cuda)
+    kw = dict(B=1, N=1, NP=M // 16, NS=16, Cin=Cin, Cout=Cout, mode=1, z_prev=zp, scale_prev=sc,
+              shift_prev=sh, w_image_t=image_t, dW=dW, gr_prev=gprev, stats_prev=stats)
+    if direct:
+        kw["dz"] = dz.float().contiguous()
+        dz = kw["dz"].double()
+    else:
+        kw.update(gr=gr, z=z, coef_a=ca, coef_b=cb, coef_c=cc)
+    _run_bwd(**kw)
+    pre = zp.double() * sc.double() + sh.double()
+    x = torch.relu(pre)
+    w2 = w.double().reshape(Cout, Cin)
+    want_dW = dz.t() @ x
+    # mask exactly as the kernel evaluates it: one fp32 fma
+    mask = torch.addcmul(sh, zp, sc) > 0
+    want_g = (dz @ w2) * mask
+    assert rel_l2(dW.cpu().numpy(), want_dW.cpu().numpy()) < TF32_TOL
+    assert rel_l2(gprev.cpu().numpy(), want_g.cpu().numpy()) < TF32_TOL
+    # the sums are sums of the kernel's own masked gradient
+    np.testing.assert_allclose(stats[0].cpu().numpy(), gprev.double().sum(0).cpu().numpy(),
+                               rtol=1e-5, atol=1e-2)
+    np.testing.assert_allclose(stats[1].cpu().numpy(),
+                               (gprev.double() * zp.double()).sum(0).cpu().numpy(),
+                               rtol=1e-5, atol=1e-2)
+
+
+@pytest.mark.parametrize("C,Cout,N,NP,NS,norm,gx", [(1, 64, 5000, 64, 64, True, False),
+                                                    (0, 64, 3000, 128, 32, True, True),
+                                                    (128, 128, 2048, 256, 32, True, False),
+                                                    (256, 128, 1024, 128, 16, False, True),
+                                                    (6, 32, 777, 64, 16, True, True),
+                                                    (128, 128, 2048, 1024, 32, True, True),
+                                                    (1, 64, 20000, 1024, 64, True, True)])
+def test_gather_layer_backward(cuda, C, Cout, N, NP, NS, norm, gx):
+    """Layer 0: dW and the scatter-added feature / xyz / centre gradients against autograd
+    through the unfused query_group op in fp64."""
+    from backtoreality_b200 import _ext, fused_sa
+    B = 2
+    g = torch.Generator(device="cpu").manual_seed(C + Cout + N)
+    xyz = torch.rand(B, N, 3, generator=g).to(cuda)
+    new_xyz = torch.rand(B, NP, 3, generator=g).to(cuda)
+    feats = torch.randn(B, C, N, generator=g).to(cuda) if C else None
+    idx = torch.randint(0, N, (B, NP, NS), generator=g, dtype=torch.int32).to(cuda)
+    w = (torch.randn(Cout, 3 + C, 1, 1, generator=g) / (3 + C) ** 0.5).to(cuda)
+    M = B * NP * NS
+    dz = torch.randn(M, Cout, generator=g).to(cuda)
+    r = 0.37
+    feat_t = fused_sa.to_point_major(feats) if C else None
+    image_t = fused_sa.pack_weight_t(w, gather=True)
+    dW = torch.zeros(Cout, 3 + C, device=cuda)
+    kw = dict(B=B, N=N, NP=NP, NS=NS, Cin=3 + C, Cout=Cout, mode=0, xyz=xyz, new_xyz=new_xyz,
+              idx=idx, radius=r, normalize_xyz=int(norm), w_image_t=image_t, dz=dz, dW=dW)
+    g_feat_t = g_xyz = g_new = None
+    if C:
+        kw["feat_t"] = feat_t
+        g_feat_t = torch.zeros(B, N, C, device=cuda)
+        kw["g_feat_t"] = g_feat_t
+    if gx:
+        g_xyz = torch.zeros(B, N, 3, device=cuda)
+        g_new = torch.zeros(B, NP, 3, device=cuda)
+        kw.update(g_xyz=g_xyz, g_new_xyz=g_new)
+    _run_bwd(**kw)
+    # fp64 reference by autograd on plain torch indexing
+    xyz64 = xyz.double().requires_grad_(True)
+    new64 = new_xyz.double().requires_grad_(True)
+    f64 = feats.double().requires_grad_(True) if C else None
+    li = idx.long()
+    bi = torch.arange(B, device=cuda)[:, None, None].expand_as(li)
+    rel = xyz64[bi, li] - new64[:, :, None, :]                     # (B,NP,NS,3)
+    if norm:
+        rel = rel / r
+    cols = [rel]
+    if C:
+        cols.append(f64.transpose(1, 2)[bi, li])                   # (B,NP,NS,C)
+    x = torch.cat(cols, dim=-1).reshape(M, 3 + C)
+    w64 = w.double().reshape(Cout, 3 + C).requires_grad_(True)
+    (x @ w64.t() * dz.double()).sum().backward()
+    assert rel_l2(dW.cpu().numpy(), w64.grad.cpu().numpy()) < TF32_TOL
+    if C:
+        assert rel_l2(g_feat_t.cpu().numpy(), f64.grad.transpose(1, 2).cpu().numpy()) < TF32_TOL
+    if gx:
+        assert rel_l2(g_xyz.cpu().numpy(), xyz64.grad.cpu().numpy()) < TF32_TOL
+        assert rel_l2(g_new.cpu().numpy(), new64.grad.cpu().numpy()) < TF32_TOL
+
+
+@pytest.mark.parametrize("cfg", [dict(N=6000, C=1, npoint=512, radius=0.2, nsample=64, mlp=[1, 64, 64, 128]),
+                                 dict(N=2048, C=128, npoint=1024, radius=0.4, nsample=32, mlp=[128, 128, 128, 256]),
+                                 dict(N=1024, C=256, npoint=256, radius=0.3, nsample=16, mlp=[256, 128, 128, 128]),
+                                 dict(N=3000, C=0, npoint=256, radius=0.3, nsample=16, mlp=[0, 64, 64, 128])])
+@pytest.mark.parametrize("training", [False, True])
+def test_fused_block_backward_vs_unfused_module(cuda, cfg, training):
+    """PointnetSAModuleVotes fwd+bwd: fused tcgen05 path (TF32) against the unfused fp32 path
+    (QueryAndGroup kernel + cuDNN fp32 SharedMLP + max_pool2d) with identical parameters."""
+    import copy
+    from backtoreality_b200 import fused_sa, scenes
+    from backtoreality_b200.pointnet2_modules import PointnetSAModuleVotes
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(13)
+        sa = PointnetSAModuleVotes(npoint=cfg["npoint"], radius=cfg["radius"],
+                                   nsample=cfg["nsample"], mlp=list(cfg["mlp"]), use_xyz=True,
+                                   normalize_xyz=True).to(cuda)
+        for blk in sa.mlp_module:
+            bn = blk.bn.bn
+            bn.weight.data = torch.randn_like(bn.weight) * 0.5 + 0.8
+            bn.bias.data = torch.randn_like(bn.bias) * 0.2
+            bn.running_mean.data = torch.randn_like(bn.running_mean) * 0.1
+            bn.running_var.data = torch.rand_like(bn.running_var) + 0.5
+        sa.train(training)
+        ref = copy.deepcopy(sa)
+        B = 2
+        pc = torch.from_numpy(scenes.batch(71, B, cfg["N"], C=max(cfg["C"], 1), kind="room",
+                                           dup=0.2)).to(cuda)
+        outs = []
+        for mod, fused in ((sa, True), (ref, False)):
+            fused_sa.ENABLED = fused
+            try:
+                xyz = pc[..., :3].contiguous().clone().requires_grad_(True)
+                feats = (torch.randn(B, cfg["C"], cfg["N"], device=cuda,
+                                     generator=torch.Generator(device=cuda).manual_seed(5))
+                         .requires_grad_(True) if cfg["C"] else None)
+                new_xyz, y, inds = mod(xyz, feats)
+                patt = torch.sin(torch.arange(y.numel(), device=cuda, dtype=torch.float64) * 12.9898)
+                ((y * patt.float().view_as(y)).sum() + (new_xyz * 0.37).sum()).backward()
+                outs.append((y.detach(), xyz.grad, feats.grad if feats is not None else None,
+                             [p.grad for p in mod.parameters()]))
+            finally:
+                fused_sa.ENABLED = True
+        (y1, gx1, gf1, gp1), (y0, gx0, gf0, gp0) = outs
+        assert rel_l2(y1.cpu().numpy(), y0.cpu().numpy()) < 5e-3
+        # TF32 vs fp32 through three BN/ReLU layers + max-pool: a forward rounding difference of
+        # ~5e-4 flips that fraction of ReLU masks / pool argmaxes, which is sqrt(5e-4) ~ 2-4e-2 in
+        # gradient L2.  cuDNN's own TF32 path shows the same 3-4e-2 against fp32 on these blocks
+        # (profiles/r01/tf32_gradient_noise_cudnn_vs_fused.log); the kernels themselves are held
+        # to 2e-3 by the per-layer tests above.
+        tol = 8e-2
+        assert rel_l2(gx1.cpu().numpy(), gx0.cpu().numpy()) < tol
+        if gf1 is not None:
+            assert rel_l2(gf1.cpu().numpy(), gf0.cpu().numpy()) < tol
+        for (n, _), a, b in zip(sa.named_parameters(), gp1, gp0):
+            assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < tol, n
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
