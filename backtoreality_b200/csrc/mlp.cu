@@ -76,7 +76,7 @@ struct LayerArgs {
   const int *asel;
   const float *bw_k1, *bw_k2, *bw_mean, *bw_invstd, *bw_gs;
   float *dz;
-  int Kp, Cout_pad, num_tiles;
+  int Kp, Cout_pad, num_tiles, chf_shift;
 };
 
 // max/min + arg over groups of NS columns held in registers; writes (centre, channel) entries
@@ -193,7 +193,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) sa_layer_fwd_kernel(const Laye
   const int KS = (a.Kp + 7) >> 3;  // K = 8 slices actually issued
   const uint32_t idesc = idesc_tf32(NT);
   const long long per_scene = (long long)a.NP * a.NS;
-  const int C = a.Cin - 3, Cf4 = (C + 3) & ~3;
+  GatherSrc gsrc;
+  gsrc.xyz = a.xyz; gsrc.new_xyz = a.new_xyz; gsrc.feat_t = a.feat_t;
+  gsrc.N = a.N; gsrc.NP = a.NP; gsrc.NS = a.NS; gsrc.C = a.Cin - 3; gsrc.Cf4 = (a.Cin - 3 + 3) & ~3;
+  gsrc.chf_shift = a.chf_shift; gsrc.radius = a.radius; gsrc.normalize_xyz = a.normalize_xyz;
   uint32_t mma_parity = 0;
   bool w_ready = false;
 
@@ -204,54 +207,42 @@ __global__ void __launch_bounds__(kMlpThreads, 1) sa_layer_fwd_kernel(const Laye
     if (a.mode == 0) {
       if (tid < NT) s_idx[tid] = a.idx[pos0 + tid];
       __syncthreads();
-      const int CHf = Cf4 >> 2;       // feature chunks per row
-      const int CH = CHf + 1;         // + the xyz chunk
-      for (int i = tid; i < NT * CH; i += kMlpThreads) {
-        const int row = i / CH, ch = i - row * CH;
-        const long long pos = pos0 + row;
-        const int b = (int)(pos / per_scene);
-        const int p = s_idx[row];
-        uint4 out;
-        if (ch < CHf) {
-          const float *src = a.feat_t + ((size_t)b * a.N + p) * C + ch * 4;
-          float f[4] = {0.f, 0.f, 0.f, 0.f};
-          if ((C & 3) == 0) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(src));
-            f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (ch * 4 + e < C) f[e] = __ldg(src + e);
-          }
-          out = make_uint4(to_tf32(f[0]), to_tf32(f[1]), to_tf32(f[2]), to_tf32(f[3]));
-        } else {
-          const int j = (int)((pos / a.NS) % a.NP);
-          const float *pp = a.xyz + ((size_t)b * a.N + p) * 3;
-          const float *qq = a.new_xyz + ((size_t)b * a.NP + j) * 3;
-          float d[3];
-#pragma unroll
-          for (int e = 0; e < 3; ++e) {
-            d[e] = __fsub_rn(__ldg(pp + e), __ldg(qq + e));
-            if (a.normalize_xyz) d[e] = __fdiv_rn(d[e], a.radius);
-          }
-          out = make_uint4(to_tf32(d[0]), to_tf32(d[1]), to_tf32(d[2]), 0u);
-        }
-        *reinterpret_cast<uint4 *>(s_x + sw128_off(row, ch, NT)) = out;
-      }
+      const int b = (int)(pos0 / per_scene);
+      const int in_scene0 = (int)(pos0 - (long long)b * per_scene);
+      build_x_gather<NT>(gsrc, b, in_scene0, s_idx, s_x, tid,
+                         [](int row, int ch) { return sw128_off(row, ch, NT); });
     } else {
+      // dense layer: the tile is one contiguous block of z_prev.  Loads are issued in batches of
+      // 8 independent 16-byte requests per thread (memory-level parallelism), and the NEXT tile
+      // of this CTA is pulled into L2 by a single bulk-prefetch instruction meanwhile.
       const int CH = a.Cin >> 2;
-      for (int i = tid; i < NT * CH; i += kMlpThreads) {
-        const int row = i / CH, ch = i - row * CH;
-        const float4 t = __ldg(reinterpret_cast<const float4 *>(
-            a.z_prev + (size_t)(pos0 + row) * a.Cin + ch * 4));
-        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + ch * 4);
-        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + ch * 4);
-        uint4 out;
-        out.x = to_tf32(fmaxf(fmaf(t.x, sc.x, sh.x), 0.f));
-        out.y = to_tf32(fmaxf(fmaf(t.y, sc.y, sh.y), 0.f));
-        out.z = to_tf32(fmaxf(fmaf(t.z, sc.z, sh.z), 0.f));
-        out.w = to_tf32(fmaxf(fmaf(t.w, sc.w, sh.w), 0.f));
-        *reinterpret_cast<uint4 *>(s_x + sw128_off(row, ch, NT)) = out;
+      const int total = NT * CH;
+      if (tid == 0 && tile + (int)gridDim.x < a.num_tiles)
+        prefetch_l2(a.z_prev + (size_t)(pos0 + (long long)gridDim.x * NT) * a.Cin,
+                    (uint32_t)total * 16u);
+      const float4 *src = reinterpret_cast<const float4 *>(a.z_prev + (size_t)pos0 * a.Cin);
+      for (int i0 = tid; i0 < total; i0 += kMlpThreads * 8) {
+        float4 t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * kMlpThreads;
+          if (i < total) t[u] = __ldg(src + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * kMlpThreads;
+          if (i < total) {
+            const int row = i / CH, ch = i - row * CH;
+            const float4 sc = *reinterpret_cast<const float4 *>(s_scale + ch * 4);
+            const float4 sh = *reinterpret_cast<const float4 *>(s_shift + ch * 4);
+            uint4 out;
+            out.x = to_tf32(fmaxf(fmaf(t[u].x, sc.x, sh.x), 0.f));
+            out.y = to_tf32(fmaxf(fmaf(t[u].y, sc.y, sh.y), 0.f));
+            out.z = to_tf32(fmaxf(fmaf(t[u].z, sc.z, sh.z), 0.f));
+            out.w = to_tf32(fmaxf(fmaf(t[u].w, sc.w, sh.w), 0.f));
+            *reinterpret_cast<uint4 *>(s_x + sw128_off(row, ch, NT)) = out;
+          }
+        }
       }
     }
     fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -466,6 +457,7 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
   a.bw_mean = d->bw_mean; a.bw_invstd = d->bw_invstd; a.bw_gs = d->bw_gs; a.dz = d->dz;
   a.Kp = packed_k(d->Cin, d->mode == 0);
   a.Cout_pad = (d->Cout + 127) & ~127;
+  a.chf_shift = pow2_shift(((d->Cin - 3 + 3) & ~3) >> 2);
   const long long M = (long long)d->B * d->NP * d->NS;
   if (d->mode == 0) {
     B2R_REQUIRE(d->Cin >= 3 && d->xyz && d->new_xyz && d->idx && (d->feat_t || d->Cin == 3),
@@ -491,9 +483,11 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
       return B2R_ERR_UNSUPPORTED;
     }
   }
-  if (a.Cout_pad > 256 || (M % 128) != 0) {
-    set_error("b2r_sa_layer_fwd: needs Cout <= 256 and B*NP*NS %% 128 == 0 (Cout=%d, M=%lld)",
-              d->Cout, M);
+  if (a.Cout_pad > 256 || (M % 128) != 0 ||
+      (d->mode == 0 && ((long long)d->NP * d->NS) % 128 != 0)) {
+    set_error("b2r_sa_layer_fwd: needs Cout <= 256, B*NP*NS %% 128 == 0 and (gather layers) "
+              "NP*NS %% 128 == 0 (Cout=%d, M=%lld, NP*NS=%lld)", d->Cout, M,
+              (long long)d->NP * d->NS);
     return B2R_ERR_UNSUPPORTED;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -52,6 +52,7 @@ struct BwdArgs {
   float *g_feat_t, *g_xyz, *g_new_xyz;
   int do_dgrad, do_wgrad;
   int Kp, KA, KAl, Cout_pad, num_tiles;   // KA: 32-wide atoms of packed K, KAl: of Cout
+  int chf_shift;
 };
 
 // Shared-memory carve-up (host + device agree through this one function).
@@ -187,6 +188,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) sa_layer_bwd_kernel(const BwdA
 
   const long long per_scene = (long long)a.NP * a.NS;
   const int C = a.Cin - 3, Cf4 = (C + 3) & ~3;   // gather mode: feature channels
+  GatherSrc gsrc;
+  gsrc.xyz = a.xyz; gsrc.new_xyz = a.new_xyz; gsrc.feat_t = a.feat_t;
+  gsrc.N = a.N; gsrc.NP = a.NP; gsrc.NS = a.NS; gsrc.C = C; gsrc.Cf4 = Cf4;
+  gsrc.chf_shift = a.chf_shift; gsrc.radius = a.radius; gsrc.normalize_xyz = a.normalize_xyz;
   const int CHl = a.Cout >> 2;                   // 16-byte chunks per DZ row
   const int KSl = (a.Cout + 7) >> 3;             // dgrad K steps (8 output channels each)
   const uint32_t idesc_dgrad = idesc_tf32(NT);   // A = W^T image, B = DZ, both K-major
@@ -204,81 +209,96 @@ __global__ void __launch_bounds__(kMlpThreads, 1) sa_layer_bwd_kernel(const BwdA
     int *s_idx = s_idx2 + (tile_iter & 1) * NT;
 
     // ---- prologue 1: DZ tile, written in both operand layouts ----------------------------------
-    for (int i = tid; i < NT * CHl; i += kMlpThreads) {
-      const int row = i / CHl, ch = i - row * CHl;
-      const size_t o = (size_t)(pos0 + row) * a.Cout + ch * 4;
-      float4 v;
-      if (!has_coef) {
-        v = __ldg(reinterpret_cast<const float4 *>(a.dz + o));
-      } else {
-        const float4 g = __ldg(reinterpret_cast<const float4 *>(a.gr + o));
-        const float4 zz = __ldg(reinterpret_cast<const float4 *>(a.z + o));
-        const float4 ca = *reinterpret_cast<const float4 *>(s_ca + ch * 4);
-        const float4 cb = *reinterpret_cast<const float4 *>(s_cb + ch * 4);
-        const float4 cc = *reinterpret_cast<const float4 *>(s_cc + ch * 4);
-        v.x = fmaf(ca.x, g.x, fmaf(cb.x, zz.x, cc.x));
-        v.y = fmaf(ca.y, g.y, fmaf(cb.y, zz.y, cc.y));
-        v.z = fmaf(ca.z, g.z, fmaf(cb.z, zz.z, cc.z));
-        v.w = fmaf(ca.w, g.w, fmaf(cb.w, zz.w, cc.w));
+    // (loads batched 4-deep per thread; the next tile of this CTA is bulk-prefetched into L2)
+    {
+      const int total = NT * CHl;
+      const size_t o0 = (size_t)pos0 * a.Cout;
+      if (tid == 0 && tile + (int)gridDim.x < a.num_tiles) {
+        const size_t on = (size_t)(pos0 + (long long)gridDim.x * NT) * a.Cout;
+        if (!has_coef) {
+          prefetch_l2(a.dz + on, (uint32_t)total * 16u);
+        } else {
+          prefetch_l2(a.gr + on, (uint32_t)total * 16u);
+          prefetch_l2(a.z + on, (uint32_t)total * 16u);
+        }
+        if (a.mode == 1)
+          prefetch_l2(a.z_prev + (size_t)(pos0 + (long long)gridDim.x * NT) * a.Cin,
+                      (uint32_t)NT * a.Cin * 4u);
       }
-      const uint4 out = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-      if (a.do_dgrad) *reinterpret_cast<uint4 *>(s_dzk + sw128_off(row, ch, NT)) = out;
-      if (a.do_wgrad) *reinterpret_cast<uint4 *>(s_dz32 + t32_off(row, ch, NT)) = out;
+      for (int i0 = tid; i0 < total; i0 += kMlpThreads * 4) {
+        float4 g[4], zz[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * kMlpThreads;
+          if (i < total) {
+            if (!has_coef) {
+              g[u] = __ldg(reinterpret_cast<const float4 *>(a.dz + o0) + i);
+            } else {
+              g[u] = __ldg(reinterpret_cast<const float4 *>(a.gr + o0) + i);
+              zz[u] = __ldg(reinterpret_cast<const float4 *>(a.z + o0) + i);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * kMlpThreads;
+          if (i < total) {
+            const int row = i / CHl, ch = i - row * CHl;
+            float4 v = g[u];
+            if (has_coef) {
+              const float4 ca = *reinterpret_cast<const float4 *>(s_ca + ch * 4);
+              const float4 cb = *reinterpret_cast<const float4 *>(s_cb + ch * 4);
+              const float4 cc = *reinterpret_cast<const float4 *>(s_cc + ch * 4);
+              v.x = fmaf(ca.x, g[u].x, fmaf(cb.x, zz[u].x, cc.x));
+              v.y = fmaf(ca.y, g[u].y, fmaf(cb.y, zz[u].y, cc.y));
+              v.z = fmaf(ca.z, g[u].z, fmaf(cb.z, zz[u].z, cc.z));
+              v.w = fmaf(ca.w, g[u].w, fmaf(cb.w, zz[u].w, cc.w));
+            }
+            const uint4 out = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+            if (a.do_dgrad) *reinterpret_cast<uint4 *>(s_dzk + sw128_off(row, ch, NT)) = out;
+            if (a.do_wgrad) *reinterpret_cast<uint4 *>(s_dz32 + t32_off(row, ch, NT)) = out;
+          }
+        }
+      }
     }
     // ---- prologue 2: X tile (same recomputation as the forward kernel), BASE32B layout ---------
+    int tile_b = 0, in_scene0 = 0;   // gather layers: the tile's scene, first position in it
     if (a.mode == 0) {
       if (tid < NT) s_idx[tid] = a.idx[pos0 + tid];
       __syncthreads();
+      tile_b = (int)(pos0 / per_scene);
+      in_scene0 = (int)(pos0 - (long long)tile_b * per_scene);
     }
     if (a.do_wgrad) {
       if (a.mode == 0) {
-        const int CHf = Cf4 >> 2, CH = CHf + 1;
-        for (int i = tid; i < NT * CH; i += kMlpThreads) {
-          const int row = i / CH, ch = i - row * CH;
-          const long long pos = pos0 + row;
-          const int b = (int)(pos / per_scene);
-          const int p = s_idx[row];
-          uint4 out;
-          if (ch < CHf) {
-            const float *src = a.feat_t + ((size_t)b * a.N + p) * C + ch * 4;
-            float f[4] = {0.f, 0.f, 0.f, 0.f};
-            if ((C & 3) == 0) {
-              const float4 t = __ldg(reinterpret_cast<const float4 *>(src));
-              f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (ch * 4 + e < C) f[e] = __ldg(src + e);
-            }
-            out = make_uint4(to_tf32(f[0]), to_tf32(f[1]), to_tf32(f[2]), to_tf32(f[3]));
-          } else {
-            const int j = (int)((pos / a.NS) % a.NP);
-            const float *pp = a.xyz + ((size_t)b * a.N + p) * 3;
-            const float *qq = a.new_xyz + ((size_t)b * a.NP + j) * 3;
-            float d[3];
-#pragma unroll
-            for (int e = 0; e < 3; ++e) {
-              d[e] = __fsub_rn(__ldg(pp + e), __ldg(qq + e));
-              if (a.normalize_xyz) d[e] = __fdiv_rn(d[e], a.radius);
-            }
-            out = make_uint4(to_tf32(d[0]), to_tf32(d[1]), to_tf32(d[2]), 0u);
-          }
-          *reinterpret_cast<uint4 *>(s_x + t32_off(row, ch, NT)) = out;
-        }
+        build_x_gather<NT>(gsrc, tile_b, in_scene0, s_idx, s_x, tid,
+                           [](int row, int ch) { return t32_off(row, ch, NT); });
       } else {
         const int CH = a.Cin >> 2;
-        for (int i = tid; i < NT * CH; i += kMlpThreads) {
-          const int row = i / CH, ch = i - row * CH;
-          const float4 t = __ldg(reinterpret_cast<const float4 *>(
-              a.z_prev + (size_t)(pos0 + row) * a.Cin + ch * 4));
-          const float4 sc = *reinterpret_cast<const float4 *>(s_scale + ch * 4);
-          const float4 sh = *reinterpret_cast<const float4 *>(s_shift + ch * 4);
-          uint4 out;
-          out.x = to_tf32(fmaxf(fmaf(t.x, sc.x, sh.x), 0.f));
-          out.y = to_tf32(fmaxf(fmaf(t.y, sc.y, sh.y), 0.f));
-          out.z = to_tf32(fmaxf(fmaf(t.z, sc.z, sh.z), 0.f));
-          out.w = to_tf32(fmaxf(fmaf(t.w, sc.w, sh.w), 0.f));
-          *reinterpret_cast<uint4 *>(s_x + t32_off(row, ch, NT)) = out;
+        const int total = NT * CH;
+        const float4 *src = reinterpret_cast<const float4 *>(a.z_prev + (size_t)pos0 * a.Cin);
+        for (int i0 = tid; i0 < total; i0 += kMlpThreads * 8) {
+          float4 t[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * kMlpThreads;
+            if (i < total) t[u] = __ldg(src + i);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * kMlpThreads;
+            if (i < total) {
+              const int row = i / CH, ch = i - row * CH;
+              const float4 sc = *reinterpret_cast<const float4 *>(s_scale + ch * 4);
+              const float4 sh = *reinterpret_cast<const float4 *>(s_shift + ch * 4);
+              uint4 out;
+              out.x = to_tf32(fmaxf(fmaf(t[u].x, sc.x, sh.x), 0.f));
+              out.y = to_tf32(fmaxf(fmaf(t[u].y, sc.y, sh.y), 0.f));
+              out.z = to_tf32(fmaxf(fmaf(t[u].z, sc.z, sh.z), 0.f));
+              out.w = to_tf32(fmaxf(fmaf(t[u].w, sc.w, sh.w), 0.f));
+              *reinterpret_cast<uint4 *>(s_x + t32_off(row, ch, NT)) = out;
+            }
+          }
         }
       }
     }
@@ -348,13 +368,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) sa_layer_bwd_kernel(const BwdA
               const float *zp = a.z_prev + (size_t)p0 * a.Cin + kp;
               float *gp = a.gr_prev + (size_t)p0 * a.Cin + kp;
               float t1 = 0.f, t2 = 0.f;
+              float zv[32];   // all 32 (L2-resident) loads in flight before the first store
+#pragma unroll
+              for (int i = 0; i < 32; ++i) zv[i] = __ldg(zp + (size_t)i * a.Cin);
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                const float zv = __ldg(zp + (size_t)i * a.Cin);
-                const float g = fmaf(zv, sc, sh) > 0.f ? __uint_as_float(r[i]) : 0.f;
+                const float g = fmaf(zv[i], sc, sh) > 0.f ? __uint_as_float(r[i]) : 0.f;
                 gp[(size_t)i * a.Cin] = g;
                 t1 += g;
-                t2 = fmaf(g, zv, t2);
+                t2 = fmaf(g, zv[i], t2);
               }
               s1[m] += t1;
               s2[m] += t2;
@@ -365,28 +387,23 @@ __global__ void __launch_bounds__(kMlpThreads, 1) sa_layer_bwd_kernel(const BwdA
             const int e = kp - Cf4;                 // 0..2 for dx,dy,dz rows
             const bool is_xyz = (e >= 0 && e < 3);
             if (is_feat && a.g_feat_t != nullptr) {
+              float *gb = a.g_feat_t + (size_t)tile_b * a.N * C + kp;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int b = (int)((p0 + i) / per_scene);
-                const int p = s_idx[cc * 32 + i];
-                atomicAdd(a.g_feat_t + ((size_t)b * a.N + p) * C + kp, __uint_as_float(r[i]));
-              }
+              for (int i = 0; i < 32; ++i)
+                atomicAdd(gb + (size_t)s_idx[cc * 32 + i] * C, __uint_as_float(r[i]));
             } else if (is_xyz && (a.g_xyz != nullptr || a.g_new_xyz != nullptr)) {
               float run = 0.f;
+              float *gx = a.g_xyz != nullptr ? a.g_xyz + (size_t)tile_b * a.N * 3 + e : nullptr;
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                const long long pos = p0 + i;
-                const int b = (int)(pos / per_scene);
-                const int p = s_idx[cc * 32 + i];
+                const int ins = in_scene0 + cc * 32 + i;   // position inside the scene
                 float v = __uint_as_float(r[i]);
                 if (a.normalize_xyz) v = __fdiv_rn(v, a.radius);
-                if (a.g_xyz != nullptr) atomicAdd(a.g_xyz + ((size_t)b * a.N + p) * 3 + e, v);
+                if (gx != nullptr) atomicAdd(gx + (size_t)s_idx[cc * 32 + i] * 3, v);
                 run += v;
-                if (((pos + 1) % a.NS) == 0 || i == 31) {   // end of this centre's run
-                  if (a.g_new_xyz != nullptr) {
-                    const long long centre = pos / a.NS;     // = b*NP + j
-                    atomicAdd(a.g_new_xyz + (size_t)centre * 3 + e, -run);
-                  }
+                if (((ins + 1) % a.NS) == 0 || i == 31) {   // end of this centre's run
+                  if (a.g_new_xyz != nullptr)
+                    atomicAdd(a.g_new_xyz + ((size_t)tile_b * a.NP + ins / a.NS) * 3 + e, -run);
                   run = 0.f;
                 }
               }
@@ -623,6 +640,7 @@ extern "C" int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *d, void *stream) {
   a.KA = (a.Kp + 31) >> 5;
   a.KAl = (d->Cout + 31) >> 5;
   a.Cout_pad = (d->Cout + 127) & ~127;
+  a.chf_shift = pow2_shift(((d->Cin - 3 + 3) & ~3) >> 2);
   a.do_dgrad = a.do_wgrad = 1;
   a.num_tiles = 0;
   int need_dgrad;
@@ -640,6 +658,11 @@ extern "C" int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *d, void *stream) {
   B2R_REQUIRE(!need_dgrad || d->w_image_t != nullptr,
               "b2r_sa_layer_bwd: null transposed weight image");
   const long long M = (long long)d->B * d->NP * d->NS;
+  if (d->mode == 0 && ((long long)d->NP * d->NS) % 64 != 0) {
+    set_error("b2r_sa_layer_bwd: gather layers need NP*NS %% 64 == 0 (got %lld)",
+              (long long)d->NP * d->NS);
+    return B2R_ERR_UNSUPPORTED;
+  }
   if (a.Cout_pad > 256 || (d->Cout % 8) != 0 || (M % 32) != 0) {
     set_error("b2r_sa_layer_bwd: needs Cout %% 8 == 0, Cout <= 256, B*NP*NS %% 32 == 0 "
               "(Cout=%d, M=%lld)", d->Cout, M);

@@ -46,6 +46,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
+// Ask the L2 to fetch a contiguous block ahead of use (one instruction, no registers, no smem):
+// issued by one thread for the NEXT tile while the current one is being processed.
+__device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -129,6 +134,90 @@ __host__ __device__ inline int packed_k(int Cin, int gather) {
   if (!gather) return (Cin + 3) & ~3;
   const int C = Cin - 3;
   return ((C + 3) & ~3) + 4;
+}
+
+// ------------------------------------------------------------------ gathered operand tile --
+// Layer-0 input rows of one tile, built on the fly (the reference's QueryAndGroup tail,
+// pointnet2_utils.py:347-366): packed row = [feature channels (padded to a multiple of 4),
+// (xyz[idx] - new_xyz) (/ radius), 0].  All NT positions of a tile lie in ONE scene `b` (the host
+// guarantees NP*NS % NT == 0), so no per-element 64-bit division is needed; feature loads are
+// issued in batches of 8 independent 16-byte requests per thread.
+struct GatherSrc {
+  const float *xyz, *new_xyz, *feat_t;
+  int N, NP, NS, C, Cf4;
+  int chf_shift;   // log2(Cf4/4) when that is a power of two, else -1
+  float radius;
+  int normalize_xyz;
+};
+
+template <int NT, class OffFn>
+__device__ __forceinline__ void build_x_gather(const GatherSrc &g, int b, int in_scene0,
+                                               const int *s_idx, uint8_t *s_x, int tid,
+                                               OffFn off) {
+  const int C = g.C, CHf = g.Cf4 >> 2;
+  // relative xyz chunk: one thread per row, six independent loads
+  for (int row = tid; row < NT; row += kMlpThreads) {
+    const int p = s_idx[row];
+    const int j = (in_scene0 + row) / g.NS;
+    const float *pp = g.xyz + ((size_t)b * g.N + p) * 3;
+    const float *qq = g.new_xyz + ((size_t)b * g.NP + j) * 3;
+    const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+    const float qx = __ldg(qq), qy = __ldg(qq + 1), qz = __ldg(qq + 2);
+    float d0 = __fsub_rn(px, qx), d1 = __fsub_rn(py, qy), d2 = __fsub_rn(pz, qz);
+    if (g.normalize_xyz) {
+      d0 = __fdiv_rn(d0, g.radius);
+      d1 = __fdiv_rn(d1, g.radius);
+      d2 = __fdiv_rn(d2, g.radius);
+    }
+    *reinterpret_cast<uint4 *>(s_x + off(row, CHf)) =
+        make_uint4(to_tf32(d0), to_tf32(d1), to_tf32(d2), 0u);
+  }
+  if (CHf == 0) return;
+  const float *fb = g.feat_t + (size_t)b * g.N * C;
+  const int total = NT * CHf;
+  if ((C & 3) == 0) {
+    for (int i0 = tid; i0 < total; i0 += kMlpThreads * 8) {
+      float4 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * kMlpThreads;
+        if (i < total) {
+          const int row = g.chf_shift >= 0 ? (i >> g.chf_shift) : (i / CHf);
+          const int ch = i - row * CHf;
+          t[u] = __ldg(reinterpret_cast<const float4 *>(fb + (size_t)s_idx[row] * C) + ch);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * kMlpThreads;
+        if (i < total) {
+          const int row = g.chf_shift >= 0 ? (i >> g.chf_shift) : (i / CHf);
+          const int ch = i - row * CHf;
+          *reinterpret_cast<uint4 *>(s_x + off(row, ch)) =
+              make_uint4(to_tf32(t[u].x), to_tf32(t[u].y), to_tf32(t[u].z), to_tf32(t[u].w));
+        }
+      }
+    }
+  } else {
+    for (int i = tid; i < total; i += kMlpThreads) {
+      const int row = g.chf_shift >= 0 ? (i >> g.chf_shift) : (i / CHf);
+      const int ch = i - row * CHf;
+      const float *src = fb + (size_t)s_idx[row] * C + ch * 4;
+      float f[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (ch * 4 + e < C) f[e] = __ldg(src + e);
+      *reinterpret_cast<uint4 *>(s_x + off(row, ch)) =
+          make_uint4(to_tf32(f[0]), to_tf32(f[1]), to_tf32(f[2]), to_tf32(f[3]));
+    }
+  }
+}
+
+inline int pow2_shift(int v) {   // log2(v) if v is a power of two (v >= 1), else -1
+  if (v < 1 || (v & (v - 1))) return -1;
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return s;
 }
 
 }  // namespace mlp

@@ -56,7 +56,7 @@ def supported(mlp_module, xyz, features, idx, pooling="max"):
     if pooling != "max" or not xyz.is_cuda:
         return False
     B, NP, NS = idx.shape
-    if NS not in (16, 32, 64) or (B * NP * NS) % 128 != 0:
+    if NS not in (16, 32, 64) or (NP * NS) % 128 != 0:
         return False
     blocks = list(mlp_module)
     if len(blocks) == 0:
@@ -77,6 +77,35 @@ def supported(mlp_module, xyz, features, idx, pooling="max"):
                 _layer_smem(cin, cout, gather=(i == 0), nt=128) > 227 * 1024:
             return False
     return True
+
+
+def _fwd_bytes(B, N, NP, NS, Cin, Cout, gather, pooled):
+    """ALGORITHMIC HBM bytes of one b2r_sa_layer_fwd launch (DESIGN.md "Kernels"): inputs read
+    once, outputs written once, weights ignored.  Gather layers read every source row at most
+    once (min(unique rows, gathered rows)) + the indices; dense layers read z_prev; epilogue 0/2
+    write (M,Cout), the pooling epilogue writes max/min + their indices per (centre, channel)."""
+    M = B * NP * NS
+    if gather:
+        rd = 4 * M + min(B * N, M) * 4 * Cin + 12 * B * NP
+    else:
+        rd = 4 * M * Cin
+    wr = 16 * B * NP * Cout if pooled else 4 * M * Cout
+    return rd + wr
+
+
+def _bwd_bytes(B, N, NP, NS, Cin, Cout, gather, direct, dgrad):
+    """ALGORITHMIC HBM bytes of one b2r_sa_layer_bwd launch: dz (or gr and z) read once, the
+    layer input read once, gr_prev written once (dense) / the scatter target read-modify-written
+    (gather layer with dgrad)."""
+    M = B * NP * NS
+    rd = 4 * M * Cout * (1 if direct else 2)
+    if gather:
+        rd += 4 * M + min(B * N, M) * 4 * Cin + 12 * B * NP
+        wr = 2 * min(B * N, M) * 4 * Cin if dgrad else 0
+    else:
+        rd += 4 * M * Cin
+        wr = 4 * M * Cin
+    return rd + wr
 
 
 def _layer_smem(cin, cout, gather, nt):
@@ -133,8 +162,8 @@ def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
             z = torch.empty((M, Cout), dtype=torch.float32, device=dev)
             d.z = _ptr(z)
         d.stats = _ptr(stats)
-        _lib.check(lib.b2r_sa_layer_fwd(ctypes.byref(d), st), "sa_layer_fwd")
-        _ext.LAUNCHES += 1
+        with _ext._timed("sa_layer_fwd", _fwd_bytes(B, N, NP, NS, Cin, Cout, i == 0, last)):
+            _lib.check(lib.b2r_sa_layer_fwd(ctypes.byref(d), st), "sa_layer_fwd")
         # BatchNorm scale / shift of THIS layer (applied by the next layer's prologue / finalize)
         if training:
             scale = torch.empty(Cout, dtype=torch.float32, device=dev)
@@ -231,8 +260,9 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
     d.dysel, d.asel = _ptr(dysel), _ptr(asel)
     d.bw_k1, d.bw_k2, d.bw_mean, d.bw_invstd, d.bw_gs = _ptr(k1), _ptr(k2), _ptr(mean), _ptr(invstd), _ptr(gs)
     d.dz = _ptr(dz_top)
-    _lib.check(lib.b2r_sa_layer_fwd(ctypes.byref(d), st), "sa_layer_fwd(epilogue 2)")
-    _ext.LAUNCHES += 3
+    with _ext._timed("sa_layer_fwd", _fwd_bytes(B, N, NP, NS, d.Cin, Ct, top == 0, False)):
+        _lib.check(lib.b2r_sa_layer_fwd(ctypes.byref(d), st), "sa_layer_fwd(epilogue 2)")
+    _ext.LAUNCHES += 2
 
     g_feat_t = g_xyz = g_new_xyz = None
     gr = coef = None
@@ -270,8 +300,9 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
             b.gr_prev, b.stats_prev = _ptr(gr_prev), _ptr(stats_prev)
         image_t = pack_weight_t(weights[l], gather=(l == 0)) if need_dgrad else None
         b.w_image_t = _ptr(image_t)
-        _lib.check(lib.b2r_sa_layer_bwd(ctypes.byref(b), st), "sa_layer_bwd")
-        _ext.LAUNCHES += 1
+        with _ext._timed("sa_layer_bwd", _bwd_bytes(B, N, NP, NS, Cin, Cout, l == 0, l == top,
+                                                    need_dgrad)):
+            _lib.check(lib.b2r_sa_layer_bwd(ctypes.byref(b), st), "sa_layer_bwd")
         if l > 0:
             mean, invstd, _, _ = bn[l - 1]
             coef = [torch.empty(Cin, **f32) for _ in range(3)]
