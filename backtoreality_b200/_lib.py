@@ -71,7 +71,8 @@ class SaLayerBwd(ctypes.Structure):
         ("xyz", _vp), ("new_xyz", _vp), ("feat_t", _vp), ("idx", _vp),
         ("radius", _f), ("normalize_xyz", _i),
         ("z_prev", _vp), ("scale_prev", _vp), ("shift_prev", _vp),
-        ("w_image_t", _vp), ("dz", _vp), ("gr", _vp), ("z", _vp),
+        ("w_image_bf16", _vp), ("dz", _vp), ("gr", _vp), ("z", _vp),
+        ("dysel", _vp), ("asel", _vp),
         ("coef_a", _vp), ("coef_b", _vp), ("coef_c", _vp),
         ("dW", _vp), ("gr_prev", _vp), ("stats_prev", _vp),
         ("g_feat_t", _vp), ("g_xyz", _vp), ("g_new_xyz", _vp),
@@ -79,14 +80,14 @@ class SaLayerBwd(ctypes.Structure):
 
 
 SIGNATURES.update({
-    "b2r_mlp_weight_t_image_bytes": [_i, _i, _i],
-    "b2r_mlp_pack_weight_t": [_vp, _i, _i, _i, _vp, _vp],
+    "b2r_mlp_weight_bf16_image_bytes": [_i, _i, _i],
+    "b2r_mlp_pack_weight_bf16": [_vp, _i, _i, _i, _vp, _vp],
     "b2r_sa_layer_bwd": [ctypes.POINTER(SaLayerBwd), _vp],
     "b2r_pool_bwd_prep": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp],
     "b2r_bn_bwd_finalize": [_vp, _i, ctypes.c_double, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp,
                             _vp, _vp, _vp, _vp],
 })
-_RESTYPES["b2r_mlp_weight_t_image_bytes"] = ctypes.c_longlong
+_RESTYPES["b2r_mlp_weight_bf16_image_bytes"] = ctypes.c_longlong
 
 _lib = None
 

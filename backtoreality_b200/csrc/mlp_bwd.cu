@@ -2,473 +2,630 @@
 //
 // Replaces, for one [1x1 conv -> BatchNorm2d -> ReLU] layer l inside PointnetSAModuleVotes
 // (reference pointnet2_modules.py:245-267 / pytorch_utils.py:11-36,67-120), what autograd runs as
-//   threshold_backward (ReLU) -> cudnn bn_bw -> cuDNN dgrad conv -> cuDNN wgrad conv
-//   (+ for layer 0: cat backward, div/sub backward, two group_points_grad scatter kernels)
-// i.e. ~8 full passes over (B, C, npoint, nsample) tensors, by ONE persistent kernel:
+//   max_pool2d backward (top layer) -> threshold_backward (ReLU) -> cudnn bn_bw -> cuDNN dgrad conv
+//   -> cuDNN wgrad conv (+ for layer 0: cat / div / sub backward and two group_points_grad
+//   scatters, _ext_src/src/group_points_gpu.cu:48-69)
+// i.e. ~8 full passes over (B, C, npoint, nsample) tensors, by ONE persistent, warp-specialised
+// kernel per layer.  Per tile of NT positions:
 //
-//   prologue  per tile of NT positions, build in 128B-swizzled shared memory
-//               DZ[pos, co] = a[co]*gr[pos,co] + b[co]*z[pos,co] + c[co]        (BatchNorm backward:
-//                             a = gamma*invstd, b = -a*k2*invstd, c = -a*k1 - b*mean, from
-//                             b2r_bn_bwd_finalize; or a precomputed dz for the pooled top layer)
-//               X[pos, k]   = the layer's input, RECOMPUTED exactly like the forward prologue
-//                             (gathered rows, or relu(bn(z_prev)))
-//   MMA       dgrad  D2[k, pos]  = sum_co W[co,k] * DZ[pos,co]      fresh per tile
-//             wgrad  D3[co, k]  += sum_pos DZ[pos,co] * X[pos,k]    accumulated in TMEM over ALL tiles
-//             wgrad contracts over POSITIONS, i.e. it needs both tiles "transposed".  tcgen05 can
-//             read an operand MN-major straight from shared memory, but for 32-bit (TF32) data
-//             only in the SWIZZLE_128B_BASE32B layout (128 B of MN x 4 K rows per atom, 32-byte
-//             chunks XOR-swizzled with the row) -- measured with scripts/probe/umma_probe.cu,
-//             profiles/r01/umma_probe_tf32_operand_layouts.log: the plain SW128 / no-swizzle
-//             MN-major views of TF32 data give wrong products.  So the prologue writes DZ twice
-//             (K-major SW128 for dgrad, BASE32B for wgrad) and X once (BASE32B); no data is ever
-//             transposed through registers or re-read from HBM.  dgrad's A operand is a K-major
-//             image of W^T packed once per step by b2r_mlp_pack_weight_t.
-//   epilogue  dense layers: gr_prev = D2 * [relu(bn(z_prev)) > 0] stored position-major, plus the
-//             per-channel sums  sum(gr_prev), sum(gr_prev * z_prev)  the next (lower) layer's
-//             BatchNorm backward needs -- fused so gr_prev is written once and never re-read for
-//             statistics;  gather layer: D2 rows are scatter-added (red.global.add.f32) straight
-//             into the POINT-major feature gradient (B,N,C) / xyz gradients: the
-//             (B,3+C,npoint,nsample) gradient tensor never exists.
-//   end       D3 -> atomicAdd into dW (Cout x Cin, the nn.Conv2d layout).
+//   X[pos, k]    the layer's input, RECOMPUTED like the forward prologue (gathered rows, or
+//                relu(bn(z_prev)))                                            -> smem, BF16
+//   DZ[pos, co]  = a[co]*g + b[co]*z[pos,co] + c[co]   (BatchNorm backward; a,b,c from
+//                b2r_bn_bwd_finalize).  Dense layers: g = gr and z are read from HBM.  Pooled top
+//                layer: z is RECOMPUTED on the tensor cores (D1 = W X^T, never stored by the
+//                forward) and g is the max-pool-routed output gradient, non-zero at ONE sample
+//                per (centre, channel)                                          -> smem, BF16
+//   dgrad        D2[k, pos]  = sum_co W[co,k] DZ[pos,co]                 TMEM, fresh per tile
+//   wgrad        D3[co, k]  += sum_pos DZ[pos,co] X[pos,k]               TMEM, accumulated over
+//                                                                        ALL tiles of the CTA
+//   epilogue     dense: gr_prev = D2 * [relu(bn(z_prev)) > 0] + the next BatchNorm-backward sums;
+//                gather layer: D2 scatter-added (red.global.add.f32) into the POINT-major feature
+//                / xyz / centre gradients.  End of kernel: D3 -> atomicAdd into dW (Cout, Cin).
+//
+// Operands are BF16 (FP32 accumulate).  Every tile lives in shared memory ONCE, in the K-major
+// 128B-swizzled layout; wgrad, which contracts over positions, reads the SAME bytes through
+// MN-major descriptors, and dgrad reads the forward-oriented weight image MN-major as W^T.
+// (For 32-bit TF32 data the MN-major view needs a different byte layout -- SWIZZLE_128B_BASE32B --
+// hence a second copy of every tile; both facts measured with scripts/probe/umma_probe*.cu, logs
+// under profiles/r01/.  The first version of this kernel was TF32 with doubled tiles: it could
+// not double-buffer the 128->256 layers in 227 KB.)  BF16 operand rounding (2^-9) adds ~3e-3 to a
+// gradient whose TF32-forward noise floor is 3-4e-2 (profiles/r01/tf32_gradient_noise*.log).
+//
+// Warp roles (12 warps): 0-3 epilogue (one TMEM lane quadrant each), 4 MMA issue (one thread),
+// 5-11 producers (global loads -> transform -> swizzled smem).  Two smem stages and two TMEM
+// stages for D1/D2, mbarrier hand-offs (full / empty / z_done / dz_ready / mma_done / d2_free):
+// producers run up to two tiles ahead of the tensor core, stores and scatters trail behind.
+#include <cuda_bf16.h>
+
 #include "mlp_common.cuh"
 
 namespace b2r {
 using namespace mlp;
 namespace {
 
+constexpr int kEpiWarps = 4, kProdWarps = 7;   // 12 warps = 3 per SM sub-partition -> 168 regs
+constexpr int kEpiThreads = kEpiWarps * 32, kProdThreads = kProdWarps * 32;
+constexpr int kBwdThreads = kEpiThreads + 32 + kProdThreads;   // 384
+
 struct BwdArgs {
-  int B, N, NP, NS, Cin, Cout, mode;
+  int B, N, NP, NS, Cin, Cout, mode, top;
   const float *xyz, *new_xyz, *feat_t;
   const int *idx;
   float radius;
   int normalize_xyz;
   const float *z_prev, *scale_prev, *shift_prev;
-  const float *w_image;
+  const void *w_image;                          // BF16 image from b2r_mlp_pack_weight_bf16
   const float *dz;                              // direct dz (M,Cout), or NULL and:
-  const float *gr, *z, *coef_a, *coef_b, *coef_c;
+  const float *gr, *z;                          //   dense: (M,Cout) each
+  const float *dysel;                           //   top:   (B*NP,Cout)
+  const int *asel;                              //   top:   (B*NP,Cout)
+  const float *coef_a, *coef_b, *coef_c;        // (Cout)
   float *dW;
   float *gr_prev;
   double *stats_prev;
   float *g_feat_t, *g_xyz, *g_new_xyz;
-  int do_dgrad, do_wgrad;
-  int Kp, KA, KAl, Cout_pad, num_tiles;   // KA: 32-wide atoms of packed K, KAl: of Cout
-  int chf_shift;
+  int do_dgrad;
+  int Kp, KA, WA, Cout_pad, num_tiles;   // KA: 64-wide atoms of packed K; WA: atoms in the image
+  int ch8_shift;                         // log2(feature 16-byte chunks per row) or -1
+  int ns_shift;                          // log2(NS) or -1
 };
 
-// Shared-memory carve-up (host + device agree through this one function).
+// packed K extent of a layer in THIS kernel's operand order: gather layers put the C feature
+// channels first (padded to a multiple of 8 = one 16-byte BF16 chunk), then dx,dy,dz and 5 zeros
+__host__ __device__ inline int packed_k16(int Cin, int gather) {
+  if (!gather) return (Cin + 7) & ~7;
+  return ((Cin - 3 + 7) & ~7) + 8;
+}
+
 struct BwdSmem {
-  uint32_t w_off, x_off, dzk_off, dz32_off, coef_off, scale_off, idx_off, bar_off, total;
-  uint32_t w_bytes, x_bytes, dzk_bytes, dz32_bytes;
+  uint32_t w_off, w_bytes, x_off[2], dz_off[2], x_bytes, dz_bytes, coef_off, scale_off, idx_off,
+      bar_off, total;
 };
-__host__ __device__ inline BwdSmem bwd_smem_layout(int Kp, int KA, int Cout, int Cout_pad, int NT,
-                                                   int do_dgrad, int do_wgrad, int has_coef) {
+__host__ __device__ inline BwdSmem bwd_smem_layout(int Kp, int KA, int WA, int Cout, int Cout_pad,
+                                                   int NT) {
   BwdSmem s;
-  const uint32_t KAl = (uint32_t)(Cout + 31) >> 5;
-  const uint32_t mt_p = (uint32_t)(KA + 3) >> 2;
-  s.w_bytes = do_dgrad ? mt_p * 128u * KAl * 128u : 0u;        // W^T image: (packed K rows, Cout)
-  s.x_bytes = do_wgrad ? (uint32_t)NT * KA * 128u : 0u;         // X, BASE32B
-  s.dzk_bytes = do_dgrad ? (uint32_t)NT * KAl * 128u : 0u;      // DZ, K-major SW128
-  s.dz32_bytes = do_wgrad ? (uint32_t)NT * (Cout_pad >> 5) * 128u : 0u;   // DZ, BASE32B
   s.w_off = 0;
-  s.x_off = s.w_off + s.w_bytes;
-  s.dzk_off = s.x_off + s.x_bytes;
-  s.dz32_off = s.dzk_off + s.dzk_bytes;
-  s.coef_off = s.dz32_off + s.dz32_bytes;
-  s.scale_off = s.coef_off + (has_coef ? 3u * Cout * 4u : 0u);
+  s.w_bytes = (uint32_t)Cout_pad * WA * 128u;
+  s.x_bytes = (uint32_t)NT * KA * 128u;
+  s.dz_bytes = (uint32_t)NT * (Cout_pad >> 6) * 128u;
+  uint32_t o = s.w_bytes;
+  for (int st = 0; st < 2; ++st) {
+    s.x_off[st] = o;
+    o += s.x_bytes;
+    s.dz_off[st] = o;
+    o += s.dz_bytes;
+  }
+  s.coef_off = o;
+  s.scale_off = s.coef_off + 3u * Cout * 4u;
   s.idx_off = s.scale_off + 2u * Kp * 4u;
-  s.bar_off = (s.idx_off + 2u * (uint32_t)NT * 4u + 15u) & ~15u;   // idx double-buffered
-  s.total = s.bar_off + 2 * 8 + 16 + 1024;  // + alignment slack
+  s.bar_off = (s.idx_off + 4u * (uint32_t)NT * 4u + 15u) & ~15u;   // idx: 4 buffers (below)
+  s.total = s.bar_off + 12 * 8 + 16 + 1024;                        // + alignment slack
   return s;
 }
 
-// byte offset of 16-byte chunk `chunk` (4 consecutive channels) of position `pos` inside an
-// MN-major SWIZZLE_128B_BASE32B tile of NT positions: 32-channel atoms NT*128 B apart; inside
-// an atom 4-position groups of 512 B, one 128 B row per position, 32 B chunk index XOR (pos & 3)
-__device__ __forceinline__ uint32_t t32_off(int pos, int chunk, int NT) {
-  const int at = chunk >> 3, c8 = (chunk >> 1) & 3, half = chunk & 1;
-  return (uint32_t)(at * NT * 128 + ((pos >> 2) << 9) + ((pos & 3) << 7) + ((c8 ^ (pos & 3)) << 5) +
-                    (half << 4));
+// byte offset of 16-byte chunk `chunk` (8 consecutive BF16 channels) of row `row` in a K-major
+// SW128 BF16 operand with `rows` rows: 64-channel atoms, then 8-row groups of 1024 B
+__device__ __forceinline__ uint32_t bf_off(int row, int chunk, int rows) {
+  const int a = chunk >> 3, c = chunk & 7, g = row >> 3, r8 = row & 7;
+  return (uint32_t)(((a * (rows >> 3) + g) << 10) + (r8 << 7) + ((c ^ r8) << 4));
 }
-__device__ __forceinline__ uint64_t smem_desc_t32(uint32_t saddr, uint32_t lbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3fffu);
-  d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;   // stride between 32-channel MN atoms
-  d |= (uint64_t)(512u >> 4) << 32;              // stride between 4-position K groups
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)1 << 61;                        // SWIZZLE_128B_BASE32B
-  return d;
+// kind::f16 instruction descriptor: BF16 x BF16 -> F32, M = 128, N = n
+__host__ __device__ constexpr uint32_t idesc_bf16(int n, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t *>(&v);
+}
+__device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads)); }
+__device__ __forceinline__ void bar_prod() { asm volatile("bar.sync 2, %0;" ::"n"(kProdThreads)); }
 
-// W (Cout, Cin) -> K-major SW128 image of W^T: rows = packed K (gather order, padded to whole
-// 128-row M tiles), contraction dimension = Cout (padded to 32-element atoms), TF32-rounded
-__global__ void pack_weight_t_kernel(const float *__restrict__ w, int Cout, int Cin, int gather,
-                                     int Kp, int rows_t, int KAl, float *__restrict__ image) {
-  const long long total = (long long)rows_t * KAl * 32;
+// W (Cout, Cin) fp32 -> BF16 K-major SW128 image, rows = Cout (padded to 128), contraction
+// dimension = packed K (this kernel's order), WA 64-wide atoms (zero padded)
+__global__ void pack_weight_bf16_kernel(const float *__restrict__ w, int Cout, int Cin, int gather,
+                                        int Kp, int Cout_pad, int WA,
+                                        __nv_bfloat16 *__restrict__ image) {
+  const long long total = (long long)Cout_pad * WA * 64;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
-    const int kp = (int)(e / (KAl * 32)), co = (int)(e % (KAl * 32));
+    const int co = (int)(e / (WA * 64)), kp = (int)(e % (WA * 64));
     float v = 0.f;
-    if (kp < Kp && co < Cout) {
+    if (co < Cout && kp < Kp) {
       int k = -1;
       if (gather) {
-        const int C = Cin - 3, Cf4 = (C + 3) & ~3;
+        const int C = Cin - 3, Cf8 = (C + 7) & ~7;
         if (kp < C) k = 3 + kp;
-        else if (kp >= Cf4 && kp < Cf4 + 3) k = kp - Cf4;
+        else if (kp >= Cf8 && kp < Cf8 + 3) k = kp - Cf8;
       } else if (kp < Cin) {
         k = kp;
       }
-      if (k >= 0) v = __uint_as_float(to_tf32(w[(size_t)co * Cin + k]));
+      if (k >= 0) v = w[(size_t)co * Cin + k];
     }
-    image[(sw128_off(kp, co >> 2, rows_t) + (co & 3) * 4) >> 2] = v;
+    image[(bf_off(co, kp >> 3, Cout_pad) >> 1) + (kp & 7)] = __float2bfloat16_rn(v);
   }
 }
 
 template <int NT>
-__global__ void __launch_bounds__(kMlpThreads, 1) sa_layer_bwd_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~(uintptr_t)1023);
-  const bool has_coef = a.dz == nullptr;
-  const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.Cout, a.Cout_pad, NT, a.do_dgrad, a.do_wgrad,
-                                    has_coef);
+  const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, NT);
   uint8_t *s_w = base + L.w_off;
-  uint8_t *s_x = base + L.x_off;
-  uint8_t *s_dzk = base + L.dzk_off;
-  uint8_t *s_dz32 = base + L.dz32_off;
   float *s_ca = reinterpret_cast<float *>(base + L.coef_off);
   float *s_cb = s_ca + a.Cout;
   float *s_cc = s_cb + a.Cout;
   float *s_scale = reinterpret_cast<float *>(base + L.scale_off);
   float *s_shift = s_scale + a.Kp;
-  int *s_idx2 = reinterpret_cast<int *>(base + L.idx_off);
+  // ball-query indices per tile, 4-deep ring: the producers may write tile k while the scatter
+  // epilogue still reads tile k-3 (MMA(k-2) only waits for the epilogue of tile k-4)
+  int *s_idx4 = reinterpret_cast<int *>(base + L.idx_off);
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(base + L.bar_off);
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2);
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 13);
+  // mbarriers: [0,1] full  [2,3] empty  [4,5] z_done  [6,7] dz_ready  [8,9] mma_done
+  //            [10,11] d2_free  [12] weights
+  auto bar = [&](int i) { return smem_u32(&s_bar[i]); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, h = warp >> 2;
-  const int KA = a.KA, KAl = a.KAl;
-  const int MTp = (KA + 3) >> 2;          // 128-row M tiles of the dgrad output (packed K rows)
-  const int MTl = a.Cout_pad >> 7;        // 128-row M tiles of the wgrad output (Cout rows)
-  constexpr int NCH = NT / 32;            // 32-column chunks per dgrad M tile
-  const uint32_t bar_w = smem_u32(&s_bar[0]), bar_mma = smem_u32(&s_bar[1]);
-  const uint32_t d3_col0 = a.do_dgrad ? (uint32_t)MTp * NT : 0u;
+  const int KA = a.KA;
+  const int MTp = (KA + 1) >> 1;          // 128-row M tiles of the dgrad output (packed K rows)
+  const int MTl = a.Cout_pad >> 7;        // 128-row M tiles over Cout (recompute, wgrad)
+  constexpr int NCH = NT / 32;
+  const bool has_coef = a.dz == nullptr;
+  const int w12 = ((a.top && MTl > (a.do_dgrad ? MTp : 0)) ? MTl : (a.do_dgrad ? MTp : 0)) * NT;
+  const uint32_t d3_col0 = 2u * (uint32_t)w12;
   constexpr uint32_t kTmemCols = 512;
+  const long long per_scene = (long long)a.NP * a.NS;
+  const int C = a.Cin - 3, Cf8 = (C + 7) & ~7;   // gather layers: feature channels
 
   if (tid == 0) {
-    mbar_init(bar_w, 1);
-    mbar_init(bar_mma, 1);
+    for (int i = 0; i < 13; ++i) mbar_init(bar(i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(s_tmem), kTmemCols);
-  {  // zero the three tiles once (adjacent regions): padding chunks are never written again
-    const uint32_t zb = L.x_bytes + L.dzk_bytes + L.dz32_bytes;
-    for (uint32_t i = tid * 16; i < zb; i += kMlpThreads * 16)
-      *reinterpret_cast<uint4 *>(s_x + i) = make_uint4(0, 0, 0, 0);
+  if (warp == 4) tmem_alloc(smem_u32(s_tmem), kTmemCols);
+  {  // zero both stages of both tiles once: padding chunks are never written again
+    const uint32_t zb = 2u * (L.x_bytes + L.dz_bytes);
+    for (uint32_t i = tid * 16; i < zb; i += kBwdThreads * 16)
+      *reinterpret_cast<uint4 *>(base + L.x_off[0] + i) = make_uint4(0, 0, 0, 0);
   }
   if (a.mode == 1)
-    for (int i = tid; i < a.Cin; i += kMlpThreads) {
+    for (int i = tid; i < a.Cin; i += kBwdThreads) {
       s_scale[i] = a.scale_prev[i];
       s_shift[i] = a.shift_prev[i];
     }
   if (has_coef)
-    for (int i = tid; i < a.Cout; i += kMlpThreads) {
+    for (int i = tid; i < a.Cout; i += kBwdThreads) {
       s_ca[i] = a.coef_a[i];
       s_cb[i] = a.coef_b[i];
       s_cc[i] = a.coef_c[i];
     }
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  bool w_ready = !a.do_dgrad;
-  if (tid == 0 && a.do_dgrad) {
-    mbar_expect_tx(bar_w, L.w_bytes);
-    bulk_g2s(smem_u32(s_w), a.w_image, L.w_bytes, bar_w);
+  const bool need_w = a.top || a.do_dgrad;
+  if (tid == 0 && need_w) {
+    mbar_expect_tx(bar(12), L.w_bytes);
+    bulk_g2s(smem_u32(s_w), a.w_image, L.w_bytes, bar(12));
   }
+  const int grid = (int)gridDim.x;
 
-  const long long per_scene = (long long)a.NP * a.NS;
-  const int C = a.Cin - 3, Cf4 = (C + 3) & ~3;   // gather mode: feature channels
-  GatherSrc gsrc;
-  gsrc.xyz = a.xyz; gsrc.new_xyz = a.new_xyz; gsrc.feat_t = a.feat_t;
-  gsrc.N = a.N; gsrc.NP = a.NP; gsrc.NS = a.NS; gsrc.C = C; gsrc.Cf4 = Cf4;
-  gsrc.chf_shift = a.chf_shift; gsrc.radius = a.radius; gsrc.normalize_xyz = a.normalize_xyz;
-  const int CHl = a.Cout >> 2;                   // 16-byte chunks per DZ row
-  const int KSl = (a.Cout + 7) >> 3;             // dgrad K steps (8 output channels each)
-  const uint32_t idesc_dgrad = idesc_tf32(NT);   // A = W^T image, B = DZ, both K-major
-  const uint32_t rows_t = (uint32_t)MTp * 128u;
-  const uint32_t lbo_t = (uint32_t)NT * 128u;    // BASE32B tiles: 32-channel atoms
-  uint32_t mma_parity = 0;
-  float s1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f};   // per owned channel (by M tile)
-  double d1[3] = {0.0, 0.0, 0.0}, d2[3] = {0.0, 0.0, 0.0};
-  int tile_iter = 0;
-
-  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tile_iter) {
-    const long long pos0 = (long long)tile * NT;
-    // ball-query indices of this tile, double-buffered by tile parity: the scatter epilogue of
-    // the previous tile may still be reading its copy while fast warps start this prologue
-    int *s_idx = s_idx2 + (tile_iter & 1) * NT;
-
-    // ---- prologue 1: DZ tile, written in both operand layouts ----------------------------------
-    // (loads batched 4-deep per thread; the next tile of this CTA is bulk-prefetched into L2)
-    {
-      const int total = NT * CHl;
-      const size_t o0 = (size_t)pos0 * a.Cout;
-      if (tid == 0 && tile + (int)gridDim.x < a.num_tiles) {
-        const size_t on = (size_t)(pos0 + (long long)gridDim.x * NT) * a.Cout;
-        if (!has_coef) {
-          prefetch_l2(a.dz + on, (uint32_t)total * 16u);
-        } else {
-          prefetch_l2(a.gr + on, (uint32_t)total * 16u);
-          prefetch_l2(a.z + on, (uint32_t)total * 16u);
+  if (warp > 4) {
+    // =============================== PRODUCERS (7 warps) ========================================
+    const int ptid = tid - (kEpiThreads + 32);
+    const int CH8 = a.Cout >> 3;     // 16-byte BF16 chunks per DZ row
+    for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k) {
+      const int s = k & 1, n = k >> 1;
+      mbar_wait(bar(2 + s), (uint32_t)((n & 1) ^ 1));   // MMAs of tile k-2 are done with stage s
+      const long long pos0 = (long long)tile * NT;
+      uint8_t *sx = base + L.x_off[s], *sdz = base + L.dz_off[s];
+      int *s_idx = s_idx4 + (k & 3) * NT;
+      if (ptid == 0 && tile + 2 * grid < a.num_tiles) {   // pull tile k+2 into L2 meanwhile
+        const size_t pn = (size_t)(pos0 + 2ll * grid * NT);
+        if (!a.top) {
+          if (!has_coef) prefetch_l2(a.dz + pn * a.Cout, (uint32_t)NT * a.Cout * 4u);
+          else {
+            prefetch_l2(a.gr + pn * a.Cout, (uint32_t)NT * a.Cout * 4u);
+            prefetch_l2(a.z + pn * a.Cout, (uint32_t)NT * a.Cout * 4u);
+          }
         }
-        if (a.mode == 1)
-          prefetch_l2(a.z_prev + (size_t)(pos0 + (long long)gridDim.x * NT) * a.Cin,
-                      (uint32_t)NT * a.Cin * 4u);
+        if (a.mode == 1) prefetch_l2(a.z_prev + pn * a.Cin, (uint32_t)NT * a.Cin * 4u);
       }
-      for (int i0 = tid; i0 < total; i0 += kMlpThreads * 4) {
-        float4 g[4], zz[4];
+      // ---- DZ tile from HBM (dense layers / direct dz); the top layer's DZ comes from D1 ------
+      if (!a.top) {
+        const int total = NT * CH8;
+        const size_t o0 = (size_t)pos0 * a.Cout;
+        for (int i0 = ptid; i0 < total; i0 += kProdThreads * 2) {
+          float4 g[2][2], zz[2][2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * kMlpThreads;
-          if (i < total) {
-            if (!has_coef) {
-              g[u] = __ldg(reinterpret_cast<const float4 *>(a.dz + o0) + i);
-            } else {
-              g[u] = __ldg(reinterpret_cast<const float4 *>(a.gr + o0) + i);
-              zz[u] = __ldg(reinterpret_cast<const float4 *>(a.z + o0) + i);
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * kMlpThreads;
-          if (i < total) {
-            const int row = i / CHl, ch = i - row * CHl;
-            float4 v = g[u];
-            if (has_coef) {
-              const float4 ca = *reinterpret_cast<const float4 *>(s_ca + ch * 4);
-              const float4 cb = *reinterpret_cast<const float4 *>(s_cb + ch * 4);
-              const float4 cc = *reinterpret_cast<const float4 *>(s_cc + ch * 4);
-              v.x = fmaf(ca.x, g[u].x, fmaf(cb.x, zz[u].x, cc.x));
-              v.y = fmaf(ca.y, g[u].y, fmaf(cb.y, zz[u].y, cc.y));
-              v.z = fmaf(ca.z, g[u].z, fmaf(cb.z, zz[u].z, cc.z));
-              v.w = fmaf(ca.w, g[u].w, fmaf(cb.w, zz[u].w, cc.w));
-            }
-            const uint4 out = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-            if (a.do_dgrad) *reinterpret_cast<uint4 *>(s_dzk + sw128_off(row, ch, NT)) = out;
-            if (a.do_wgrad) *reinterpret_cast<uint4 *>(s_dz32 + t32_off(row, ch, NT)) = out;
-          }
-        }
-      }
-    }
-    // ---- prologue 2: X tile (same recomputation as the forward kernel), BASE32B layout ---------
-    int tile_b = 0, in_scene0 = 0;   // gather layers: the tile's scene, first position in it
-    if (a.mode == 0) {
-      if (tid < NT) s_idx[tid] = a.idx[pos0 + tid];
-      __syncthreads();
-      tile_b = (int)(pos0 / per_scene);
-      in_scene0 = (int)(pos0 - (long long)tile_b * per_scene);
-    }
-    if (a.do_wgrad) {
-      if (a.mode == 0) {
-        build_x_gather<NT>(gsrc, tile_b, in_scene0, s_idx, s_x, tid,
-                           [](int row, int ch) { return t32_off(row, ch, NT); });
-      } else {
-        const int CH = a.Cin >> 2;
-        const int total = NT * CH;
-        const float4 *src = reinterpret_cast<const float4 *>(a.z_prev + (size_t)pos0 * a.Cin);
-        for (int i0 = tid; i0 < total; i0 += kMlpThreads * 8) {
-          float4 t[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int i = i0 + u * kMlpThreads;
-            if (i < total) t[u] = __ldg(src + i);
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int i = i0 + u * kMlpThreads;
+          for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * kProdThreads;
             if (i < total) {
-              const int row = i / CH, ch = i - row * CH;
-              const float4 sc = *reinterpret_cast<const float4 *>(s_scale + ch * 4);
-              const float4 sh = *reinterpret_cast<const float4 *>(s_shift + ch * 4);
-              uint4 out;
-              out.x = to_tf32(fmaxf(fmaf(t[u].x, sc.x, sh.x), 0.f));
-              out.y = to_tf32(fmaxf(fmaf(t[u].y, sc.y, sh.y), 0.f));
-              out.z = to_tf32(fmaxf(fmaf(t[u].z, sc.z, sh.z), 0.f));
-              out.w = to_tf32(fmaxf(fmaf(t[u].w, sc.w, sh.w), 0.f));
-              *reinterpret_cast<uint4 *>(s_x + t32_off(row, ch, NT)) = out;
+              if (!has_coef) {
+                const float4 *p = reinterpret_cast<const float4 *>(a.dz + o0) + 2 * i;
+                g[u][0] = __ldg(p); g[u][1] = __ldg(p + 1);
+              } else {
+                const float4 *p = reinterpret_cast<const float4 *>(a.gr + o0) + 2 * i;
+                const float4 *qz = reinterpret_cast<const float4 *>(a.z + o0) + 2 * i;
+                g[u][0] = __ldg(p); g[u][1] = __ldg(p + 1);
+                zz[u][0] = __ldg(qz); zz[u][1] = __ldg(qz + 1);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * kProdThreads;
+            if (i < total) {
+              const int row = i / CH8, ch = i - row * CH8;
+              float v[8] = {g[u][0].x, g[u][0].y, g[u][0].z, g[u][0].w,
+                            g[u][1].x, g[u][1].y, g[u][1].z, g[u][1].w};
+              if (has_coef) {
+                const float zv[8] = {zz[u][0].x, zz[u][0].y, zz[u][0].z, zz[u][0].w,
+                                     zz[u][1].x, zz[u][1].y, zz[u][1].z, zz[u][1].w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  v[e] = fmaf(s_ca[ch * 8 + e], v[e], fmaf(s_cb[ch * 8 + e], zv[e], s_cc[ch * 8 + e]));
+              }
+              *reinterpret_cast<uint4 *>(sdz + bf_off(row, ch, NT)) =
+                  make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                             pack_bf16(v[6], v[7]));
             }
           }
         }
       }
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-
-    // ---- MMA issue (one thread) ---------------------------------------------------------------
-    if (tid == 0) {
-      if (!w_ready) {
-        mbar_wait(bar_w, 0);
-        w_ready = true;
-      }
-      tc_fence_after();
-      const uint32_t xa = smem_u32(s_x), wa = smem_u32(s_w);
-      const uint32_t dka = smem_u32(s_dzk), d32a = smem_u32(s_dz32);
-      if (a.do_dgrad) {
-        // D2[m-tile of packed K rows, NT positions] = W^T image (K-major) * DZ (K-major)
-        for (int m = 0; m < MTp; ++m)
-          for (int ks = 0; ks < KSl; ++ks) {
-            const uint64_t adesc =
-                smem_desc_sw128(wa + (uint32_t)(ks >> 2) * 1024u * (rows_t >> 3) +
-                                (uint32_t)m * 16u * 1024u + (uint32_t)(ks & 3) * 32u);
-            const uint64_t bdesc = smem_desc_sw128(dka + (uint32_t)(ks >> 2) * 1024u * (NT >> 3) +
-                                                   (uint32_t)(ks & 3) * 32u);
-            umma_tf32(tmem_base + (uint32_t)m * NT, adesc, bdesc, idesc_dgrad, ks > 0 ? 1u : 0u);
+      // ---- X tile ---------------------------------------------------------------------------
+      if (a.mode == 0) {
+        if (ptid < NT) s_idx[ptid] = a.idx[pos0 + ptid];
+        bar_prod();
+        const int b = (int)(pos0 / per_scene);
+        const int in_scene0 = (int)(pos0 - (long long)b * per_scene);
+        const int CH8f = Cf8 >> 3;
+        for (int row = ptid; row < NT; row += kProdThreads) {   // relative xyz chunk
+          const int p = s_idx[row];
+          const int j = (in_scene0 + row) / a.NS;
+          const float *pp = a.xyz + ((size_t)b * a.N + p) * 3;
+          const float *qq = a.new_xyz + ((size_t)b * a.NP + j) * 3;
+          const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+          const float qx = __ldg(qq), qy = __ldg(qq + 1), qz = __ldg(qq + 2);
+          float d0 = __fsub_rn(px, qx), d1 = __fsub_rn(py, qy), d2 = __fsub_rn(pz, qz);
+          if (a.normalize_xyz) {
+            d0 = __fdiv_rn(d0, a.radius);
+            d1 = __fdiv_rn(d1, a.radius);
+            d2 = __fdiv_rn(d2, a.radius);
           }
-      }
-      if (a.do_wgrad) {
-        // D3[m-tile of Cout rows, packed K columns] += DZ^T * X  (both MN-major, K = positions)
-        for (int ml = 0; ml < MTl; ++ml)
-          for (int a0 = 0; a0 < KA; a0 += 8) {
-            const int na = (KA - a0) < 8 ? (KA - a0) : 8;
-            const uint32_t idesc_w = idesc_tf32_ex(na * 32, 1, 1);
-            for (int k8 = 0; k8 < NT / 8; ++k8) {
-              const uint64_t adesc = smem_desc_t32(
-                  d32a + (uint32_t)(4 * ml) * lbo_t + (uint32_t)k8 * 1024u, lbo_t);
-              const uint64_t bdesc =
-                  smem_desc_t32(xa + (uint32_t)a0 * lbo_t + (uint32_t)k8 * 1024u, lbo_t);
-              umma_tf32(tmem_base + d3_col0 + (uint32_t)(ml * KA + a0) * 32u, adesc, bdesc,
-                        idesc_w, (tile_iter > 0 || k8 > 0) ? 1u : 0u);
-            }
-          }
-      }
-      umma_commit(bar_mma);
-    }
-
-    // ---- epilogue: dgrad accumulator -> masked gradient + statistics, or scatter ---------------
-    mbar_wait(bar_mma, mma_parity);
-    mma_parity ^= 1u;
-    tc_fence_after();
-    if (a.do_dgrad) {
+          *reinterpret_cast<uint4 *>(sx + bf_off(row, CH8f, NT)) =
+              make_uint4(pack_bf16(d0, d1), pack_bf16(d2, 0.f), 0u, 0u);
+        }
+        if (CH8f > 0) {
+          const float *fb = a.feat_t + (size_t)b * a.N * C;
+          const int total = NT * CH8f;
+          if ((C & 7) == 0) {
+            for (int i0 = ptid; i0 < total; i0 += kProdThreads * 4) {
+              float4 t[4][2];
 #pragma unroll
-      for (int m = 0; m < 3; ++m) {
-#pragma unroll
-        for (int cc = 0; cc < NCH; ++cc) {
-          if (m >= MTp || ((m * NCH + cc) & 1) != h) continue;
-          uint32_t r[32];
-          cuda::ptx::tcgen05_ld_32x32b(
-              r, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * NT + cc * 32));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const int kp = m * 128 + q * 32 + lane;   // packed K row owned by this thread
-          const long long p0 = pos0 + cc * 32;
-          if (a.mode == 1) {
-            if (kp < a.Cin) {
-              const float sc = s_scale[kp], sh = s_shift[kp];
-              const float *zp = a.z_prev + (size_t)p0 * a.Cin + kp;
-              float *gp = a.gr_prev + (size_t)p0 * a.Cin + kp;
-              float t1 = 0.f, t2 = 0.f;
-              float zv[32];   // all 32 (L2-resident) loads in flight before the first store
-#pragma unroll
-              for (int i = 0; i < 32; ++i) zv[i] = __ldg(zp + (size_t)i * a.Cin);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float g = fmaf(zv[i], sc, sh) > 0.f ? __uint_as_float(r[i]) : 0.f;
-                gp[(size_t)i * a.Cin] = g;
-                t1 += g;
-                t2 = fmaf(g, zv[i], t2);
+              for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kProdThreads;
+                if (i < total) {
+                  const int row = a.ch8_shift >= 0 ? (i >> a.ch8_shift) : (i / CH8f);
+                  const int ch = i - row * CH8f;
+                  const float4 *p =
+                      reinterpret_cast<const float4 *>(fb + (size_t)s_idx[row] * C) + 2 * ch;
+                  t[u][0] = __ldg(p); t[u][1] = __ldg(p + 1);
+                }
               }
-              s1[m] += t1;
-              s2[m] += t2;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kProdThreads;
+                if (i < total) {
+                  const int row = a.ch8_shift >= 0 ? (i >> a.ch8_shift) : (i / CH8f);
+                  const int ch = i - row * CH8f;
+                  *reinterpret_cast<uint4 *>(sx + bf_off(row, ch, NT)) =
+                      make_uint4(pack_bf16(t[u][0].x, t[u][0].y), pack_bf16(t[u][0].z, t[u][0].w),
+                                 pack_bf16(t[u][1].x, t[u][1].y), pack_bf16(t[u][1].z, t[u][1].w));
+                }
+              }
             }
           } else {
-            // gather layer: scatter-add into the point-major feature / xyz gradients
-            const bool is_feat = kp < C;
-            const int e = kp - Cf4;                 // 0..2 for dx,dy,dz rows
-            const bool is_xyz = (e >= 0 && e < 3);
-            if (is_feat && a.g_feat_t != nullptr) {
-              float *gb = a.g_feat_t + (size_t)tile_b * a.N * C + kp;
+            for (int i = ptid; i < total; i += kProdThreads) {
+              const int row = i / CH8f, ch = i - row * CH8f;
+              const float *src = fb + (size_t)s_idx[row] * C + ch * 8;
+              float f[8];
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                atomicAdd(gb + (size_t)s_idx[cc * 32 + i] * C, __uint_as_float(r[i]));
-            } else if (is_xyz && (a.g_xyz != nullptr || a.g_new_xyz != nullptr)) {
-              float run = 0.f;
-              float *gx = a.g_xyz != nullptr ? a.g_xyz + (size_t)tile_b * a.N * 3 + e : nullptr;
+              for (int e = 0; e < 8; ++e) f[e] = (ch * 8 + e < C) ? __ldg(src + e) : 0.f;
+              *reinterpret_cast<uint4 *>(sx + bf_off(row, ch, NT)) =
+                  make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                             pack_bf16(f[6], f[7]));
+            }
+          }
+        }
+      } else {
+        const int CH = a.Cin >> 3;
+        const int total = NT * CH;
+        const float4 *src = reinterpret_cast<const float4 *>(a.z_prev + (size_t)pos0 * a.Cin);
+        for (int i0 = ptid; i0 < total; i0 += kProdThreads * 4) {
+          float4 t[4][2];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kProdThreads;
+            if (i < total) { t[u][0] = __ldg(src + 2 * i); t[u][1] = __ldg(src + 2 * i + 1); }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kProdThreads;
+            if (i < total) {
+              const int row = i / CH, ch = i - row * CH;
+              const float *sc = s_scale + ch * 8, *sh = s_shift + ch * 8;
+              const float x0 = fmaxf(fmaf(t[u][0].x, sc[0], sh[0]), 0.f);
+              const float x1 = fmaxf(fmaf(t[u][0].y, sc[1], sh[1]), 0.f);
+              const float x2 = fmaxf(fmaf(t[u][0].z, sc[2], sh[2]), 0.f);
+              const float x3 = fmaxf(fmaf(t[u][0].w, sc[3], sh[3]), 0.f);
+              const float x4 = fmaxf(fmaf(t[u][1].x, sc[4], sh[4]), 0.f);
+              const float x5 = fmaxf(fmaf(t[u][1].y, sc[5], sh[5]), 0.f);
+              const float x6 = fmaxf(fmaf(t[u][1].z, sc[6], sh[6]), 0.f);
+              const float x7 = fmaxf(fmaf(t[u][1].w, sc[7], sh[7]), 0.f);
+              *reinterpret_cast<uint4 *>(sx + bf_off(row, ch, NT)) =
+                  make_uint4(pack_bf16(x0, x1), pack_bf16(x2, x3), pack_bf16(x4, x5),
+                             pack_bf16(x6, x7));
+            }
+          }
+        }
+      }
+      fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+      bar_prod();
+      if (ptid == 0) mbar_arrive(bar(0 + s));
+    }
+  } else if (warp == 4) {
+    // =============================== MMA ISSUE (one thread) =====================================
+    if (lane == 0) {
+      if (need_w) mbar_wait(bar(12), 0);
+      const uint32_t wa = smem_u32(s_w);
+      const uint32_t lbo_w = (uint32_t)(a.Cout_pad >> 3) * 1024u;   // 64-wide K atoms of the image
+      const uint32_t lbo_t = (uint32_t)(NT >> 3) * 1024u;           // 64-wide atoms of the tiles
+      const int KS16 = (a.Kp + 15) >> 4, KSl16 = (a.Cout + 15) >> 4;
+      for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k) {
+        const int s = k & 1, n = k >> 1;
+        const uint32_t xa = smem_u32(base + L.x_off[s]), dza = smem_u32(base + L.dz_off[s]);
+        const uint32_t d12 = tmem_base + (uint32_t)(s * w12);
+        mbar_wait(bar(0 + s), (uint32_t)(n & 1));           // X (and DZ) of tile k are in smem
+        mbar_wait(bar(10 + s), (uint32_t)((n & 1) ^ 1));    // epilogue of tile k-2 left D1/D2[s]
+        tc_fence_after();
+        if (a.top) {
+          // D1[co, pos] = W (K-major) * X (K-major): the top layer's z, never stored by the forward
+          for (int ml = 0; ml < MTl; ++ml)
+            for (int ks = 0; ks < KS16; ++ks) {
+              const uint64_t ad = smem_desc_sw128(wa + (uint32_t)(ks >> 2) * lbo_w +
+                                                  (uint32_t)ml * 16u * 1024u + (uint32_t)(ks & 3) * 32u);
+              const uint64_t bd =
+                  smem_desc_sw128(xa + (uint32_t)(ks >> 2) * lbo_t + (uint32_t)(ks & 3) * 32u);
+              umma_bf16(d12 + (uint32_t)ml * NT, ad, bd, idesc_bf16(NT, 0, 0), ks > 0 ? 1u : 0u);
+            }
+          umma_commit(bar(4 + s));
+          mbar_wait(bar(6 + s), (uint32_t)(n & 1));         // epilogue warps wrote DZ from D1
+          tc_fence_after();
+        }
+        if (a.do_dgrad) {
+          // D2[k rows, pos] = W^T (the image viewed MN-major) * DZ (K-major)
+          for (int m = 0; m < MTp; ++m)
+            for (int ks = 0; ks < KSl16; ++ks) {
+              const uint64_t ad = smem_desc_sw128_mn(
+                  wa + (uint32_t)(2 * m) * lbo_w + (uint32_t)ks * 2048u, lbo_w, 1024u);
+              const uint64_t bd =
+                  smem_desc_sw128(dza + (uint32_t)(ks >> 2) * lbo_t + (uint32_t)(ks & 3) * 32u);
+              umma_bf16(d12 + (uint32_t)m * NT, ad, bd, idesc_bf16(NT, 1, 0), ks > 0 ? 1u : 0u);
+            }
+        }
+        // D3[co rows, k cols] += DZ^T * X: both tiles viewed MN-major, contraction over positions
+        for (int ml = 0; ml < MTl; ++ml)
+          for (int a0 = 0; a0 < KA; a0 += 4) {
+            const int na = (KA - a0) < 4 ? (KA - a0) : 4;
+            const uint32_t idw = idesc_bf16(na * 64, 1, 1);
+            for (int k16 = 0; k16 < NT / 16; ++k16) {
+              const uint64_t ad = smem_desc_sw128_mn(
+                  dza + (uint32_t)(2 * ml) * lbo_t + (uint32_t)k16 * 2048u, lbo_t, 1024u);
+              const uint64_t bd = smem_desc_sw128_mn(
+                  xa + (uint32_t)a0 * lbo_t + (uint32_t)k16 * 2048u, lbo_t, 1024u);
+              umma_bf16(tmem_base + d3_col0 + (uint32_t)(ml * KA + a0) * 64u, ad, bd, idw,
+                        (k > 0 || k16 > 0) ? 1u : 0u);
+            }
+          }
+        umma_commit(bar(8 + s));   // -> epilogue
+        umma_commit(bar(2 + s));   // -> producers: stage s may be overwritten
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== EPILOGUE (4 warps, one TMEM lane quadrant each) ============
+    const int q = warp;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    float s1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f};
+    double d1[3] = {0.0, 0.0, 0.0}, d2[3] = {0.0, 0.0, 0.0};
+    int ntiles = 0;
+    for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k, ++ntiles) {
+      const int s = k & 1, n = k >> 1;
+      const long long pos0 = (long long)tile * NT;
+      const uint32_t d12 = tmem_base + (uint32_t)(s * w12);
+      const int *s_idx = s_idx4 + (k & 3) * NT;
+      if (a.top) {
+        // ---- D1 (recomputed z) -> dz = a*dy_routed + b*z + c -> DZ tile (BF16) ------------------
+        uint8_t *sdz = base + L.dz_off[s];
+        const int ns_mask = a.NS - 1;                         // NS is a power of two (host check)
+        const long long centre0 = pos0 >> a.ns_shift;
+        const int base_s = (int)(pos0 & ns_mask);
+        mbar_wait(bar(4 + s), (uint32_t)(n & 1));
+        tc_fence_after();
+        for (int ml = 0; ml < MTl; ++ml) {
+          const int co = ml * 128 + q * 32 + lane;
+          const bool ok = co < a.Cout;
+          const float ca = ok ? s_ca[co] : 0.f, cb = ok ? s_cb[co] : 0.f, cc = ok ? s_cc[co] : 0.f;
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            uint32_t r[32];
+            cuda::ptx::tcgen05_ld_32x32b(r, d12 + lane_addr + (uint32_t)(ml * NT + ch * 32));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (ok) {
+              float dyv = 0.f;
+              int as = -1;
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                const int ins = in_scene0 + cc * 32 + i;   // position inside the scene
-                float v = __uint_as_float(r[i]);
-                if (a.normalize_xyz) v = __fdiv_rn(v, a.radius);
-                if (gx != nullptr) atomicAdd(gx + (size_t)s_idx[cc * 32 + i] * 3, v);
-                run += v;
-                if (((ins + 1) % a.NS) == 0 || i == 31) {   // end of this centre's run
-                  if (a.g_new_xyz != nullptr)
-                    atomicAdd(a.g_new_xyz + ((size_t)tile_b * a.NP + ins / a.NS) * 3 + e, -run);
-                  run = 0.f;
+                const int t = base_s + ch * 32 + i;          // sample position counted from the
+                const int sidx = t & ns_mask;                // first centre touching this tile
+                if (i == 0 || sidx == 0) {   // first column of a centre inside this chunk
+                  const size_t o = (size_t)(centre0 + (t >> a.ns_shift)) * a.Cout + co;
+                  dyv = __ldg(a.dysel + o);
+                  as = __ldg(a.asel + o);
+                }
+                const float dy = (sidx == as) ? dyv : 0.f;
+                const float v = fmaf(ca, dy, fmaf(cb, __uint_as_float(r[i]), cc));
+                *reinterpret_cast<__nv_bfloat16 *>(sdz + bf_off(ch * 32 + i, co >> 3, NT) +
+                                                   (co & 7) * 2) = __float2bfloat16_rn(v);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        fence_async_smem();
+        bar_epi();
+        if (tid == 0) mbar_arrive(bar(6 + s));
+      }
+      mbar_wait(bar(8 + s), (uint32_t)(n & 1));
+      tc_fence_after();
+      if (a.do_dgrad) {
+        int tile_b = 0, in_scene0 = 0;
+        if (a.mode == 0) {
+          tile_b = (int)(pos0 / per_scene);
+          in_scene0 = (int)(pos0 - (long long)tile_b * per_scene);
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          if (m >= MTp) continue;
+#pragma unroll
+          for (int cc = 0; cc < NCH; ++cc) {
+            uint32_t r[32];
+            cuda::ptx::tcgen05_ld_32x32b(r, d12 + lane_addr + (uint32_t)(m * NT + cc * 32));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int kp = m * 128 + q * 32 + lane;   // packed K row owned by this thread
+            const long long p0 = pos0 + cc * 32;
+            if (a.mode == 1) {
+              if (kp < a.Cin) {
+                const float sc = s_scale[kp], sh = s_shift[kp];
+                const float *zp = a.z_prev + (size_t)p0 * a.Cin + kp;
+                float *gp = a.gr_prev + (size_t)p0 * a.Cin + kp;
+                float t1 = 0.f, t2 = 0.f;
+                float zv[32];   // all 32 (L2-resident) loads in flight before the first store
+#pragma unroll
+                for (int i = 0; i < 32; ++i) zv[i] = __ldg(zp + (size_t)i * a.Cin);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const float g = fmaf(zv[i], sc, sh) > 0.f ? __uint_as_float(r[i]) : 0.f;
+                  gp[(size_t)i * a.Cin] = g;
+                  t1 += g;
+                  t2 = fmaf(g, zv[i], t2);
+                }
+                s1[m] += t1;
+                s2[m] += t2;
+              }
+            } else {
+              // gather layer: scatter-add into the point-major feature / xyz / centre gradients
+              const bool is_feat = kp < C;
+              const int e = kp - Cf8;                 // 0..2 for the dx,dy,dz rows
+              const bool is_xyz = (e >= 0 && e < 3);
+              if (is_feat && a.g_feat_t != nullptr) {
+                float *gb = a.g_feat_t + (size_t)tile_b * a.N * C + kp;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  atomicAdd(gb + (size_t)s_idx[cc * 32 + i] * C, __uint_as_float(r[i]));
+              } else if (is_xyz && (a.g_xyz != nullptr || a.g_new_xyz != nullptr)) {
+                float run = 0.f;
+                float *gx = a.g_xyz != nullptr ? a.g_xyz + (size_t)tile_b * a.N * 3 + e : nullptr;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const int ins = in_scene0 + cc * 32 + i;   // position inside the scene
+                  float v = __uint_as_float(r[i]);
+                  if (a.normalize_xyz) v = __fdiv_rn(v, a.radius);
+                  if (gx != nullptr) atomicAdd(gx + (size_t)s_idx[cc * 32 + i] * 3, v);
+                  run += v;
+                  if (((ins + 1) % a.NS) == 0 || i == 31) {   // end of this centre's run
+                    if (a.g_new_xyz != nullptr)
+                      atomicAdd(a.g_new_xyz + ((size_t)tile_b * a.NP + ins / a.NS) * 3 + e, -run);
+                    run = 0.f;
+                  }
                 }
               }
             }
           }
         }
+        if (a.mode == 1) {
+#pragma unroll
+          for (int m = 0; m < 3; ++m) {
+            d1[m] += (double)s1[m];
+            d2[m] += (double)s2[m];
+            s1[m] = 0.f;
+            s2[m] = 0.f;
+          }
+        }
       }
       tc_fence_before();
-      if (a.mode == 1) {
+      bar_epi();   // every epilogue thread is done with D1/D2[s] (and, gather layers, s_idx)
+      if (tid == 0) mbar_arrive(bar(10 + s));
+    }
+
+    if (a.do_dgrad && a.mode == 1 && a.stats_prev != nullptr) {
 #pragma unroll
-        for (int m = 0; m < 3; ++m) {
-          d1[m] += (double)s1[m];
-          d2[m] += (double)s2[m];
-          s1[m] = 0.f;
-          s2[m] = 0.f;
+      for (int m = 0; m < 3; ++m) {
+        const int kp = m * 128 + q * 32 + lane;
+        if (m < MTp && kp < a.Cin) {
+          atomicAdd(a.stats_prev + kp, d1[m]);
+          atomicAdd(a.stats_prev + a.Cin + kp, d2[m]);
         }
       }
     }
-  }
-
-  if (a.do_dgrad && a.mode == 1 && a.stats_prev != nullptr) {
+    // ---- wgrad accumulator -> dW (Cout, Cin): the last mma_done wait covered every MMA ----------
+    if (ntiles > 0) {
+      tc_fence_after();
+      for (int ml = 0; ml < MTl; ++ml) {
+        const int co = ml * 128 + q * 32 + lane;
+        for (int at = 0; at < KA * 2; ++at) {
+          uint32_t r[32];
+          cuda::ptx::tcgen05_ld_32x32b(
+              r, tmem_base + lane_addr + d3_col0 + (uint32_t)(ml * KA * 64 + at * 32));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (co < a.Cout) {
 #pragma unroll
-    for (int m = 0; m < 3; ++m) {
-      const int kp = m * 128 + q * 32 + lane;
-      // this thread's warp quad handled a chunk of M tile m iff NCH == 2 or the parity matches
-      const bool mine = (NCH == 2) || ((m & 1) == h);
-      if (m < MTp && mine && kp < a.Cin) {
-        atomicAdd(a.stats_prev + kp, d1[m]);
-        atomicAdd(a.stats_prev + a.Cin + kp, d2[m]);
-      }
-    }
-  }
-
-  // ---- wgrad accumulator -> dW (Cout, Cin) ------------------------------------------------------
-  if (a.do_wgrad && tile_iter > 0) {
-    // the last tile's commit (already waited on above) covers every wgrad MMA
-    tc_fence_after();
-    for (int u = h; u < MTl * KA; u += 2) {
-      const int ml = u / KA, at = u - ml * KA;
-      uint32_t r[32];
-      cuda::ptx::tcgen05_ld_32x32b(r, tmem_base + ((uint32_t)(q * 32) << 16) + d3_col0 +
-                                          (uint32_t)(ml * KA + at) * 32u);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int co = ml * 128 + q * 32 + lane;
-      if (co < a.Cout) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kp = at * 32 + i;
-          int k = -1;
-          if (a.mode == 0) {
-            if (kp < C) k = 3 + kp;
-            else if (kp >= Cf4 && kp < Cf4 + 3) k = kp - Cf4;
-          } else if (kp < a.Cin) {
-            k = kp;
+            for (int i = 0; i < 32; ++i) {
+              const int kp = at * 32 + i;
+              int kk = -1;
+              if (a.mode == 0) {
+                if (kp < C) kk = 3 + kp;
+                else if (kp >= Cf8 && kp < Cf8 + 3) kk = kp - Cf8;
+              } else if (kp < a.Cin) {
+                kk = kp;
+              }
+              if (kk >= 0) atomicAdd(a.dW + (size_t)co * a.Cin + kk, __uint_as_float(r[i]));
+            }
           }
-          if (k >= 0) atomicAdd(a.dW + (size_t)co * a.Cin + k, __uint_as_float(r[i]));
         }
       }
     }
   }
-  (void)KAl;
-  if (tid == 0 && !w_ready) mbar_wait(bar_w, 0);
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ---- max-pool / ReLU / BatchNorm backward of the pooled top layer: the sparse part ------------
@@ -554,67 +711,43 @@ __global__ void bn_bwd_finalize_kernel(const double *__restrict__ stats, int Cch
 }
 
 }  // namespace
+
 }  // namespace b2r
 
 using namespace b2r;
 
-extern "C" long long b2r_mlp_weight_t_image_bytes(int Cout, int Cin, int gather) {
-  if (Cout <= 0 || Cin <= 0) return 0;
-  const int Kp = packed_k(Cin, gather);
-  const int KA = (Kp + 31) >> 5, KAl = (Cout + 31) >> 5;
-  return (long long)((KA + 3) >> 2) * 128 * KAl * 128;
-}
-
-extern "C" int b2r_mlp_pack_weight_t(const float *w, int Cout, int Cin, int gather, float *image,
-                                     void *stream) {
-  B2R_REQUIRE(w && image && Cout > 0 && Cin > 0, "b2r_mlp_pack_weight_t: bad argument");
-  B2R_REQUIRE(!gather || Cin >= 3, "b2r_mlp_pack_weight_t: gather layers need Cin >= 3");
-  const int Kp = packed_k(Cin, gather);
-  const int KA = (Kp + 31) >> 5, KAl = (Cout + 31) >> 5;
-  const int rows_t = ((KA + 3) >> 2) * 128;
-  const long long total = (long long)rows_t * KAl * 32;
-  pack_weight_t_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, Cout, Cin, gather, Kp, rows_t, KAl, image);
-  B2R_CHECK_LAUNCH();
-  return B2R_OK;
-}
-
 namespace {
-// one launch with the given work split; returns B2R_ERR_UNSUPPORTED when it does not fit
-int launch_bwd(BwdArgs a, int do_dgrad, int do_wgrad, long long M, cudaStream_t st) {
-  a.do_dgrad = do_dgrad;
-  a.do_wgrad = do_wgrad;
-  const int MTp = (a.KA + 3) >> 2, MTl = a.Cout_pad >> 7;
-  const int has_coef = a.dz == nullptr;
-  int NT = 0;
-  for (int nt : {64, 32}) {
-    if (M % nt) continue;
-    const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.Cout, a.Cout_pad, nt, do_dgrad, do_wgrad,
-                                      has_coef);
-    const int cols = (do_dgrad ? MTp * nt : 0) + (do_wgrad ? MTl * a.KA * 32 : 0);
-    if (L.total <= 227u * 1024u && cols <= 512 && MTp <= 3) {
-      NT = nt;
-      break;
-    }
-  }
-  if (NT == 0) return B2R_ERR_UNSUPPORTED;
-  const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.Cout, a.Cout_pad, NT, do_dgrad, do_wgrad,
-                                    has_coef);
-  a.num_tiles = (int)(M / NT);
-  const int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
-  if (NT == 64) {
-    B2R_CUDA(cudaFuncSetAttribute(sa_layer_bwd_kernel<64>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    sa_layer_bwd_kernel<64><<<grid, kMlpThreads, L.total, st>>>(a);
-  } else {
-    B2R_CUDA(cudaFuncSetAttribute(sa_layer_bwd_kernel<32>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    sa_layer_bwd_kernel<32><<<grid, kMlpThreads, L.total, st>>>(a);
-  }
-  B2R_CHECK_LAUNCH();
-  return B2R_OK;
+struct Geometry {
+  int Kp, KA, WA, Cout_pad;
+};
+Geometry bwd_geometry(int Cout, int Cin, int gather) {
+  Geometry g;
+  g.Kp = packed_k16(Cin, gather);
+  g.KA = (g.Kp + 63) >> 6;
+  const int MTp = (g.KA + 1) >> 1;
+  g.WA = g.KA > 2 * MTp ? g.KA : 2 * MTp;   // dgrad reads the image in whole 128-wide M tiles
+  g.Cout_pad = (Cout + 127) & ~127;
+  return g;
 }
 }  // namespace
+
+extern "C" long long b2r_mlp_weight_bf16_image_bytes(int Cout, int Cin, int gather) {
+  if (Cout <= 0 || Cin <= 0) return 0;
+  const Geometry g = bwd_geometry(Cout, Cin, gather);
+  return (long long)g.Cout_pad * g.WA * 128;
+}
+
+extern "C" int b2r_mlp_pack_weight_bf16(const float *w, int Cout, int Cin, int gather, void *image,
+                                        void *stream) {
+  B2R_REQUIRE(w && image && Cout > 0 && Cin > 0, "b2r_mlp_pack_weight_bf16: bad argument");
+  B2R_REQUIRE(!gather || Cin >= 3, "b2r_mlp_pack_weight_bf16: gather layers need Cin >= 3");
+  const Geometry g = bwd_geometry(Cout, Cin, gather);
+  const long long total = (long long)g.Cout_pad * g.WA * 64;
+  pack_weight_bf16_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, Cout, Cin, gather, g.Kp, g.Cout_pad, g.WA, static_cast<__nv_bfloat16 *>(image));
+  B2R_CHECK_LAUNCH();
+  return B2R_OK;
+}
 
 extern "C" int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *d, void *stream) {
   B2R_REQUIRE(d != nullptr, "b2r_sa_layer_bwd: null descriptor");
@@ -622,63 +755,86 @@ extern "C" int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *d, void *stream) {
               "b2r_sa_layer_bwd: non-positive size");
   B2R_REQUIRE(d->mode == 0 || d->mode == 1, "b2r_sa_layer_bwd: mode must be 0 or 1");
   B2R_REQUIRE(d->dW != nullptr, "b2r_sa_layer_bwd: null dW");
-  B2R_REQUIRE(d->dz != nullptr ||
-                  (d->gr && d->z && d->coef_a && d->coef_b && d->coef_c),
-              "b2r_sa_layer_bwd: needs dz, or gr + z + coef_a/b/c");
+  const bool top = d->dysel != nullptr;
+  B2R_REQUIRE(d->dz != nullptr || (d->coef_a && d->coef_b && d->coef_c &&
+                                   ((d->gr && d->z) || (top && d->asel))),
+              "b2r_sa_layer_bwd: needs dz, or gr + z + coef_a/b/c, or dysel + asel + coef_a/b/c");
   BwdArgs a;
   a.B = d->B; a.N = d->N; a.NP = d->NP; a.NS = d->NS; a.Cin = d->Cin; a.Cout = d->Cout;
   a.mode = d->mode;
+  a.top = (d->dz == nullptr && top) ? 1 : 0;
   a.xyz = d->xyz; a.new_xyz = d->new_xyz; a.feat_t = d->feat_t; a.idx = d->idx;
   a.radius = d->radius; a.normalize_xyz = d->normalize_xyz;
   a.z_prev = d->z_prev; a.scale_prev = d->scale_prev; a.shift_prev = d->shift_prev;
-  a.w_image = d->w_image_t;
-  a.dz = d->dz; a.gr = d->gr; a.z = d->z;
+  a.w_image = d->w_image_bf16;
+  a.dz = d->dz; a.gr = d->gr; a.z = d->z; a.dysel = d->dysel; a.asel = d->asel;
   a.coef_a = d->coef_a; a.coef_b = d->coef_b; a.coef_c = d->coef_c;
   a.dW = d->dW; a.gr_prev = d->gr_prev; a.stats_prev = d->stats_prev;
   a.g_feat_t = d->g_feat_t; a.g_xyz = d->g_xyz; a.g_new_xyz = d->g_new_xyz;
-  a.Kp = packed_k(d->Cin, d->mode == 0);
-  a.KA = (a.Kp + 31) >> 5;
-  a.KAl = (d->Cout + 31) >> 5;
-  a.Cout_pad = (d->Cout + 127) & ~127;
-  a.chf_shift = pow2_shift(((d->Cin - 3 + 3) & ~3) >> 2);
-  a.do_dgrad = a.do_wgrad = 1;
+  const Geometry g = bwd_geometry(d->Cout, d->Cin, d->mode == 0);
+  a.Kp = g.Kp; a.KA = g.KA; a.WA = g.WA; a.Cout_pad = g.Cout_pad;
+  a.ch8_shift = pow2_shift((((d->Cin - 3 + 7) & ~7) >> 3));
+  a.ns_shift = pow2_shift(d->NS);
+  if (a.top && a.ns_shift < 0) {
+    set_error("b2r_sa_layer_bwd: the pooled top layer needs a power-of-two nsample (got %d)", d->NS);
+    return B2R_ERR_UNSUPPORTED;
+  }
   a.num_tiles = 0;
-  int need_dgrad;
   if (d->mode == 0) {
     B2R_REQUIRE(d->Cin >= 3 && d->xyz && d->new_xyz && d->idx && (d->feat_t || d->Cin == 3),
                 "b2r_sa_layer_bwd: gather mode needs xyz, new_xyz, idx (and feat_t when Cin > 3)");
-    need_dgrad = (d->g_feat_t != nullptr && d->Cin > 3) || d->g_xyz != nullptr ||
+    a.do_dgrad = (d->g_feat_t != nullptr && d->Cin > 3) || d->g_xyz != nullptr ||
                  d->g_new_xyz != nullptr;
   } else {
-    B2R_REQUIRE(d->z_prev && d->scale_prev && d->shift_prev && (d->Cin % 4) == 0,
-                "b2r_sa_layer_bwd: dense mode needs z_prev/scale/shift and Cin %% 4 == 0");
+    B2R_REQUIRE(d->z_prev && d->scale_prev && d->shift_prev,
+                "b2r_sa_layer_bwd: dense mode needs z_prev/scale/shift");
     B2R_REQUIRE(d->gr_prev != nullptr, "b2r_sa_layer_bwd: dense mode needs gr_prev");
-    need_dgrad = 1;
+    a.do_dgrad = 1;
   }
-  B2R_REQUIRE(!need_dgrad || d->w_image_t != nullptr,
-              "b2r_sa_layer_bwd: null transposed weight image");
+  B2R_REQUIRE(!(a.do_dgrad || a.top) || d->w_image_bf16 != nullptr,
+              "b2r_sa_layer_bwd: null weight image");
   const long long M = (long long)d->B * d->NP * d->NS;
-  if (d->mode == 0 && ((long long)d->NP * d->NS) % 64 != 0) {
-    set_error("b2r_sa_layer_bwd: gather layers need NP*NS %% 64 == 0 (got %lld)",
-              (long long)d->NP * d->NS);
+  const long long per_scene = (long long)d->NP * d->NS;
+  if (a.Cout_pad > 256 || (d->Cout % 8) != 0 || (d->mode == 1 && (d->Cin % 8) != 0)) {
+    set_error("b2r_sa_layer_bwd: needs Cout %% 8 == 0, Cout <= 256, dense Cin %% 8 == 0 "
+              "(Cin=%d Cout=%d)", d->Cin, d->Cout);
     return B2R_ERR_UNSUPPORTED;
   }
-  if (a.Cout_pad > 256 || (d->Cout % 8) != 0 || (M % 32) != 0) {
-    set_error("b2r_sa_layer_bwd: needs Cout %% 8 == 0, Cout <= 256, B*NP*NS %% 32 == 0 "
-              "(Cout=%d, M=%lld)", d->Cout, M);
+  const int MTp = (a.KA + 1) >> 1, MTl = a.Cout_pad >> 7;
+  int NT = 0;
+  for (int nt : {128, 64, 32}) {
+    if (M % nt) continue;
+    if (d->mode == 0 && per_scene % nt) continue;       // a tile must lie inside one scene
+    if (a.top && (nt % d->NS) != 0 && (d->NS % nt) != 0) continue;
+    const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, nt);
+    const int w12 = ((a.top && MTl > (a.do_dgrad ? MTp : 0)) ? MTl : (a.do_dgrad ? MTp : 0)) * nt;
+    const int cols = 2 * w12 + MTl * a.KA * 64;
+    if (L.total <= 227u * 1024u && cols <= 512 && MTp <= 3) {
+      NT = nt;
+      break;
+    }
+  }
+  if (NT == 0) {
+    set_error("b2r_sa_layer_bwd: layer Cin=%d Cout=%d M=%lld does not fit shared memory / TMEM",
+              d->Cin, d->Cout, M);
     return B2R_ERR_UNSUPPORTED;
   }
+  const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, NT);
+  a.num_tiles = (int)(M / NT);
+  const int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // one fused launch when both GEMMs' operands fit in shared memory + TMEM, else two launches
-  int rc = launch_bwd(a, need_dgrad, 1, M, st);
-  if (rc == B2R_ERR_UNSUPPORTED && need_dgrad) {
-    rc = launch_bwd(a, 0, 1, M, st);
-    if (rc == B2R_OK) rc = launch_bwd(a, 1, 0, M, st);
-  }
-  if (rc == B2R_ERR_UNSUPPORTED)
-    set_error("b2r_sa_layer_bwd: layer Cin=%d Cout=%d does not fit shared memory / TMEM", d->Cin,
-              d->Cout);
-  return rc;
+#define B2R_LAUNCH_BWD(NTV)                                                                     \
+  do {                                                                                          \
+    B2R_CUDA(cudaFuncSetAttribute(sa_layer_bwd_kernel<NTV>,                                     \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));  \
+    sa_layer_bwd_kernel<NTV><<<grid, kBwdThreads, L.total, st>>>(a);                            \
+  } while (0)
+  if (NT == 128) B2R_LAUNCH_BWD(128);
+  else if (NT == 64) B2R_LAUNCH_BWD(64);
+  else B2R_LAUNCH_BWD(32);
+#undef B2R_LAUNCH_BWD
+  B2R_CHECK_LAUNCH();
+  return B2R_OK;
 }
 
 extern "C" int b2r_pool_bwd_prep(const float *dout_cm, const float *dout_pm, const float *zmax,

@@ -68,7 +68,7 @@ def supported(mlp_module, xyz, features, idx, pooling="max"):
         if bn.momentum is None or not bn.track_running_stats or not bn.affine:
             return False
         cout, cin = blk.conv.out_channels, blk.conv.in_channels
-        if cout > 256 or cout % 8 != 0 or cin > 380 or (i > 0 and cin % 4 != 0):
+        if cout > 256 or cout % 8 != 0 or cin > 380 or (i > 0 and cin % 8 != 0):
             return False
         smem = _layer_smem(cin, cout, gather=(i == 0), nt=64)
         if smem > 227 * 1024:
@@ -196,14 +196,16 @@ def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
     return out_cm, out_pm
 
 
-def pack_weight_t(weight, gather):
-    """Conv weight (Cout,Cin,1,1) -> packed TF32 image of W^T (the dgrad A operand)."""
+def pack_weight_bf16(weight, gather):
+    """Conv weight (Cout,Cin,1,1) -> BF16 swizzled image for the backward kernel (serves the
+    top-layer recomputation K-major and dgrad MN-major from the same bytes)."""
     Cout, Cin = weight.shape[0], weight.shape[1]
     w = weight.detach().reshape(Cout, Cin).contiguous()
-    nbytes = _lib.lib().b2r_mlp_weight_t_image_bytes(Cout, Cin, 1 if gather else 0)
-    image = torch.empty(nbytes // 4, dtype=torch.float32, device=weight.device)
-    _lib.check(_lib.lib().b2r_mlp_pack_weight_t(_ptr(w), Cout, Cin, 1 if gather else 0,
-                                                _ptr(image), _ext._stream()), "mlp_pack_weight_t")
+    nbytes = _lib.lib().b2r_mlp_weight_bf16_image_bytes(Cout, Cin, 1 if gather else 0)
+    image = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=weight.device)
+    _lib.check(_lib.lib().b2r_mlp_pack_weight_bf16(_ptr(w), Cout, Cin, 1 if gather else 0,
+                                                   _ptr(image), _ext._stream()),
+               "mlp_pack_weight_bf16")
     _ext.LAUNCHES += 1
     return image
 
@@ -239,43 +241,26 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
                                      _ptr(saved["amax"]), _ptr(saved["amin"]), _ptr(scale),
                                      _ptr(shift), B, NP, Ct, _ptr(dysel), _ptr(asel), _ptr(stats),
                                      st), "pool_bwd_prep")
-    k1, k2, gs = torch.empty(Ct, **f32), torch.empty(Ct, **f32), torch.empty(Ct, **f32)
+    coef = [torch.empty(Ct, **f32) for _ in range(3)]
     dgammas[top], dbetas[top] = torch.empty(Ct, **f32), torch.empty(Ct, **f32)
     _lib.check(lib.b2r_bn_bwd_finalize(_ptr(stats), Ct, float(M), _ptr(gammas[top]), _ptr(mean),
-                                       _ptr(invstd), tr, None, None, None, _ptr(k1), _ptr(k2),
-                                       _ptr(gs), _ptr(dgammas[top]), _ptr(dbetas[top]), st),
-               "bn_bwd_finalize")
-    # recompute z of the top layer on the tensor cores and emit its dz
-    dz_top = torch.empty((M, Ct), **f32)
-    d = _lib.SaLayer()
-    d.B, d.N, d.NP, d.NS = B, N, NP, NS
-    d.Cin, d.Cout = weights[top].shape[1], Ct
-    d.mode, d.epilogue = (0 if top == 0 else 1), 2
-    if top == 0:
-        d.xyz, d.new_xyz, d.feat_t, d.idx = _ptr(xyz), _ptr(new_xyz), _ptr(feat_t), _ptr(idx)
-        d.radius, d.normalize_xyz = float(radius), 1 if normalize_xyz else 0
-    else:
-        d.z_prev, d.scale_prev, d.shift_prev = _ptr(zs[top - 1]), _ptr(bn[top - 1][2]), _ptr(bn[top - 1][3])
-    d.w_image = _ptr(images[top])
-    d.dysel, d.asel = _ptr(dysel), _ptr(asel)
-    d.bw_k1, d.bw_k2, d.bw_mean, d.bw_invstd, d.bw_gs = _ptr(k1), _ptr(k2), _ptr(mean), _ptr(invstd), _ptr(gs)
-    d.dz = _ptr(dz_top)
-    with _ext._timed("sa_layer_fwd", _fwd_bytes(B, N, NP, NS, d.Cin, Ct, top == 0, False)):
-        _lib.check(lib.b2r_sa_layer_fwd(ctypes.byref(d), st), "sa_layer_fwd(epilogue 2)")
+                                       _ptr(invstd), tr, _ptr(coef[0]), _ptr(coef[1]),
+                                       _ptr(coef[2]), None, None, None, _ptr(dgammas[top]),
+                                       _ptr(dbetas[top]), st), "bn_bwd_finalize")
     _ext.LAUNCHES += 2
 
     g_feat_t = g_xyz = g_new_xyz = None
-    gr = coef = None
+    gr = None
     for l in range(L - 1, -1, -1):
         Cout, Cin = weights[l].shape[0], weights[l].shape[1]
         b = _lib.SaLayerBwd()
         b.B, b.N, b.NP, b.NS, b.Cin, b.Cout = B, N, NP, NS, Cin, Cout
         b.mode = 0 if l == 0 else 1
-        if l == top:
-            b.dz = _ptr(dz_top)
+        if l == top:   # z is recomputed inside the kernel from the layer's input
+            b.dysel, b.asel = _ptr(dysel), _ptr(asel)
         else:
             b.gr, b.z = _ptr(gr), _ptr(zs[l])
-            b.coef_a, b.coef_b, b.coef_c = _ptr(coef[0]), _ptr(coef[1]), _ptr(coef[2])
+        b.coef_a, b.coef_b, b.coef_c = _ptr(coef[0]), _ptr(coef[1]), _ptr(coef[2])
         dWs[l] = torch.zeros((Cout, Cin), **f32)
         b.dW = _ptr(dWs[l])
         need_dgrad = True
@@ -298,8 +283,8 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
             gr_prev = torch.empty((M, Cin), **f32)
             stats_prev = torch.zeros((2, Cin), dtype=torch.float64, device=dev)
             b.gr_prev, b.stats_prev = _ptr(gr_prev), _ptr(stats_prev)
-        image_t = pack_weight_t(weights[l], gather=(l == 0)) if need_dgrad else None
-        b.w_image_t = _ptr(image_t)
+        image = pack_weight_bf16(weights[l], gather=(l == 0)) if (need_dgrad or l == top) else None
+        b.w_image_bf16 = _ptr(image)
         with _ext._timed("sa_layer_bwd", _bwd_bytes(B, N, NP, NS, Cin, Cout, l == 0, l == top,
                                                     need_dgrad)):
             _lib.check(lib.b2r_sa_layer_bwd(ctypes.byref(b), st), "sa_layer_bwd")

@@ -227,10 +227,11 @@ B2R_API int b2r_to_point_major(const float *in, int B, int C, int N, float *out,
  *   b2r_pool_bwd_prep      grad of the pooled output -> the ONE sample per (centre, channel) it
  *                          reaches (dysel, asel) + BatchNorm-backward sums of the top layer
  *   b2r_bn_bwd_finalize    sums -> per-channel coefficients of dz = a*gr + b*z + c, dgamma, dbeta
- *   b2r_sa_layer_fwd (epilogue 2)   recompute z of the top layer, emit its dz
- *   b2r_sa_layer_bwd       ONE layer: dW (+)= dz^T x  and  gr_prev = (dz W) * relu-mask with the
- *                          next BatchNorm-backward sums (dense layers), or the scatter-add of
- *                          dz W into the point-major feature / xyz gradients (gather layer)
+ *   b2r_sa_layer_bwd       ONE layer (BF16 operands, FP32 accumulate): dW (+)= dz^T x  and
+ *                          gr_prev = (dz W) * relu-mask with the next BatchNorm-backward sums
+ *                          (dense layers), or the scatter-add of dz W into the point-major
+ *                          feature / xyz gradients (gather layer).  For the pooled top layer z is
+ *                          recomputed inside the kernel (the forward never stored it).
  */
 typedef struct b2r_sa_layer_bwd_desc {
   int B, N, NP, NS;
@@ -242,12 +243,15 @@ typedef struct b2r_sa_layer_bwd_desc {
   float radius;
   int normalize_xyz;
   const float *z_prev, *scale_prev, *shift_prev; /* mode 1 */
-  const float *w_image_t;   /* b2r_mlp_pack_weight_t image; may be NULL when no dgrad is needed */
-  /* the layer's output gradient: either dz directly ... */
-  const float *dz;          /* (M,Cout) or NULL */
-  /* ... or gr = dL/d(bn output, ReLU-masked) with z and the b2r_bn_bwd_finalize coefficients */
-  const float *gr, *z;      /* (M,Cout) */
-  const float *coef_a, *coef_b, *coef_c; /* (Cout) */
+  const void *w_image_bf16; /* b2r_mlp_pack_weight_bf16 image; NULL only when neither dgrad nor
+                               the top-layer recomputation is needed */
+  /* the layer's output gradient, one of three forms: */
+  const float *dz;          /* (a) dz (M,Cout) given directly, or NULL */
+  const float *gr, *z;      /* (b) dense: gr = dL/d(bn output, ReLU-masked) and z, (M,Cout) each */
+  const float *dysel;       /* (c) pooled top layer: routed output gradient (B*NP,Cout) ... */
+  const int *asel;          /*     ... and the sample it reaches, from b2r_pool_bwd_prep; z is
+                                   recomputed on the tensor cores */
+  const float *coef_a, *coef_b, *coef_c; /* (b),(c): dz = a*g + b*z + c, b2r_bn_bwd_finalize */
   /* outputs */
   float *dW;                /* (Cout,Cin) nn.Conv2d layout; ACCUMULATED (caller zeroes) */
   float *gr_prev;           /* mode 1: (M,Cin) ReLU-masked gradient of the layer below */
@@ -257,9 +261,9 @@ typedef struct b2r_sa_layer_bwd_desc {
   float *g_new_xyz;         /* mode 0: (B,NP,3) ACCUMULATED; NULL = not needed */
 } b2r_sa_layer_bwd_desc;
 
-B2R_API long long b2r_mlp_weight_t_image_bytes(int Cout, int Cin, int gather);
-B2R_API int b2r_mlp_pack_weight_t(const float *w, int Cout, int Cin, int gather, float *image,
-                                  void *stream);
+B2R_API long long b2r_mlp_weight_bf16_image_bytes(int Cout, int Cin, int gather);
+B2R_API int b2r_mlp_pack_weight_bf16(const float *w, int Cout, int Cin, int gather, void *image,
+                                     void *stream);
 B2R_API int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *desc, void *stream);
 
 /* dout_cm (B,C,NP) and/or dout_pm (B,NP,C) (summed; either may be NULL) -> dysel (B*NP,C),
