@@ -79,10 +79,10 @@ __host__ __device__ inline int packed_k16(int Cin, int gather) {
 
 struct BwdSmem {
   uint32_t w_off, w_bytes, x_off[2], dz_off[2], x_bytes, dz_bytes, coef_off, scale_off, idx_off,
-      bar_off, total;
+      route_off, bar_off, total;
 };
 __host__ __device__ inline BwdSmem bwd_smem_layout(int Kp, int KA, int WA, int Cout, int Cout_pad,
-                                                   int NT) {
+                                                   int NT, int top) {
   BwdSmem s;
   s.w_off = 0;
   s.w_bytes = (uint32_t)Cout_pad * WA * 128u;
@@ -98,8 +98,9 @@ __host__ __device__ inline BwdSmem bwd_smem_layout(int Kp, int KA, int WA, int C
   s.coef_off = o;
   s.scale_off = s.coef_off + 3u * Cout * 4u;
   s.idx_off = s.scale_off + 2u * Kp * 4u;
-  s.bar_off = (s.idx_off + 4u * (uint32_t)NT * 4u + 15u) & ~15u;   // idx: 4 buffers (below)
-  s.total = s.bar_off + 12 * 8 + 16 + 1024;                        // + alignment slack
+  s.route_off = (s.idx_off + 4u * (uint32_t)NT * 4u + 15u) & ~15u;   // idx: 4 buffers (below)
+  s.bar_off = s.route_off + (top ? 2u * (uint32_t)(NT / 16) * Cout_pad * 4u : 0u);
+  s.total = s.bar_off + 13 * 8 + 16 + 1024;                        // + alignment slack
   return s;
 }
 
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~(uintptr_t)1023);
-  const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, NT);
+  const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, NT, a.top);
   uint8_t *s_w = base + L.w_off;
   float *s_ca = reinterpret_cast<float *>(base + L.coef_off);
   float *s_cb = s_ca + a.Cout;
@@ -175,6 +176,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
   // ball-query indices per tile, 4-deep ring: the producers may write tile k while the scatter
   // epilogue still reads tile k-3 (MMA(k-2) only waits for the epilogue of tile k-4)
   int *s_idx4 = reinterpret_cast<int *>(base + L.idx_off);
+  float *s_dy = reinterpret_cast<float *>(base + L.route_off);
+  int *s_as = reinterpret_cast<int *>(s_dy + (NT / 16) * a.Cout_pad);
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(base + L.bar_off);
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 13);
   // mbarriers: [0,1] full  [2,3] empty  [4,5] z_done  [6,7] dz_ready  [8,9] mma_done
@@ -251,10 +254,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
       if (!a.top) {
         const int total = NT * CH8;
         const size_t o0 = (size_t)pos0 * a.Cout;
-        for (int i0 = ptid; i0 < total; i0 += kProdThreads * 2) {
-          float4 g[2][2], zz[2][2];
+        for (int i0 = ptid; i0 < total; i0 += kProdThreads * 4) {
+          float4 g[4][2], zz[4][2];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
+          for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * kProdThreads;
             if (i < total) {
               if (!has_coef) {
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
             }
           }
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
+          for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * kProdThreads;
             if (i < total) {
               const int row = i / CH8, ch = i - row * CH8;
@@ -467,9 +470,24 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
         const int ns_mask = a.NS - 1;                         // NS is a power of two (host check)
         const long long centre0 = pos0 >> a.ns_shift;
         const int base_s = (int)(pos0 & ns_mask);
+        // routed gradient of every centre touching this tile (<= NT/16), fetched BEFORE the wait
+        // on the recomputed z (global latency hides behind the tensor core) and parked in smem;
+        // every thread reads back only the entries it wrote itself, so no barrier is needed
+        const int ncen = ((base_s + NT - 1) >> a.ns_shift) + 1;
+        for (int ml = 0; ml < MTl; ++ml) {
+          const int co = ml * 128 + q * 32 + lane;
+          if (co < a.Cout)
+            for (int c = 0; c < ncen; ++c) {
+              const size_t o = (size_t)(centre0 + c) * a.Cout + co;
+              s_dy[c * a.Cout_pad + co] = __ldg(a.dysel + o);
+              s_as[c * a.Cout_pad + co] = __ldg(a.asel + o);
+            }
+        }
         mbar_wait(bar(4 + s), (uint32_t)(n & 1));
         tc_fence_after();
-        for (int ml = 0; ml < MTl; ++ml) {
+#pragma unroll
+        for (int ml = 0; ml < 2; ++ml) {
+          if (ml >= MTl) continue;
           const int co = ml * 128 + q * 32 + lane;
           const bool ok = co < a.Cout;
           const float ca = ok ? s_ca[co] : 0.f, cb = ok ? s_cb[co] : 0.f, cc = ok ? s_cc[co] : 0.f;
@@ -479,18 +497,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
             cuda::ptx::tcgen05_ld_32x32b(r, d12 + lane_addr + (uint32_t)(ml * NT + ch * 32));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (ok) {
-              float dyv = 0.f;
-              int as = -1;
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 const int t = base_s + ch * 32 + i;          // sample position counted from the
                 const int sidx = t & ns_mask;                // first centre touching this tile
-                if (i == 0 || sidx == 0) {   // first column of a centre inside this chunk
-                  const size_t o = (size_t)(centre0 + (t >> a.ns_shift)) * a.Cout + co;
-                  dyv = __ldg(a.dysel + o);
-                  as = __ldg(a.asel + o);
-                }
-                const float dy = (sidx == as) ? dyv : 0.f;
+                const int c = t >> a.ns_shift;
+                const float dy = (sidx == s_as[c * a.Cout_pad + co]) ? s_dy[c * a.Cout_pad + co] : 0.f;
                 const float v = fmaf(ca, dy, fmaf(cb, __uint_as_float(r[i]), cc));
                 *reinterpret_cast<__nv_bfloat16 *>(sdz + bf_off(ch * 32 + i, co >> 3, NT) +
                                                    (co & 7) * 2) = __float2bfloat16_rn(v);
@@ -806,7 +818,7 @@ extern "C" int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *d, void *stream) {
     if (M % nt) continue;
     if (d->mode == 0 && per_scene % nt) continue;       // a tile must lie inside one scene
     if (a.top && (nt % d->NS) != 0 && (d->NS % nt) != 0) continue;
-    const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, nt);
+    const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, nt, a.top);
     const int w12 = ((a.top && MTl > (a.do_dgrad ? MTp : 0)) ? MTl : (a.do_dgrad ? MTp : 0)) * nt;
     const int cols = 2 * w12 + MTl * a.KA * 64;
     if (L.total <= 227u * 1024u && cols <= 512 && MTp <= 3) {
@@ -819,7 +831,7 @@ extern "C" int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *d, void *stream) {
               d->Cin, d->Cout, M);
     return B2R_ERR_UNSUPPORTED;
   }
-  const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, NT);
+  const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, NT, a.top);
   a.num_tiles = (int)(M / NT);
   const int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

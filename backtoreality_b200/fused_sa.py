@@ -93,12 +93,13 @@ def _fwd_bytes(B, N, NP, NS, Cin, Cout, gather, pooled):
     return rd + wr
 
 
-def _bwd_bytes(B, N, NP, NS, Cin, Cout, gather, direct, dgrad):
-    """ALGORITHMIC HBM bytes of one b2r_sa_layer_bwd launch: dz (or gr and z) read once, the
-    layer input read once, gr_prev written once (dense) / the scatter target read-modify-written
-    (gather layer with dgrad)."""
+def _bwd_bytes(B, N, NP, NS, Cin, Cout, gather, top, dgrad):
+    """ALGORITHMIC HBM bytes of one b2r_sa_layer_bwd launch: dense layers read gr and z once, the
+    pooled top layer reads only the routed (centre, channel) gradient + index (its z is recomputed
+    in the kernel); the layer input is read once; gr_prev is written once (dense) / the scatter
+    target is read-modify-written (gather layer with dgrad)."""
     M = B * NP * NS
-    rd = 4 * M * Cout * (1 if direct else 2)
+    rd = 8 * B * NP * Cout if top else 8 * M * Cout
     if gather:
         rd += 4 * M + min(B * N, M) * 4 * Cin + 12 * B * NP
         wr = 2 * min(B * N, M) * 4 * Cin if dgrad else 0

@@ -64,8 +64,8 @@ def workload_config(a, world):
         "loss": "synthetic scalar: mean(proposal_scores^2) + mean((vote_xyz-seed_xyz)^2)",
         "parallelism": "dp%d (scenes sharded, flat-gradient NCCL all-reduce)" % world,
         "l2": "256 MB buffer written between steps (flush) + 4 rotating input batches",
-        "mlp_math": "SA blocks: fused tcgen05 TF32 (fp32 accumulate); FP/vote heads: cuDNN with TF32 "
-                    "allowed (torch default, as the reference runs)",
+        "mlp_math": "SA blocks: fused tcgen05, forward TF32 / backward BF16 operands, fp32 accumulate; "
+                    "FP/vote heads: cuDNN with TF32 allowed (torch default, as the reference runs)",
     }
 
 
@@ -317,7 +317,7 @@ def run_b2r(a):
                 kern]["dram_bytes_per_launch"]
         except Exception:
             pass
-        out["roofline"] = {"kernel": "%s (fused tcgen05 SA layer, %d launches/step; TF32 tensor "
+        out["roofline"] = {"kernel": "%s (fused tcgen05 SA layer, %d launches/step; tensor "
                                      "work is <10%% of its time, it is HBM-bound)" % (kern, n // a.steps),
                            "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                            "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
