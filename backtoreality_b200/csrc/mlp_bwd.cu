@@ -99,7 +99,7 @@ __host__ __device__ inline BwdSmem bwd_smem_layout(int Kp, int KA, int WA, int C
   s.scale_off = s.coef_off + 3u * Cout * 4u;
   s.idx_off = s.scale_off + 2u * Kp * 4u;
   s.route_off = (s.idx_off + 4u * (uint32_t)NT * 4u + 15u) & ~15u;   // idx: 4 buffers (below)
-  s.bar_off = s.route_off + (top ? 2u * (uint32_t)(NT / 16) * Cout_pad * 4u : 0u);
+  s.bar_off = s.route_off + (top ? 4u * (uint32_t)(NT / 16) * Cout_pad * 4u : 0u);   // 2 stages
   s.total = s.bar_off + 13 * 8 + 16 + 1024;                        // + alignment slack
   return s;
 }
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
   // epilogue still reads tile k-3 (MMA(k-2) only waits for the epilogue of tile k-4)
   int *s_idx4 = reinterpret_cast<int *>(base + L.idx_off);
   float *s_dy = reinterpret_cast<float *>(base + L.route_off);
-  int *s_as = reinterpret_cast<int *>(s_dy + (NT / 16) * a.Cout_pad);
+  int *s_as = reinterpret_cast<int *>(s_dy + 2 * (NT / 16) * a.Cout_pad);
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(base + L.bar_off);
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 13);
   // mbarriers: [0,1] full  [2,3] empty  [4,5] z_done  [6,7] dz_ready  [8,9] mma_done
@@ -281,9 +281,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
               if (has_coef) {
                 const float zv[8] = {zz[u][0].x, zz[u][0].y, zz[u][0].z, zz[u][0].w,
                                      zz[u][1].x, zz[u][1].y, zz[u][1].z, zz[u][1].w};
+                float ca8[8], cb8[8], cc8[8];
+                *reinterpret_cast<float4 *>(ca8) = *reinterpret_cast<const float4 *>(s_ca + ch * 8);
+                *reinterpret_cast<float4 *>(ca8 + 4) = *reinterpret_cast<const float4 *>(s_ca + ch * 8 + 4);
+                *reinterpret_cast<float4 *>(cb8) = *reinterpret_cast<const float4 *>(s_cb + ch * 8);
+                *reinterpret_cast<float4 *>(cb8 + 4) = *reinterpret_cast<const float4 *>(s_cb + ch * 8 + 4);
+                *reinterpret_cast<float4 *>(cc8) = *reinterpret_cast<const float4 *>(s_cc + ch * 8);
+                *reinterpret_cast<float4 *>(cc8 + 4) = *reinterpret_cast<const float4 *>(s_cc + ch * 8 + 4);
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  v[e] = fmaf(s_ca[ch * 8 + e], v[e], fmaf(s_cb[ch * 8 + e], zv[e], s_cc[ch * 8 + e]));
+                for (int e = 0; e < 8; ++e) v[e] = fmaf(ca8[e], v[e], fmaf(cb8[e], zv[e], cc8[e]));
               }
               *reinterpret_cast<uint4 *>(sdz + bf_off(row, ch, NT)) =
                   make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
@@ -459,62 +465,76 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
     float s1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f};
     double d1[3] = {0.0, 0.0, 0.0}, d2[3] = {0.0, 0.0, 0.0};
     int ntiles = 0;
+    // Top layer: D1 (recomputed z) -> dz = a*dy_routed + b*z + c -> DZ tile (BF16) of tile k.
+    // Called one tile AHEAD of the D2 epilogue (software pipelining): while these warps turn
+    // D1(k+1) into DZ(k+1), the tensor core runs dgrad/wgrad(k), so neither waits for the other.
+    auto produce_dz = [&](int k, int tile) {
+      const int s = k & 1, n = k >> 1;
+      const long long pos0 = (long long)tile * NT;
+      const uint32_t d12 = tmem_base + (uint32_t)(s * w12);
+      uint8_t *sdz = base + L.dz_off[s];
+      const int ns_mask = a.NS - 1;                         // NS is a power of two >= 16 (host)
+      const long long centre0 = pos0 >> a.ns_shift;
+      const int base_s = (int)(pos0 & ns_mask);
+      // routed gradient of every centre touching this tile (<= NT/16), fetched BEFORE the wait
+      // on the recomputed z and parked in smem; every thread reads back only its own entries
+      const int ncen = ((base_s + NT - 1) >> a.ns_shift) + 1;
+      float *my_dy = s_dy + (size_t)s * (NT / 16) * a.Cout_pad;
+      int *my_as = s_as + (size_t)s * (NT / 16) * a.Cout_pad;
+      for (int ml = 0; ml < MTl; ++ml) {
+        const int co = ml * 128 + q * 32 + lane;
+        if (co < a.Cout)
+          for (int c = 0; c < ncen; ++c) {
+            const size_t o = (size_t)(centre0 + c) * a.Cout + co;
+            my_dy[c * a.Cout_pad + co] = __ldg(a.dysel + o);
+            my_as[c * a.Cout_pad + co] = __ldg(a.asel + o);
+          }
+      }
+      mbar_wait(bar(4 + s), (uint32_t)(n & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int ml = 0; ml < 2; ++ml) {
+        if (ml >= MTl) continue;
+        const int co = ml * 128 + q * 32 + lane;
+        const bool ok = co < a.Cout;
+        const float ca = ok ? s_ca[co] : 0.f, cb = ok ? s_cb[co] : 0.f, cc = ok ? s_cc[co] : 0.f;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          uint32_t r[32];
+          cuda::ptx::tcgen05_ld_32x32b(r, d12 + lane_addr + (uint32_t)(ml * NT + ch * 32));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (ok) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {   // 16 columns = one centre (NS >= 16, aligned)
+              const int t0 = base_s + ch * 32 + hf * 16;
+              const int c = t0 >> a.ns_shift;
+              const int s0 = t0 & ns_mask;
+              const float dyv = my_dy[c * a.Cout_pad + co];
+              const int as = my_as[c * a.Cout_pad + co] - s0;   // routed sample, relative
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float dy = (i == as) ? dyv : 0.f;
+                const float v = fmaf(ca, dy, fmaf(cb, __uint_as_float(r[hf * 16 + i]), cc));
+                *reinterpret_cast<__nv_bfloat16 *>(
+                    sdz + bf_off(ch * 32 + hf * 16 + i, co >> 3, NT) + (co & 7) * 2) =
+                    __float2bfloat16_rn(v);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      fence_async_smem();
+      bar_epi();
+      if (tid == 0) mbar_arrive(bar(6 + s));
+    };
+    if (a.top && (int)blockIdx.x < a.num_tiles) produce_dz(0, blockIdx.x);
     for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k, ++ntiles) {
       const int s = k & 1, n = k >> 1;
       const long long pos0 = (long long)tile * NT;
       const uint32_t d12 = tmem_base + (uint32_t)(s * w12);
       const int *s_idx = s_idx4 + (k & 3) * NT;
-      if (a.top) {
-        // ---- D1 (recomputed z) -> dz = a*dy_routed + b*z + c -> DZ tile (BF16) ------------------
-        uint8_t *sdz = base + L.dz_off[s];
-        const int ns_mask = a.NS - 1;                         // NS is a power of two (host check)
-        const long long centre0 = pos0 >> a.ns_shift;
-        const int base_s = (int)(pos0 & ns_mask);
-        // routed gradient of every centre touching this tile (<= NT/16), fetched BEFORE the wait
-        // on the recomputed z (global latency hides behind the tensor core) and parked in smem;
-        // every thread reads back only the entries it wrote itself, so no barrier is needed
-        const int ncen = ((base_s + NT - 1) >> a.ns_shift) + 1;
-        for (int ml = 0; ml < MTl; ++ml) {
-          const int co = ml * 128 + q * 32 + lane;
-          if (co < a.Cout)
-            for (int c = 0; c < ncen; ++c) {
-              const size_t o = (size_t)(centre0 + c) * a.Cout + co;
-              s_dy[c * a.Cout_pad + co] = __ldg(a.dysel + o);
-              s_as[c * a.Cout_pad + co] = __ldg(a.asel + o);
-            }
-        }
-        mbar_wait(bar(4 + s), (uint32_t)(n & 1));
-        tc_fence_after();
-#pragma unroll
-        for (int ml = 0; ml < 2; ++ml) {
-          if (ml >= MTl) continue;
-          const int co = ml * 128 + q * 32 + lane;
-          const bool ok = co < a.Cout;
-          const float ca = ok ? s_ca[co] : 0.f, cb = ok ? s_cb[co] : 0.f, cc = ok ? s_cc[co] : 0.f;
-#pragma unroll
-          for (int ch = 0; ch < NCH; ++ch) {
-            uint32_t r[32];
-            cuda::ptx::tcgen05_ld_32x32b(r, d12 + lane_addr + (uint32_t)(ml * NT + ch * 32));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (ok) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int t = base_s + ch * 32 + i;          // sample position counted from the
-                const int sidx = t & ns_mask;                // first centre touching this tile
-                const int c = t >> a.ns_shift;
-                const float dy = (sidx == s_as[c * a.Cout_pad + co]) ? s_dy[c * a.Cout_pad + co] : 0.f;
-                const float v = fmaf(ca, dy, fmaf(cb, __uint_as_float(r[i]), cc));
-                *reinterpret_cast<__nv_bfloat16 *>(sdz + bf_off(ch * 32 + i, co >> 3, NT) +
-                                                   (co & 7) * 2) = __float2bfloat16_rn(v);
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        fence_async_smem();
-        bar_epi();
-        if (tid == 0) mbar_arrive(bar(6 + s));
-      }
+      if (a.top && tile + grid < a.num_tiles) produce_dz(k + 1, tile + grid);
       mbar_wait(bar(8 + s), (uint32_t)(n & 1));
       tc_fence_after();
       if (a.do_dgrad) {

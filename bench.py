@@ -180,7 +180,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------- GPU arm ---------
 def run_b2r(a):
     import torch.distributed as dist
-    from backtoreality_b200 import _ext, _lib, scenes
+    from backtoreality_b200 import _ext, _lib, dist_utils, scenes
     from backtoreality_b200.votenet import VoteNet
 
     rank = int(os.environ.get("RANK", "0"))
@@ -201,11 +201,8 @@ def run_b2r(a):
     net = VoteNet(22, 1, 22, np.ones((22, 3), np.float32), input_feature_dim=1, num_proposal=256,
                   vote_factor=1, sampling="vote_fps").to(dev).train()
     params = [p for p in net.parameters()]
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
-    off = 0
-    for p in params:  # gradients live in one flat buffer: a single all-reduce per step
-        p.grad = flat[off:off + p.numel()].view_as(p)
-        off += p.numel()
+    bucket = dist_utils.FlatGradBucket(params)  # one flat buffer: a single all-reduce per step
+    flat = bucket.flat
     opt = torch.optim.Adam(params, lr=1e-3, fused=True)
 
     pool_n = 4
@@ -219,11 +216,9 @@ def run_b2r(a):
         ep = net({"point_clouds": pc})
         loss = synthetic_loss(ep)
         loss.backward()
-        if world > 1:
-            dist.all_reduce(flat)
-            flat.mul_(1.0 / world)
+        bucket.allreduce_mean()
         opt.step()
-        flat.zero_()
+        bucket.zero()
         return loss
 
     def barrier():
