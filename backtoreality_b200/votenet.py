@@ -60,7 +60,10 @@ def decode_scores(net, end_points, num_class, num_heading_bin, num_size_cluster,
     srn = nt[:, :, 5 + NH * 2 + NS:5 + NH * 2 + NS * 4].view([B, P, NS, 3])
     end_points['size_scores'] = size_scores
     end_points['size_residuals_normalized'] = srn
-    msa = torch.from_numpy(np.asarray(mean_size_arr, np.float32)).to(net.device)[None, None]
+    if isinstance(mean_size_arr, torch.Tensor):   # device-resident copy kept by ProposalModule
+        msa = mean_size_arr[None, None]
+    else:
+        msa = torch.from_numpy(np.asarray(mean_size_arr, np.float32)).to(net.device)[None, None]
     end_points['size_residuals'] = srn * msa
     size_recover = msa + end_points['size_residuals']
     cls = torch.argmax(size_scores, -1).unsqueeze(-1).unsqueeze(-1).repeat(1, 1, 1, 3)
@@ -92,6 +95,11 @@ class ProposalModule(nn.Module):
             128, 2 + 3 + num_heading_bin * 2 + num_size_cluster * 4 + self.num_class, 1)
         self.bn1 = nn.BatchNorm1d(128)
         self.bn2 = nn.BatchNorm1d(128)
+        # device-resident mean sizes (the reference re-uploads the numpy array every forward,
+        # proposal_module.py:40: a host->device copy per step that also forbids graph capture);
+        # non-persistent, so the state dict stays the reference's
+        self.register_buffer("_mean_size", torch.from_numpy(
+            np.asarray(mean_size_arr, np.float32)).clone(), persistent=False)
 
     def forward(self, xyz, features, end_points):
         if self.sampling == 'vote_fps':
@@ -118,7 +126,7 @@ class ProposalModule(nn.Module):
         net = self.conv3(net)
         end_points['proposal_scores_raw'] = net
         return decode_scores(net, end_points, self.num_class, self.num_heading_bin,
-                             self.num_size_cluster, self.mean_size_arr)
+                             self.num_size_cluster, self._mean_size)
 
 
 class VoteNet(nn.Module):

@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--npoints", type=int, default=40000)
     ap.add_argument("--cpu-scenes", type=int, default=2, help="scenes per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch every kernel from Python instead of replaying the captured step")
     return ap.parse_args()
 
 
@@ -64,6 +66,7 @@ def workload_config(a, world):
         "loss": "synthetic scalar: mean(proposal_scores^2) + mean((vote_xyz-seed_xyz)^2)",
         "parallelism": "dp%d (scenes sharded, flat-gradient NCCL all-reduce)" % world,
         "l2": "256 MB buffer written between steps (flush) + 4 rotating input batches",
+        "launch": "whole step (fwd+bwd+all-reduce+Adam) captured in one CUDA graph, replayed per batch",
         "mlp_math": "SA blocks: fused tcgen05, forward TF32 / backward BF16 operands, fp32 accumulate; "
                     "FP/vote heads: cuDNN with TF32 allowed (torch default, as the reference runs)",
     }
@@ -203,7 +206,7 @@ def run_b2r(a):
     params = [p for p in net.parameters()]
     bucket = dist_utils.FlatGradBucket(params)  # one flat buffer: a single all-reduce per step
     flat = bucket.flat
-    opt = torch.optim.Adam(params, lr=1e-3, fused=True)
+    opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
 
     pool_n = 4
     host = [torch.from_numpy(scenes.batch((rank * pool_n + i) * a.batch, a.batch, a.npoints, C=1,
@@ -244,21 +247,46 @@ def run_b2r(a):
 
     for i in range(max(a.warmup, 3)):
         step(resident[i % pool_n])
+
+    # kernel-level timing (roofline / fps blocks): a few eager steps with CUDA events around every
+    # libb2r launch on its launching stream -- events cannot be recorded inside a graph replay
+    _ext.TIME_OPS.update(["sa_layer_fwd", "sa_layer_bwd", "furthest_point_sampling"])
+    _ext.TIMED.clear()
+    k_steps = min(a.steps, 5)
+    torch.cuda.synchronize()
+    l0 = _ext.LAUNCHES
+    for i in range(k_steps):
+        flush.zero_()
+        step(resident[i % pool_n])
+    torch.cuda.synchronize()
+    launches_per_step = (_ext.LAUNCHES - l0) // k_steps
+    timed = {k: list(v) for k, v in _ext.TIMED.items()}
+    _ext.TIME_OPS.clear()
+
+    # the step as the user runs it: captured once into a CUDA graph, replayed per batch
+    graphed = None
+    if not a.no_graph:
+        try:
+            from backtoreality_b200.train_step import CapturedTrainStep
+            graphed = CapturedTrainStep(step, resident[0])
+        except Exception as e:  # report, then measure the eager loop instead
+            log("CUDA-graph capture failed (%s: %s); timing the eager step" % (type(e).__name__, e))
+            graphed = None
+    run_step = (lambda pc: graphed(pc)) if graphed is not None else step
+    for i in range(3):
+        run_step(resident[i % pool_n])
     sampler = ClockSampler(dev) if rank == 0 else None
     time.sleep(0.3)
 
-    # (1) inputs resident in HBM
-    _ext.TIME_OPS.update(["sa_layer_fwd", "sa_layer_bwd", "furthest_point_sampling"])
-    _ext.TIMED.clear()
-    l0 = _ext.LAUNCHES
-    ms_dev, t0, t1 = timed_loop(lambda i: step(resident[i % pool_n]))
-    launches = _ext.LAUNCHES - l0
-    timed = {k: list(v) for k, v in _ext.TIMED.items()}
-    _ext.TIME_OPS.clear()
+    # (1) inputs resident in HBM (graph mode: one device-to-device copy into the static input)
+    ms_dev, t0, t1 = timed_loop(lambda i: run_step(resident[i % pool_n]))
+    launches = launches_per_step * a.steps
     clocks = sampler.window(t0, t1) if sampler else None
 
     # (2) end to end: pinned host input -> device each step, loss read back each step
     def e2e_step(i):
+        if graphed is not None:
+            return float(graphed(host[i % pool_n]).item())   # H2D straight into the static input
         pc = host[i % pool_n].to(dev, non_blocking=True)
         return float(step(pc).item())
 
@@ -286,6 +314,9 @@ def run_b2r(a):
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    if graphed is None:
+        out["config"]["launch"] = "eager: every kernel launched from Python"
+    k_div = k_steps
 
     # roofline of the dominant HBM-bound libb2r kernel, from events recorded in the timed loop
     peaks = {}
@@ -313,20 +344,20 @@ def run_b2r(a):
         except Exception:
             pass
         out["roofline"] = {"kernel": "%s (fused tcgen05 SA layer, %d launches/step; tensor "
-                                     "work is <10%% of its time, it is HBM-bound)" % (kern, n // a.steps),
+                                     "work is <10%% of its time, it is HBM-bound)" % (kern, n // k_div),
                            "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                            "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                            "algorithmic_bytes_per_launch": tot_b / n,
                            "avg_launch_us": 1e3 * tot_ms / n, "launches_timed": n,
-                           "ms_per_step": tot_ms / a.steps,
-                           "other": {k: {"ms_per_step": v[0] / a.steps,
+                           "ms_per_step": tot_ms / k_div,
+                           "other": {k: {"ms_per_step": v[0] / k_div,
                                          "achieved_gbs": v[1] / (v[0] * 1e-3) / 1e9,
-                                         "launches_per_step": v[2] // a.steps}
+                                         "launches_per_step": v[2] // k_div}
                                      for k, v in cand.items() if k != name}}
     fp = timed.get("furthest_point_sampling", [])
     if fp:
-        per_step = len(fp) // a.steps
-        ms_step = sum(s.elapsed_time(e) for s, e, _ in fp) / a.steps
+        per_step = len(fp) // k_div
+        ms_step = sum(s.elapsed_time(e) for s, e, _ in fp) / k_div
         # SA1 is the first FPS launch of every step: N points -> 2048 samples
         sa1 = [fp[i] for i in range(0, len(fp), per_step)]
         sa1_ms = float(np.mean([s.elapsed_time(e) for s, e, _ in sa1]))

@@ -237,3 +237,42 @@ def test_backbone_full_size_40k_vs_oracle_port(cuda, mode):
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
         fused_sa.ENABLED = True
+
+
+def test_captured_train_step_matches_eager(cuda):
+    """The whole training step replayed from ONE CUDA graph (train_step.CapturedTrainStep) must
+    follow the eager step: same losses step by step (float atomics in the scatter-adds make the
+    two runs differ at the 1e-6 level, hence a tolerance, not equality)."""
+    from backtoreality_b200.train_step import CapturedTrainStep
+    from backtoreality_b200.votenet import VoteNet
+
+    def make():
+        torch.manual_seed(5)
+        net = VoteNet(4, 1, 4, np.ones((4, 3), np.float32), input_feature_dim=1, num_proposal=64,
+                      vote_factor=1, sampling="vote_fps").to(cuda).train()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, fused=True, capturable=True)
+
+        def step(pc):
+            ep = net({"point_clouds": pc})
+            loss = (ep["proposal_scores_raw"] ** 2).mean() + ((ep["vote_xyz"] - ep["seed_xyz"]) ** 2).mean()
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=False)
+            return loss.detach()
+        return net, step
+
+    batches = [torch.from_numpy(scenes.batch(300 + 2 * i, 2, 8192, C=1, kind="room", dup=0.2)).to(cuda)
+               for i in range(4)]
+    net_e, step_e = make()
+    eager = []
+    for i in range(3):                      # the three warm-up steps CapturedTrainStep runs
+        step_e(batches[0])
+    for b in batches:
+        eager.append(float(step_e(b)))
+    net_g, step_g = make()
+    captured = CapturedTrainStep(step_g, batches[0], warmup=3)
+    assert captured.launches_per_step > 50   # libb2r launches inside the captured step
+    got = [float(captured(b)) for b in batches]
+    np.testing.assert_allclose(got, eager, rtol=2e-2)
+    for (n1, p1), (n2, p2) in zip(net_e.named_parameters(), net_g.named_parameters()):
+        assert rel_l2(p2.detach().cpu().numpy(), p1.detach().cpu().numpy()) < 2e-2, n1
