@@ -18,8 +18,9 @@ class CapturedTrainStep:
     """`step_fn(static_input) -> loss tensor` runs fwd + bwd + all-reduce + optimizer, eagerly.
     This wraps it: `loss = captured(batch)` copies `batch` into the static input and replays."""
 
-    def __init__(self, step_fn, example_input, warmup=3):
+    def __init__(self, step_fn, example_input, warmup=3, after_warmup_step=None):
         self.step_fn = step_fn
+        self.after_warmup_step = after_warmup_step   # e.g. the eager optimizer / gradient reset
         self.static_in = example_input.clone()
         self.warmup = warmup
         self.graph = None
@@ -34,6 +35,8 @@ class CapturedTrainStep:
         with torch.cuda.stream(side):
             for _ in range(self.warmup):
                 self.step_fn(self.static_in)
+                if self.after_warmup_step is not None:
+                    self.after_warmup_step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         saved_ops = set(_ext.TIME_OPS)

@@ -66,7 +66,8 @@ def workload_config(a, world):
         "loss": "synthetic scalar: mean(proposal_scores^2) + mean((vote_xyz-seed_xyz)^2)",
         "parallelism": "dp%d (scenes sharded, flat-gradient NCCL all-reduce)" % world,
         "l2": "256 MB buffer written between steps (flush) + 4 rotating input batches",
-        "launch": "whole step (fwd+bwd+all-reduce+Adam) captured in one CUDA graph, replayed per batch",
+        "launch": ("whole step (fwd+bwd+Adam) captured in one CUDA graph, replayed per batch" if world == 1
+                   else "fwd+bwd replayed from one CUDA graph; NCCL all-reduce + fused Adam eager"),
         "mlp_math": "SA blocks: fused tcgen05, forward TF32 / backward BF16 operands, fp32 accumulate; "
                     "FP/vote heads: cuDNN with TF32 allowed (torch default, as the reference runs)",
     }
@@ -215,14 +216,25 @@ def run_b2r(a):
     resident = [h.to(dev) for h in host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def step(pc):
+    def fwd_bwd(pc):
         ep = net({"point_clouds": pc})
         loss = synthetic_loss(ep)
         loss.backward()
-        bucket.allreduce_mean()
+        return loss
+
+    def finish():
+        bucket.allreduce_mean()   # the step's only collective: one NCCL sum of the flat gradient
         opt.step()
         bucket.zero()
+
+    def step(pc):
+        loss = fwd_bwd(pc)
+        finish()
         return loss
+
+    def stage(msg):
+        if world > 1 or os.environ.get("B2R_BENCH_VERBOSE"):
+            log("[rank %d] %s" % (rank, msg))
 
     def barrier():
         if world > 1:
@@ -245,8 +257,11 @@ def run_b2r(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), t0, t1
 
+    stage("model and %d resident batches ready; eager warm-up" % pool_n)
     for i in range(max(a.warmup, 3)):
         step(resident[i % pool_n])
+    torch.cuda.synchronize()
+    stage("warm-up done")
 
     # kernel-level timing (roofline / fps blocks): a few eager steps with CUDA events around every
     # libb2r launch on its launching stream -- events cannot be recorded inside a graph replay
@@ -264,15 +279,29 @@ def run_b2r(a):
     _ext.TIME_OPS.clear()
 
     # the step as the user runs it: captured once into a CUDA graph, replayed per batch
+    # (N = 1: the optimizer too; N > 1: forward+backward are replayed, the NCCL all-reduce and the
+    # 3-kernel fused Adam stay eager so no collective is ever captured)
     graphed = None
+    capture_all = world == 1
     if not a.no_graph:
         try:
             from backtoreality_b200.train_step import CapturedTrainStep
-            graphed = CapturedTrainStep(step, resident[0])
+            stage("capturing the step into a CUDA graph")
+            graphed = CapturedTrainStep(step if capture_all else fwd_bwd, resident[0],
+                                        after_warmup_step=None if capture_all else finish)
+            stage("captured (%d libb2r launches per step)" % graphed.launches_per_step)
         except Exception as e:  # report, then measure the eager loop instead
             log("CUDA-graph capture failed (%s: %s); timing the eager step" % (type(e).__name__, e))
             graphed = None
-    run_step = (lambda pc: graphed(pc)) if graphed is not None else step
+
+    def run_step(pc):
+        if graphed is None:
+            return step(pc)
+        loss = graphed(pc)
+        if not capture_all:
+            finish()
+        return loss
+
     for i in range(3):
         run_step(resident[i % pool_n])
     sampler = ClockSampler(dev) if rank == 0 else None
@@ -286,7 +315,7 @@ def run_b2r(a):
     # (2) end to end: pinned host input -> device each step, loss read back each step
     def e2e_step(i):
         if graphed is not None:
-            return float(graphed(host[i % pool_n]).item())   # H2D straight into the static input
+            return float(run_step(host[i % pool_n]).item())  # H2D straight into the static input
         pc = host[i % pool_n].to(dev, non_blocking=True)
         return float(step(pc).item())
 
