@@ -366,6 +366,11 @@ bool make_plan(int B, int N, FpsPlan *pl) {
       c = 1;
       while (c * 2 <= max_c && (long long)B * (c * 2) <= kNumSMs && rows / (c * 2) >= 2) c *= 2;
       while (c < max_c && (rows + c - 1) / c > kPMax) c *= 2;  // capacity wins over residency
+      // Measured on B200 (scripts/fps_sweep.py, profiles/r01/fps_cluster_sweep.log): at N = 40000
+      // an 8-CTA cluster with 10 points per thread beats 16 CTAs x 5 points by 11 % (744 vs 834
+      // ns per iteration) -- the per-iteration cost is the DSMEM fan-out (one st.async pair per
+      // peer) and the mbarrier round trip, not the register-resident distance updates.
+      if (c == 16 && (rows + 7) / 8 <= 10) c = 8;
     }
     const int forced = env_int("B2R_FPS_CLUSTER", 0);
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) c = forced;
