@@ -346,8 +346,10 @@ __global__ void bn_finalize_kernel(const double *__restrict__ stats, int Cch, do
                                    float eps, float momentum, float *__restrict__ running_mean,
                                    float *__restrict__ running_var, float *__restrict__ scale,
                                    float *__restrict__ shift, float *__restrict__ mean_out,
-                                   float *__restrict__ invstd_out) {
+                                   float *__restrict__ invstd_out,
+                                   long long *__restrict__ num_batches_tracked) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
   if (ch >= Cch) return;
   const double mean = stats[ch] / count;
   double var = stats[Cch + ch] / count - mean * mean;
@@ -523,11 +525,11 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
 extern "C" int b2r_bn_finalize(const double *stats, int C, double count, const float *gamma,
                                const float *beta, float eps, float momentum, float *running_mean,
                                float *running_var, float *scale, float *shift, float *mean_out,
-                               float *invstd_out, void *stream) {
+                               float *invstd_out, long long *num_batches_tracked, void *stream) {
   B2R_REQUIRE(stats && scale && shift && C > 0 && count > 0, "b2r_bn_finalize: bad argument");
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       stats, C, count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift,
-      mean_out, invstd_out);
+      mean_out, invstd_out, num_batches_tracked);
   B2R_CHECK_LAUNCH();
   return B2R_OK;
 }

@@ -21,17 +21,35 @@ def shard_scene_indices(global_batch, rank, world, step=0, first_seed=1000):
 
 
 class FlatGradBucket:
-    """All parameters' .grad as views into one contiguous fp32 buffer."""
+    """One contiguous fp32 buffer with a view per parameter.
 
-    def __init__(self, params):
+    as_views=True (default): every p.grad IS its view, autograd accumulates into the flat buffer
+    (one small add kernel per parameter per step) and `zero()` resets it.
+    as_views=False: p.grad is left alone (None between steps, so autograd ASSIGNS fresh gradients
+    without any add kernel); `reduce_from(grads)` packs them with one multi-tensor copy,
+    all-reduces, and points every p.grad at its averaged view for the optimizer.
+    """
+
+    def __init__(self, params, as_views=True):
         self.params = [p for p in params]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device if self.params else torch.device("cpu")
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+        if as_views:
+            for p, v in zip(self.params, self.views):
+                p.grad = v
+
+    def reduce_from(self, grads):
+        """grads: one tensor per parameter (e.g. the p.grad list right after backward)."""
+        torch._foreach_copy_(self.views, list(grads))
+        self.allreduce_mean()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def allreduce_mean(self):
         """Sum over ranks, divide by world size (DDP semantics).  No-op without a process group."""

@@ -134,6 +134,12 @@ def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
     L = len(blocks)
     z_prev = scale = shift = None
     zs, bn_saved, images = [], [], []
+    # batch statistics of every layer: ONE zero-filled buffer (one memset instead of one per layer)
+    stats_all = None
+    if training:
+        stats_all = torch.zeros(sum(2 * b.conv.out_channels for b in blocks), dtype=torch.float64,
+                                device=dev)
+    stats_off = 0
     zmax = zmin = amax = amin = None
     for i, blk in enumerate(blocks):
         conv, bn = blk.conv, blk.bn.bn
@@ -141,7 +147,10 @@ def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
         last = i == L - 1
         image = pack_weight(conv.weight, gather=(i == 0))
         images.append(image)
-        stats = torch.zeros((2, Cout), dtype=torch.float64, device=dev) if training else None
+        stats = None
+        if training:
+            stats = stats_all[stats_off:stats_off + 2 * Cout]
+            stats_off += 2 * Cout
         d = _lib.SaLayer()
         d.B, d.N, d.NP, d.NS, d.Cin, d.Cout = B, N, NP, NS, Cin, Cout
         d.mode = 0 if i == 0 else 1
@@ -174,10 +183,10 @@ def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
             _lib.check(lib.b2r_bn_finalize(_ptr(stats), Cout, float(M), _ptr(bn.weight),
                                            _ptr(bn.bias), float(bn.eps), float(bn.momentum),
                                            _ptr(bn.running_mean), _ptr(bn.running_var),
-                                           _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), st),
+                                           _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
+                                           _ptr(bn.num_batches_tracked), st),
                        "bn_finalize")
             _ext.LAUNCHES += 1
-            bn.num_batches_tracked.add_(1)
         else:
             invstd = torch.rsqrt(bn.running_var + bn.eps)
             mean = bn.running_mean
@@ -235,7 +244,14 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
     top = L - 1
     Ct = weights[top].shape[0]
     mean, invstd, scale, shift = bn[top]
-    stats = torch.zeros((2, Ct), dtype=torch.float64, device=dev)
+    # every accumulated output of the block from two zero-filled buffers (two memsets in total)
+    stats_all = torch.zeros(sum(2 * w.shape[0] for w in weights), dtype=torch.float64, device=dev)
+    dW_all = torch.zeros(sum(w.numel() for w in weights), **f32)
+    s_off, w_off = [0], [0]
+    for w in weights:
+        s_off.append(s_off[-1] + 2 * w.shape[0])
+        w_off.append(w_off[-1] + w.numel())
+    stats = stats_all[s_off[top]:s_off[top + 1]]
     dysel = torch.empty((B * NP, Ct), **f32)
     asel = torch.empty((B * NP, Ct), dtype=torch.int32, device=dev)
     _lib.check(lib.b2r_pool_bwd_prep(_ptr(g_out_cm), None, _ptr(saved["zmax"]), _ptr(saved["zmin"]),
@@ -262,7 +278,7 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
         else:
             b.gr, b.z = _ptr(gr), _ptr(zs[l])
         b.coef_a, b.coef_b, b.coef_c = _ptr(coef[0]), _ptr(coef[1]), _ptr(coef[2])
-        dWs[l] = torch.zeros((Cout, Cin), **f32)
+        dWs[l] = dW_all[w_off[l]:w_off[l + 1]].view(Cout, Cin)
         b.dW = _ptr(dWs[l])
         need_dgrad = True
         gr_prev = stats_prev = None
@@ -282,7 +298,7 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
         else:
             b.z_prev, b.scale_prev, b.shift_prev = _ptr(zs[l - 1]), _ptr(bn[l - 1][2]), _ptr(bn[l - 1][3])
             gr_prev = torch.empty((M, Cin), **f32)
-            stats_prev = torch.zeros((2, Cin), dtype=torch.float64, device=dev)
+            stats_prev = stats_all[s_off[l - 1]:s_off[l]]
             b.gr_prev, b.stats_prev = _ptr(gr_prev), _ptr(stats_prev)
         image = pack_weight_bf16(weights[l], gather=(l == 0)) if (need_dgrad or l == top) else None
         b.w_image_bf16 = _ptr(image)

@@ -205,9 +205,10 @@ def run_b2r(a):
     net = VoteNet(22, 1, 22, np.ones((22, 3), np.float32), input_feature_dim=1, num_proposal=256,
                   vote_factor=1, sampling="vote_fps").to(dev).train()
     params = [p for p in net.parameters()]
-    bucket = dist_utils.FlatGradBucket(params)  # one flat buffer: a single all-reduce per step
-    flat = bucket.flat
+    # N > 1: gradients are packed into one flat buffer for a single all-reduce per step
+    bucket = dist_utils.FlatGradBucket(params, as_views=False) if world > 1 else None
     opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
+    live = {"grads": None}   # the gradient tensors the last backward (or the graph) produced
 
     pool_n = 4
     host = [torch.from_numpy(scenes.batch((rank * pool_n + i) * a.batch, a.batch, a.npoints, C=1,
@@ -217,15 +218,18 @@ def run_b2r(a):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def fwd_bwd(pc):
+        for p in params:          # autograd then ASSIGNS fresh gradients: no accumulate kernels,
+            p.grad = None         # nothing to zero
         ep = net({"point_clouds": pc})
         loss = synthetic_loss(ep)
         loss.backward()
+        live["grads"] = [p.grad for p in params]
         return loss
 
     def finish():
-        bucket.allreduce_mean()   # the step's only collective: one NCCL sum of the flat gradient
+        if bucket is not None:    # the step's only collective: one NCCL sum of the flat gradient
+            bucket.reduce_from(live["grads"])
         opt.step()
-        bucket.zero()
 
     def step(pc):
         loss = fwd_bwd(pc)

@@ -203,11 +203,12 @@ B2R_API int b2r_sa_layer_fwd(const b2r_sa_layer *desc, void *stream);
 /* BatchNorm bookkeeping from accumulated statistics (replaces the statistics half of
  * nn.BatchNorm2d in training mode, reference pytorch_utils.py:55-58): scale = gamma*invstd,
  * shift = beta - mean*scale; running stats updated with `momentum` (unbiased variance) when
- * running_mean/var are non-NULL.  mean_out / invstd_out (C) are optional (saved for backward). */
+ * running_mean/var are non-NULL; *num_batches_tracked (int64, may be NULL) is incremented.
+ * mean_out / invstd_out (C) are optional (saved for backward). */
 B2R_API int b2r_bn_finalize(const double *stats, int C, double count, const float *gamma,
                             const float *beta, float eps, float momentum, float *running_mean,
                             float *running_var, float *scale, float *shift, float *mean_out,
-                            float *invstd_out, void *stream);
+                            float *invstd_out, long long *num_batches_tracked, void *stream);
 
 /* out = relu(scale*(scale>=0 ? zmax : zmin) + shift): (B,C,NP) channel-major (reference layout)
  * and/or (B,NP,C) point-major (the next layer's gather source).  Either output may be NULL. */

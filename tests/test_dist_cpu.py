@@ -28,26 +28,35 @@ def _scene(seed):
     return torch.randn(4, 50, generator=g)
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, as_views):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         net = _make_net()
-        bucket = dist_utils.FlatGradBucket(net.parameters())
+        bucket = dist_utils.FlatGradBucket(net.parameters(), as_views=as_views)
         seeds = dist_utils.shard_scene_indices(8, rank, world, step=3)
         x = torch.stack([_scene(s) for s in seeds])
         net(x).square().mean().backward()   # per-rank mean over its local scenes
-        bucket.allreduce_mean()
+        if as_views:
+            bucket.allreduce_mean()
+        else:                                # gradients assigned by autograd, packed afterwards
+            bucket.reduce_from([p.grad for p in net.parameters()])
+            for p, v in zip(net.parameters(), bucket.views):
+                assert p.grad is v
         torch.save({"seeds": seeds, "flat": bucket.flat.clone()}, out % rank)
     finally:
         dist.destroy_process_group()
 
 
-def test_two_rank_flat_gradient_allreduce_matches_full_batch(tmp_path):
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("as_views", [True, False])
+def test_two_rank_flat_gradient_allreduce_matches_full_batch(tmp_path, as_views):
     world = 2
     out = str(tmp_path / "r%d.pt")
-    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, as_views), nprocs=world, join=True)
     r0, r1 = torch.load(out % 0), torch.load(out % 1)
     # disjoint shards that cover the global batch of that step
     assert sorted(r0["seeds"] + r1["seeds"]) == list(range(1000 + 3 * 8, 1000 + 4 * 8))
