@@ -47,8 +47,6 @@ class SaLayer(ctypes.Structure):
         ("z_prev", _vp), ("scale_prev", _vp), ("shift_prev", _vp),
         ("w_image", _vp), ("z", _vp), ("stats", _vp),
         ("zmax", _vp), ("zmin", _vp), ("amax", _vp), ("amin", _vp),
-        ("dysel", _vp), ("asel", _vp), ("bw_k1", _vp), ("bw_k2", _vp), ("bw_mean", _vp),
-        ("bw_invstd", _vp), ("bw_gs", _vp), ("dz", _vp),
     ]
 
 

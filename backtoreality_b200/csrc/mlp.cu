@@ -22,6 +22,7 @@
 // the column a position, so BN statistics, BN scale/shift and the max-pool over `nsample` are all
 // per-THREAD register work in the epilogue (one thread owns one channel), no shuffles.
 //
+// Warp-specialised and double-buffered (see the role table above the kernel).
 // Blackwell specifics: tcgen05.mma (kind::tf32, cta_group::1, M=128, N=64/128, K=8) issued by one
 // elected thread, operands in 128B-swizzled K-major shared memory, accumulators in TMEM read back
 // with tcgen05.ld.32x32b.x32, MMA completion signalled through tcgen05.commit -> mbarrier.
@@ -71,271 +72,257 @@ struct LayerArgs {
   double *stats;
   float *zmax, *zmin;
   int *amax, *amin;
-  // epilogue 2 (backward helper): dz of the pooled top layer
-  const float *dysel;
-  const int *asel;
-  const float *bw_k1, *bw_k2, *bw_mean, *bw_invstd, *bw_gs;
-  float *dz;
-  int Kp, Cout_pad, num_tiles, chf_shift;
+  int Kp, Cout_pad, num_tiles, chf_shift, ns_shift;
 };
 
-// max/min + arg over groups of NS columns held in registers; writes (centre, channel) entries
-template <int NS>
-__device__ __forceinline__ void pool_groups(const float (&v)[64], long long pos0, int c, int Cout,
-                                            float *__restrict__ zmax, float *__restrict__ zmin,
-                                            int *__restrict__ amax, int *__restrict__ amin) {
-#pragma unroll
-  for (int g = 0; g < 64 / NS; ++g) {
-    float mx = v[g * NS], mn = v[g * NS];
-    int ax = 0, an = 0;
-#pragma unroll
-    for (int s = 1; s < NS; ++s) {
-      const float x = v[g * NS + s];
-      if (x > mx) { mx = x; ax = s; }   // strict: the first maximum wins, like max_pool2d
-      if (x < mn) { mn = x; an = s; }
-    }
-    const long long centre = (pos0 + g * NS) / NS;
-    const size_t o = (size_t)centre * Cout + c;
-    zmax[o] = mx; zmin[o] = mn; amax[o] = ax; amin[o] = an;
-  }
+// Warp roles (12 warps = 3 per SM sub-partition -> 168 registers/thread):
+//   0-3  epilogue   one TMEM lane quadrant each: TMEM -> registers -> statistics, store / pool
+//   4    MMA issue  one elected thread
+//   5-11 producers  global loads (batched) -> BN+ReLU / gather -> TF32 -> swizzled smem tile
+// Two smem stages for the X tile and two TMEM stages for the accumulator, mbarrier hand-offs
+// (full / empty / mma_done / d_free): producers run up to two tiles ahead of the tensor core and
+// the epilogue's stores trail behind, so HBM reads, MMAs and HBM writes of different tiles overlap.
+constexpr int kFwdEpiThreads = 128, kFwdProdThreads = 224;
+constexpr int kFwdThreads = kFwdEpiThreads + 32 + kFwdProdThreads;   // 384
+
+struct FwdSmem {
+  uint32_t w_off, w_bytes, x_off[2], x_bytes, scale_off, idx_off, bar_off, total;
+};
+__host__ __device__ inline FwdSmem fwd_smem_layout(int Kp, int Cout_pad, int NT) {
+  FwdSmem s;
+  const uint32_t KA = (uint32_t)(Kp + 31) >> 5;
+  s.w_off = 0;
+  s.w_bytes = (uint32_t)Cout_pad * KA * 128u;
+  s.x_bytes = (uint32_t)NT * KA * 128u;
+  s.x_off[0] = s.w_bytes;
+  s.x_off[1] = s.w_bytes + s.x_bytes;
+  s.scale_off = s.x_off[1] + s.x_bytes;
+  s.idx_off = s.scale_off + 2u * Kp * 4u;
+  s.bar_off = (s.idx_off + (uint32_t)NT * 4u + 15u) & ~15u;
+  s.total = s.bar_off + 9 * 8 + 16 + 1024;   // + alignment slack
+  return s;
+}
+__device__ __forceinline__ void fwd_bar_epi() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kFwdEpiThreads));
+}
+__device__ __forceinline__ void fwd_bar_prod() {
+  asm volatile("bar.sync 2, %0;" ::"n"(kFwdProdThreads));
+}
+__device__ __forceinline__ void mbar_arrive1(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// Backward helper (epilogue 2): with z of the pooled top layer back in registers, emit
-//   dz = gamma*invstd * (dy - mean(dy) - xhat * mean(dy*xhat)),   xhat = (z - mean) * invstd
-// where dy is the max-pool / ReLU routed output gradient: non-zero only at the selected sample.
-template <int NS>
-__device__ __forceinline__ void dz_groups(const float (&v)[64], long long pos0, int c, int Cout,
-                                          const float *__restrict__ dysel,
-                                          const int *__restrict__ asel, float k1, float k2,
-                                          float mean, float invstd, float gs,
-                                          float *__restrict__ dz) {
-#pragma unroll
-  for (int g = 0; g < 64 / NS; ++g) {
-    const long long centre = (pos0 + g * NS) / NS;
-    const float dyv = dysel[(size_t)centre * Cout + c];
-    const int as = asel[(size_t)centre * Cout + c];
-    float *o = dz + (size_t)(pos0 + g * NS) * Cout + c;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      const float dy = (s == as) ? dyv : 0.f;
-      const float xh = (v[g * NS + s] - mean) * invstd;
-      o[(size_t)s * Cout] = gs * (dy - k1 - xh * k2);
-    }
-  }
-}
-
-// NT = positions per tile (MMA N).  MT = Cout_pad / 128 M-tiles.
-//   MT == 1: warps 0-3 take columns [0,NT/2), warps 4-7 columns [NT/2,NT) of the single M tile
-//   MT == 2: warps 0-3 take M tile 0, warps 4-7 M tile 1, all NT columns (NT must be 64)
+// NT = positions per tile (MMA N); MT = Cout_pad / 128 accumulator M tiles (1 or 2).
 template <int NT>
-__global__ void __launch_bounds__(kMlpThreads, 1) sa_layer_fwd_kernel(const LayerArgs a) {
+__global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const LayerArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve-up (all 1024-byte aligned where the swizzle needs it)
-  const int KA = (a.Kp + 31) >> 5;
-  const uint32_t w_bytes = (uint32_t)a.Cout_pad * KA * 128;
-  const uint32_t x_bytes = (uint32_t)NT * KA * 128;
   uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~(uintptr_t)1023);
-  uint8_t *s_w = base;
-  uint8_t *s_x = s_w + w_bytes;
-  float *s_scale = reinterpret_cast<float *>(s_x + x_bytes);
+  const FwdSmem L = fwd_smem_layout(a.Kp, a.Cout_pad, NT);
+  uint8_t *s_w = base + L.w_off;
+  float *s_scale = reinterpret_cast<float *>(base + L.scale_off);
   float *s_shift = s_scale + a.Kp;
-  int *s_idx = reinterpret_cast<int *>(s_shift + a.Kp);
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(
-      (reinterpret_cast<uintptr_t>(s_idx + NT) + 15) & ~(uintptr_t)15);  // [0]: weights, [1]: MMA
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2);
+  int *s_idx = reinterpret_cast<int *>(base + L.idx_off);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(base + L.bar_off);
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 9);
+  // mbarriers: [0,1] full  [2,3] empty  [4,5] mma_done  [6,7] d_free  [8] weights
+  auto bar = [&](int i) { return smem_u32(&s_bar[i]); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int MT = a.Cout_pad >> 7;
-  const uint32_t bar_w = smem_u32(&s_bar[0]), bar_mma = smem_u32(&s_bar[1]);
-  constexpr uint32_t kTmemCols = 128;
+  constexpr int NCH = NT / 32;
+  constexpr uint32_t kTmemCols = 512;
+  const int grid = (int)gridDim.x;
 
-  // ---- one-time setup ----------------------------------------------------------------------
   if (tid == 0) {
-    mbar_init(bar_w, 1);
-    mbar_init(bar_mma, 1);
+    for (int i = 0; i < 9; ++i) mbar_init(bar(i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(s_tmem), kTmemCols);
-  // zero the X tile once: padding chunks are never written again
-  for (uint32_t i = tid * 16; i < x_bytes; i += kMlpThreads * 16)
-    *reinterpret_cast<uint4 *>(s_x + i) = make_uint4(0, 0, 0, 0);
+  if (warp == 4) tmem_alloc(smem_u32(s_tmem), kTmemCols);
+  for (uint32_t i = tid * 16; i < 2u * L.x_bytes; i += kFwdThreads * 16)   // padding stays zero
+    *reinterpret_cast<uint4 *>(base + L.x_off[0] + i) = make_uint4(0, 0, 0, 0);
   if (a.mode == 1)
-    for (int i = tid; i < a.Cin; i += kMlpThreads) {
+    for (int i = tid; i < a.Cin; i += kFwdThreads) {
       s_scale[i] = a.scale_prev[i];
       s_shift[i] = a.shift_prev[i];
     }
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   if (tid == 0) {  // TMA unit stages the whole pre-swizzled weight image
-    mbar_expect_tx(bar_w, w_bytes);
-    bulk_g2s(smem_u32(s_w), a.w_image, w_bytes, bar_w);
+    mbar_expect_tx(bar(8), L.w_bytes);
+    bulk_g2s(smem_u32(s_w), a.w_image, L.w_bytes, bar(8));
   }
 
-  // epilogue role of this thread
-  const int q = warp & 3, h = warp >> 2;
-  const int mt = (MT == 2) ? h : 0;
-  const int col0 = (MT == 2) ? 0 : h * (NT / 2);
-  constexpr int kColsMax = (NT == 128) ? 64 : 64;
-  const int ncols = (MT == 2) ? NT : NT / 2;  // 64, or 32 when (MT == 1, NT == 64)
-  const int c = mt * 128 + q * 32 + lane;     // output channel owned by this thread
-  const bool c_ok = c < a.Cout;
-  double acc_s = 0.0, acc_ss = 0.0;
-  (void)kColsMax;
-  float e2_k1 = 0.f, e2_k2 = 0.f, e2_mean = 0.f, e2_invstd = 0.f, e2_gs = 0.f;
-  if (a.epilogue == 2 && c_ok) {
-    e2_k1 = a.bw_k1[c]; e2_k2 = a.bw_k2[c]; e2_mean = a.bw_mean[c];
-    e2_invstd = a.bw_invstd[c]; e2_gs = a.bw_gs[c];
-  }
-
-  const int KS = (a.Kp + 7) >> 3;  // K = 8 slices actually issued
-  const uint32_t idesc = idesc_tf32(NT);
-  const long long per_scene = (long long)a.NP * a.NS;
-  GatherSrc gsrc;
-  gsrc.xyz = a.xyz; gsrc.new_xyz = a.new_xyz; gsrc.feat_t = a.feat_t;
-  gsrc.N = a.N; gsrc.NP = a.NP; gsrc.NS = a.NS; gsrc.C = a.Cin - 3; gsrc.Cf4 = (a.Cin - 3 + 3) & ~3;
-  gsrc.chf_shift = a.chf_shift; gsrc.radius = a.radius; gsrc.normalize_xyz = a.normalize_xyz;
-  uint32_t mma_parity = 0;
-  bool w_ready = false;
-
-  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-    const long long pos0 = (long long)tile * NT;
-
-    // ---- prologue: build the X tile (B operand) in swizzled shared memory ------------------
-    if (a.mode == 0) {
-      if (tid < NT) s_idx[tid] = a.idx[pos0 + tid];
-      __syncthreads();
-      const int b = (int)(pos0 / per_scene);
-      const int in_scene0 = (int)(pos0 - (long long)b * per_scene);
-      build_x_gather<NT>(gsrc, b, in_scene0, s_idx, s_x, tid,
-                         [](int row, int ch) { return sw128_off(row, ch, NT); });
-    } else {
-      // dense layer: the tile is one contiguous block of z_prev.  Loads are issued in batches of
-      // 8 independent 16-byte requests per thread (memory-level parallelism), and the NEXT tile
-      // of this CTA is pulled into L2 by a single bulk-prefetch instruction meanwhile.
-      const int CH = a.Cin >> 2;
-      const int total = NT * CH;
-      if (tid == 0 && tile + (int)gridDim.x < a.num_tiles)
-        prefetch_l2(a.z_prev + (size_t)(pos0 + (long long)gridDim.x * NT) * a.Cin,
-                    (uint32_t)total * 16u);
-      const float4 *src = reinterpret_cast<const float4 *>(a.z_prev + (size_t)pos0 * a.Cin);
-      for (int i0 = tid; i0 < total; i0 += kMlpThreads * 8) {
-        float4 t[8];
+  if (warp > 4) {
+    // =============================== PRODUCERS ==================================================
+    const int ptid = tid - (kFwdEpiThreads + 32);
+    const long long per_scene = (long long)a.NP * a.NS;
+    GatherSrc gsrc;
+    gsrc.xyz = a.xyz; gsrc.new_xyz = a.new_xyz; gsrc.feat_t = a.feat_t;
+    gsrc.N = a.N; gsrc.NP = a.NP; gsrc.NS = a.NS; gsrc.C = a.Cin - 3;
+    gsrc.Cf4 = (a.Cin - 3 + 3) & ~3;
+    gsrc.chf_shift = a.chf_shift; gsrc.radius = a.radius; gsrc.normalize_xyz = a.normalize_xyz;
+    for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k) {
+      const int s = k & 1, n = k >> 1;
+      mbar_wait(bar(2 + s), (uint32_t)((n & 1) ^ 1));   // MMAs of tile k-2 are done with stage s
+      const long long pos0 = (long long)tile * NT;
+      uint8_t *sx = base + L.x_off[s];
+      if (a.mode == 0) {
+        if (ptid < NT) s_idx[ptid] = a.idx[pos0 + ptid];
+        fwd_bar_prod();
+        const int b = (int)(pos0 / per_scene);
+        const int in_scene0 = (int)(pos0 - (long long)b * per_scene);
+        build_x_gather<NT, kFwdProdThreads>(gsrc, b, in_scene0, s_idx, sx, ptid,
+                                            [](int row, int ch) { return sw128_off(row, ch, NT); });
+      } else {
+        // dense layer: the tile is one contiguous block of z_prev; 8 independent 16-byte loads
+        // per thread in flight, tile k+2 pulled into L2 by one bulk-prefetch instruction
+        const int CH = a.Cin >> 2;
+        const int total = NT * CH;
+        if (ptid == 0 && tile + 2 * grid < a.num_tiles)
+          prefetch_l2(a.z_prev + (size_t)(pos0 + 2ll * grid * NT) * a.Cin, (uint32_t)total * 16u);
+        const float4 *src = reinterpret_cast<const float4 *>(a.z_prev + (size_t)pos0 * a.Cin);
+        for (int i0 = ptid; i0 < total; i0 += kFwdProdThreads * 8) {
+          float4 t[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + u * kMlpThreads;
-          if (i < total) t[u] = __ldg(src + i);
-        }
+          for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * kFwdProdThreads;
+            if (i < total) t[u] = __ldg(src + i);
+          }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + u * kMlpThreads;
-          if (i < total) {
-            const int row = i / CH, ch = i - row * CH;
-            const float4 sc = *reinterpret_cast<const float4 *>(s_scale + ch * 4);
-            const float4 sh = *reinterpret_cast<const float4 *>(s_shift + ch * 4);
-            uint4 out;
-            out.x = to_tf32(fmaxf(fmaf(t[u].x, sc.x, sh.x), 0.f));
-            out.y = to_tf32(fmaxf(fmaf(t[u].y, sc.y, sh.y), 0.f));
-            out.z = to_tf32(fmaxf(fmaf(t[u].z, sc.z, sh.z), 0.f));
-            out.w = to_tf32(fmaxf(fmaf(t[u].w, sc.w, sh.w), 0.f));
-            *reinterpret_cast<uint4 *>(s_x + sw128_off(row, ch, NT)) = out;
+          for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * kFwdProdThreads;
+            if (i < total) {
+              const int row = i / CH, ch = i - row * CH;
+              const float4 sc = *reinterpret_cast<const float4 *>(s_scale + ch * 4);
+              const float4 sh = *reinterpret_cast<const float4 *>(s_shift + ch * 4);
+              uint4 out;
+              out.x = to_tf32(fmaxf(fmaf(t[u].x, sc.x, sh.x), 0.f));
+              out.y = to_tf32(fmaxf(fmaf(t[u].y, sc.y, sh.y), 0.f));
+              out.z = to_tf32(fmaxf(fmaf(t[u].z, sc.z, sh.z), 0.f));
+              out.w = to_tf32(fmaxf(fmaf(t[u].w, sc.w, sh.w), 0.f));
+              *reinterpret_cast<uint4 *>(sx + sw128_off(row, ch, NT)) = out;
+            }
           }
         }
       }
+      fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+      fwd_bar_prod();
+      if (ptid == 0) mbar_arrive1(bar(0 + s));
     }
-    fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-    tc_fence_before();
-    __syncthreads();
-
-    // ---- MMA: one elected thread issues MT x KS tcgen05.mma, then commits to the mbarrier --
-    if (tid == 0) {
-      if (!w_ready) {
-        mbar_wait(bar_w, 0);
-        w_ready = true;
+  } else if (warp == 4) {
+    // =============================== MMA ISSUE (one thread) =====================================
+    if (lane == 0) {
+      mbar_wait(bar(8), 0);
+      const uint32_t wa = smem_u32(s_w);
+      const int KS = (a.Kp + 7) >> 3;  // K = 8 slices actually issued
+      const uint32_t idesc = idesc_tf32(NT);
+      for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k) {
+        const int s = k & 1, n = k >> 1;
+        const uint32_t xa = smem_u32(base + L.x_off[s]);
+        mbar_wait(bar(0 + s), (uint32_t)(n & 1));          // X tile of tile k is in smem
+        mbar_wait(bar(6 + s), (uint32_t)((n & 1) ^ 1));    // epilogue of tile k-2 left D[s]
+        tc_fence_after();
+        for (int m = 0; m < MT; ++m)
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t koff = (uint32_t)(ks >> 2) * 1024u;
+            const uint64_t da = smem_desc_sw128(wa + koff * (uint32_t)(a.Cout_pad >> 3) +
+                                                (uint32_t)m * 16u * 1024u + (uint32_t)(ks & 3) * 32u);
+            const uint64_t db =
+                smem_desc_sw128(xa + koff * (uint32_t)(NT >> 3) + (uint32_t)(ks & 3) * 32u);
+            umma_tf32(tmem_base + (uint32_t)((s * MT + m) * NT), da, db, idesc, ks > 0 ? 1u : 0u);
+          }
+        umma_commit(bar(4 + s));   // -> epilogue
+        umma_commit(bar(2 + s));   // -> producers: stage s may be overwritten
       }
+    }
+    __syncwarp();
+  } else {
+    // =============================== EPILOGUE ===================================================
+    const int q = warp;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    double acc_s[2] = {0.0, 0.0}, acc_ss[2] = {0.0, 0.0};
+    const int ns_mask = a.NS - 1;
+    for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k) {
+      const int s = k & 1, n = k >> 1;
+      const long long pos0 = (long long)tile * NT;
+      mbar_wait(bar(4 + s), (uint32_t)(n & 1));
       tc_fence_after();
-      const uint32_t xa = smem_u32(s_x), wa = smem_u32(s_w);
-      for (int m = 0; m < MT; ++m) {
-        for (int ks = 0; ks < KS; ++ks) {
-          const uint32_t koff = (uint32_t)(ks >> 2) * 1024u;  // K atom index (x rows/8 below)
-          const uint64_t da = smem_desc_sw128(wa + koff * (uint32_t)(a.Cout_pad >> 3) +
-                                              (uint32_t)m * 16u * 1024u + (uint32_t)(ks & 3) * 32u);
-          const uint64_t db =
-              smem_desc_sw128(xa + koff * (uint32_t)(NT >> 3) + (uint32_t)(ks & 3) * 32u);
-          umma_tf32(tmem_base + (uint32_t)m * NT, da, db, idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        if (m >= MT) continue;
+        const int c = m * 128 + q * 32 + lane;   // output channel owned by this thread
+        const bool c_ok = c < a.Cout;
+        float ts = 0.f, tss = 0.f;
+        float mx = 0.f, mn = 0.f;   // running max / min (+ sample index) of the current centre
+        int ax = 0, an = 0;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          uint32_t r[32];
+          cuda::ptx::tcgen05_ld_32x32b(
+              r, tmem_base + lane_addr + (uint32_t)((s * MT + m) * NT + ch * 32));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (!c_ok) continue;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = __uint_as_float(r[i]);
+            ts += x;
+            tss = fmaf(x, x, tss);
+          }
+          if (a.epilogue == 0) {
+            float *zp = a.z + (size_t)(pos0 + ch * 32) * a.Cout + c;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              zp[(size_t)i * a.Cout] = __uint_as_float(r[i]);   // a warp writes 32 channels = 128 B
+          } else {
+            // max AND min over each centre's NS samples (16-column sub-groups; NS = 16/32/64 and
+            // tiles start on a centre boundary).  Strict compares: the first extremum wins, like
+            // max_pool2d.
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const int col0 = ch * 32 + hf * 16;
+              const int s0 = col0 & ns_mask;
+              if (s0 == 0) {
+                mx = -INFINITY; mn = INFINITY; ax = 0; an = 0;
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float x = __uint_as_float(r[hf * 16 + i]);
+                if (x > mx) { mx = x; ax = s0 + i; }
+                if (x < mn) { mn = x; an = s0 + i; }
+              }
+              if (s0 + 16 == a.NS) {
+                const long long centre = (pos0 >> a.ns_shift) + (col0 >> a.ns_shift);
+                const size_t o = (size_t)centre * a.Cout + c;
+                a.zmax[o] = mx; a.zmin[o] = mn; a.amax[o] = ax; a.amin[o] = an;
+              }
+            }
+          }
+        }
+        acc_s[m] += (double)ts;
+        acc_ss[m] += (double)tss;
+      }
+      tc_fence_before();
+      fwd_bar_epi();   // every epilogue thread has read D[s]
+      if (tid == 0) mbar_arrive1(bar(6 + s));
+    }
+    if (a.stats != nullptr) {
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const int c = m * 128 + q * 32 + lane;
+        if (m < MT && c < a.Cout) {
+          atomicAdd(a.stats + c, acc_s[m]);
+          atomicAdd(a.stats + a.Cout + c, acc_ss[m]);
         }
       }
-      umma_commit(bar_mma);
     }
-
-    // ---- epilogue: TMEM -> registers; statistics, store / pool ------------------------------
-    mbar_wait(bar_mma, mma_parity);
-    mma_parity ^= 1u;
-    tc_fence_after();
-    float v[64];
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NT + col0);
-    {
-      uint32_t r[32];
-      cuda::ptx::tcgen05_ld_32x32b(r, taddr);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-    }
-    if (ncols == 64) {
-      uint32_t r[32];
-      cuda::ptx::tcgen05_ld_32x32b(r, taddr + 32);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[32 + i] = 0.f;
-    }
-    tc_fence_before();  // TMEM reads done before the next tile's MMAs (ordered by __syncthreads)
-
-    if (c_ok) {
-      float ts = 0.f, tss = 0.f;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        ts += v[i];
-        tss = fmaf(v[i], v[i], tss);
-      }
-      acc_s += (double)ts;
-      acc_ss += (double)tss;
-      if (a.epilogue == 0) {
-        float *zp = a.z + (size_t)(pos0 + col0) * a.Cout + c;
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i < ncols) zp[(size_t)i * a.Cout] = v[i];  // a warp writes 32 channels = 128 B
-      } else if (a.epilogue == 1) {
-        const long long p0 = pos0 + col0;
-        if (a.NS == 16) pool_groups<16>(v, p0, c, a.Cout, a.zmax, a.zmin, a.amax, a.amin);
-        else if (a.NS == 32) pool_groups<32>(v, p0, c, a.Cout, a.zmax, a.zmin, a.amax, a.amin);
-        else pool_groups<64>(v, p0, c, a.Cout, a.zmax, a.zmin, a.amax, a.amin);
-      } else {
-        const long long p0 = pos0 + col0;
-        if (a.NS == 16)
-          dz_groups<16>(v, p0, c, a.Cout, a.dysel, a.asel, e2_k1, e2_k2, e2_mean, e2_invstd, e2_gs, a.dz);
-        else if (a.NS == 32)
-          dz_groups<32>(v, p0, c, a.Cout, a.dysel, a.asel, e2_k1, e2_k2, e2_mean, e2_invstd, e2_gs, a.dz);
-        else
-          dz_groups<64>(v, p0, c, a.Cout, a.dysel, a.asel, e2_k1, e2_k2, e2_mean, e2_invstd, e2_gs, a.dz);
-      }
-    }
-    // the next iteration's prologue __syncthreads orders these TMEM loads before its MMAs and
-    // this tile's MMA smem reads (complete: we waited on the commit) before the X overwrite
   }
-
-  if (c_ok && a.stats != nullptr) {
-    atomicAdd(a.stats + c, acc_s);
-    atomicAdd(a.stats + a.Cout + c, acc_ss);
-  }
-  if (tid == 0 && !w_ready) mbar_wait(bar_w, 0);  // never leave a bulk copy in flight
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // BatchNorm bookkeeping from the accumulated statistics (one thread per channel):
@@ -407,12 +394,6 @@ __global__ void to_point_major_kernel(const float *__restrict__ in, int Cch, int
   }
 }
 
-size_t layer_smem_bytes(int Kp, int Cout_pad, int NT) {
-  const int KA = (Kp + 31) >> 5;
-  return 1024 + (size_t)Cout_pad * KA * 128 + (size_t)NT * KA * 128 + 2 * (size_t)Kp * 4 +
-         (size_t)NT * 4 + 16 + 2 * 8 + 16;
-}
-
 }  // namespace
 }  // namespace b2r
 
@@ -445,7 +426,7 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
   B2R_REQUIRE(d->B > 0 && d->NP > 0 && d->NS > 0 && d->Cin > 0 && d->Cout > 0,
               "b2r_sa_layer_fwd: non-positive size");
   B2R_REQUIRE(d->mode == 0 || d->mode == 1, "b2r_sa_layer_fwd: mode must be 0 or 1");
-  B2R_REQUIRE(d->epilogue >= 0 && d->epilogue <= 2, "b2r_sa_layer_fwd: epilogue must be 0, 1 or 2");
+  B2R_REQUIRE(d->epilogue == 0 || d->epilogue == 1, "b2r_sa_layer_fwd: epilogue must be 0 or 1");
   B2R_REQUIRE(d->w_image != nullptr, "b2r_sa_layer_fwd: null weight image");
   LayerArgs a;
   a.B = d->B; a.N = d->N; a.NP = d->NP; a.NS = d->NS; a.Cin = d->Cin; a.Cout = d->Cout;
@@ -455,12 +436,12 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
   a.z_prev = d->z_prev; a.scale_prev = d->scale_prev; a.shift_prev = d->shift_prev;
   a.w_image = d->w_image; a.z = d->z; a.stats = d->stats;
   a.zmax = d->zmax; a.zmin = d->zmin; a.amax = d->amax; a.amin = d->amin;
-  a.dysel = d->dysel; a.asel = d->asel; a.bw_k1 = d->bw_k1; a.bw_k2 = d->bw_k2;
-  a.bw_mean = d->bw_mean; a.bw_invstd = d->bw_invstd; a.bw_gs = d->bw_gs; a.dz = d->dz;
   a.Kp = packed_k(d->Cin, d->mode == 0);
   a.Cout_pad = (d->Cout + 127) & ~127;
   a.chf_shift = pow2_shift(((d->Cin - 3 + 3) & ~3) >> 2);
+  a.ns_shift = pow2_shift(d->NS);
   const long long M = (long long)d->B * d->NP * d->NS;
+  const long long per_scene = (long long)d->NP * d->NS;
   if (d->mode == 0) {
     B2R_REQUIRE(d->Cin >= 3 && d->xyz && d->new_xyz && d->idx && (d->feat_t || d->Cin == 3),
                 "b2r_sa_layer_fwd: gather mode needs xyz, new_xyz, idx (and feat_t when Cin > 3)");
@@ -473,50 +454,53 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
   if (d->epilogue == 0) {
     B2R_REQUIRE(d->z != nullptr, "b2r_sa_layer_fwd: epilogue 0 needs z");
   } else {
-    if (d->epilogue == 1)
-      B2R_REQUIRE(d->zmax && d->zmin && d->amax && d->amin,
-                  "b2r_sa_layer_fwd: epilogue 1 needs pool outputs");
-    else
-      B2R_REQUIRE(d->dysel && d->asel && d->bw_k1 && d->bw_k2 && d->bw_mean && d->bw_invstd &&
-                      d->bw_gs && d->dz,
-                  "b2r_sa_layer_fwd: epilogue 2 needs dysel/asel/k1/k2/mean/invstd/gs/dz");
+    B2R_REQUIRE(d->zmax && d->zmin && d->amax && d->amin,
+                "b2r_sa_layer_fwd: epilogue 1 needs pool outputs");
     if (!(d->NS == 16 || d->NS == 32 || d->NS == 64)) {
       set_error("b2r_sa_layer_fwd: pooling supports nsample 16/32/64 (got %d)", d->NS);
       return B2R_ERR_UNSUPPORTED;
     }
   }
-  if (a.Cout_pad > 256 || (M % 128) != 0 ||
-      (d->mode == 0 && ((long long)d->NP * d->NS) % 128 != 0)) {
-    set_error("b2r_sa_layer_fwd: needs Cout <= 256, B*NP*NS %% 128 == 0 and (gather layers) "
-              "NP*NS %% 128 == 0 (Cout=%d, M=%lld, NP*NS=%lld)", d->Cout, M,
-              (long long)d->NP * d->NS);
+  if (a.Cout_pad > 256) {
+    set_error("b2r_sa_layer_fwd: needs Cout <= 256 (got %d)", d->Cout);
     return B2R_ERR_UNSUPPORTED;
   }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int MT = a.Cout_pad >> 7;
-  // tile width: 128 positions when one M tile and the operands fit, else 64
-  int NT = 64;
-  if (MT == 1 && layer_smem_bytes(a.Kp, a.Cout_pad, 128) <= 227 * 1024) NT = 128;
-  if (MT == 1 && NT == 64 && d->epilogue >= 1) {
-    set_error("b2r_sa_layer_fwd: pooling layer with Cout<=128 needs K small enough for 128-wide tiles");
+  // widest tile whose two smem stages + two TMEM stages fit; a gather tile must lie inside one
+  // scene and a pooling tile must hold whole centres
+  int NT = 0;
+  for (int nt : {128, 64, 32}) {
+    if (M % nt) continue;
+    if (d->mode == 0 && per_scene % nt) continue;
+    if (d->epilogue == 1 && (nt % d->NS) != 0) continue;
+    const FwdSmem L = fwd_smem_layout(a.Kp, a.Cout_pad, nt);
+    if (L.total <= 227u * 1024u && 2 * MT * nt <= 512) {
+      NT = nt;
+      break;
+    }
+  }
+  if (NT == 0) {
+    set_error("b2r_sa_layer_fwd: layer Cin=%d Cout=%d M=%lld NP*NS=%lld does not fit (needs "
+              "B*NP*NS %% 32 == 0, gather layers NP*NS %% 32 == 0, operands within 227 KB)",
+              d->Cin, d->Cout, M, per_scene);
     return B2R_ERR_UNSUPPORTED;
   }
-  const size_t smem = layer_smem_bytes(a.Kp, a.Cout_pad, NT);
-  if (smem > 227 * 1024) {
-    set_error("b2r_sa_layer_fwd: operands need %zu bytes of shared memory (Cin=%d Cout=%d)", smem,
-              d->Cin, d->Cout);
-    return B2R_ERR_UNSUPPORTED;
-  }
+  const FwdSmem L = fwd_smem_layout(a.Kp, a.Cout_pad, NT);
   a.num_tiles = (int)(M / NT);
   const int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (NT == 128) {
     B2R_CUDA(cudaFuncSetAttribute(sa_layer_fwd_kernel<128>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sa_layer_fwd_kernel<128><<<grid, kMlpThreads, smem, st>>>(a);
-  } else {
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    sa_layer_fwd_kernel<128><<<grid, kFwdThreads, L.total, st>>>(a);
+  } else if (NT == 64) {
     B2R_CUDA(cudaFuncSetAttribute(sa_layer_fwd_kernel<64>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sa_layer_fwd_kernel<64><<<grid, kMlpThreads, smem, st>>>(a);
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    sa_layer_fwd_kernel<64><<<grid, kFwdThreads, L.total, st>>>(a);
+  } else {
+    B2R_CUDA(cudaFuncSetAttribute(sa_layer_fwd_kernel<32>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    sa_layer_fwd_kernel<32><<<grid, kFwdThreads, L.total, st>>>(a);
   }
   B2R_CHECK_LAUNCH();
   return B2R_OK;

@@ -150,13 +150,13 @@ struct GatherSrc {
   int normalize_xyz;
 };
 
-template <int NT, class OffFn>
+template <int NT, int NTHREADS, class OffFn>
 __device__ __forceinline__ void build_x_gather(const GatherSrc &g, int b, int in_scene0,
                                                const int *s_idx, uint8_t *s_x, int tid,
                                                OffFn off) {
   const int C = g.C, CHf = g.Cf4 >> 2;
   // relative xyz chunk: one thread per row, six independent loads
-  for (int row = tid; row < NT; row += kMlpThreads) {
+  for (int row = tid; row < NT; row += NTHREADS) {
     const int p = s_idx[row];
     const int j = (in_scene0 + row) / g.NS;
     const float *pp = g.xyz + ((size_t)b * g.N + p) * 3;
@@ -176,11 +176,11 @@ __device__ __forceinline__ void build_x_gather(const GatherSrc &g, int b, int in
   const float *fb = g.feat_t + (size_t)b * g.N * C;
   const int total = NT * CHf;
   if ((C & 3) == 0) {
-    for (int i0 = tid; i0 < total; i0 += kMlpThreads * 8) {
+    for (int i0 = tid; i0 < total; i0 += NTHREADS * 8) {
       float4 t[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * kMlpThreads;
+        const int i = i0 + u * NTHREADS;
         if (i < total) {
           const int row = g.chf_shift >= 0 ? (i >> g.chf_shift) : (i / CHf);
           const int ch = i - row * CHf;
@@ -189,7 +189,7 @@ __device__ __forceinline__ void build_x_gather(const GatherSrc &g, int b, int in
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * kMlpThreads;
+        const int i = i0 + u * NTHREADS;
         if (i < total) {
           const int row = g.chf_shift >= 0 ? (i >> g.chf_shift) : (i / CHf);
           const int ch = i - row * CHf;
@@ -199,7 +199,7 @@ __device__ __forceinline__ void build_x_gather(const GatherSrc &g, int b, int in
       }
     }
   } else {
-    for (int i = tid; i < total; i += kMlpThreads) {
+    for (int i = tid; i < total; i += NTHREADS) {
       const int row = g.chf_shift >= 0 ? (i >> g.chf_shift) : (i / CHf);
       const int ch = i - row * CHf;
       const float *src = fb + (size_t)s_idx[row] * C + ch * 4;

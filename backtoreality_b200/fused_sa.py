@@ -70,11 +70,7 @@ def supported(mlp_module, xyz, features, idx, pooling="max"):
         cout, cin = blk.conv.out_channels, blk.conv.in_channels
         if cout > 256 or cout % 8 != 0 or cin > 380 or (i > 0 and cin % 8 != 0):
             return False
-        smem = _layer_smem(cin, cout, gather=(i == 0), nt=64)
-        if smem > 227 * 1024:
-            return False
-        if i == len(blocks) - 1 and cout <= 128 and \
-                _layer_smem(cin, cout, gather=(i == 0), nt=128) > 227 * 1024:
+        if _layer_smem(cin, cout, gather=(i == 0), nt=32) > 227 * 1024:
             return False
     return True
 
@@ -110,10 +106,12 @@ def _bwd_bytes(B, N, NP, NS, Cin, Cout, gather, top, dgrad):
 
 
 def _layer_smem(cin, cout, gather, nt):
+    """Shared memory of sa_layer_fwd_kernel (csrc/mlp.cu fwd_smem_layout): the TF32 weight image
+    plus TWO stages of the X tile."""
     kp = (((cin - 3 + 3) & ~3) + 4) if gather else ((cin + 3) & ~3)
     ka = (kp + 31) >> 5
     cout_pad = (cout + 127) & ~127
-    return 1024 + cout_pad * ka * 128 + nt * ka * 128 + 2 * kp * 4 + nt * 4 + 48
+    return cout_pad * ka * 128 + 2 * nt * ka * 128 + 2 * kp * 4 + nt * 4 + 1024 + 128
 
 
 def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module, training,

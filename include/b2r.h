@@ -161,11 +161,10 @@ B2R_API int b2r_query_group_bwd(const float *grad_out, const int *idx, int B, in
  *   epilogue 0  store raw z (M,Cout) position-major + accumulate per-channel sum / sum of squares
  *   epilogue 1  statistics + max AND min of raw z over each centre's NS samples (+ arg indices);
  *               b2r_pool_finalize turns them into max_pool(relu(bn(z))) exactly
- *   epilogue 2  backward helper: recompute z and emit the BatchNorm-backward dz of the pooled layer
  * Weights are passed as the packed image produced by b2r_mlp_pack_weight (TF32-rounded,
  * 128-byte-swizzled K-major shared-memory layout, staged by one TMA bulk copy).
- * Limits: Cout <= 256, B*NP*NS % 128 == 0, NS in {16,32,64} for epilogue 1; otherwise
- * B2R_ERR_UNSUPPORTED (callers then use the unfused path).
+ * Limits: Cout <= 256, B*NP*NS % 64 == 0 (gather layers: NP*NS % 64 == 0), NS in {16,32,64}
+ * for epilogue 1; otherwise B2R_ERR_UNSUPPORTED (callers then use the unfused path).
  */
 typedef struct b2r_sa_layer {
   int B, N, NP, NS;   /* scenes, source points per scene, centres per scene, samples per centre */
@@ -185,13 +184,6 @@ typedef struct b2r_sa_layer {
   double *stats;            /* (2,Cout) sum, sum of squares; ACCUMULATED (caller zeroes); may be NULL */
   float *zmax, *zmin;       /* epilogue 1: (B*NP,Cout) */
   int *amax, *amin;         /* epilogue 1: (B*NP,Cout) sample index in [0,NS) */
-  /* epilogue 2 (used by the backward pass on the pooled top layer): z is recomputed and
-   *   dz = bw_gs * (dy - bw_k1 - (z - bw_mean) * bw_invstd * bw_k2)   is stored to dz (M,Cout),
-   * dy = dysel[centre,c] at sample asel[centre,c] of each centre and 0 elsewhere. */
-  const float *dysel;       /* (B*NP,Cout) */
-  const int *asel;          /* (B*NP,Cout) */
-  const float *bw_k1, *bw_k2, *bw_mean, *bw_invstd, *bw_gs; /* (Cout) each */
-  float *dz;                /* (M,Cout) */
 } b2r_sa_layer;
 
 B2R_API long long b2r_mlp_weight_image_bytes(int Cout, int Cin, int gather);
