@@ -72,7 +72,7 @@ struct LayerArgs {
   double *stats;
   float *zmax, *zmin;
   int *amax, *amin;
-  int Kp, Cout_pad, num_tiles, chf_shift, ns_shift;
+  int Kp, Cout_pad, num_tiles, chf_shift, ns_shift, raw_stage;
 };
 
 // Warp roles (12 warps = 3 per SM sub-partition -> 168 registers/thread):
@@ -86,9 +86,12 @@ constexpr int kFwdEpiThreads = 128, kFwdProdThreads = 224;
 constexpr int kFwdThreads = kFwdEpiThreads + 32 + kFwdProdThreads;   // 384
 
 struct FwdSmem {
-  uint32_t w_off, w_bytes, x_off[2], x_bytes, scale_off, idx_off, bar_off, total;
+  uint32_t w_off, w_bytes, x_off[2], x_bytes, raw_off[2], raw_bytes, scale_off, idx_off, bar_off,
+      total;
 };
-__host__ __device__ inline FwdSmem fwd_smem_layout(int Kp, int Cout_pad, int NT) {
+// raw_cin > 0 (dense layers): two raw staging buffers of NT x raw_cin fp32, filled by TMA bulk
+// copies two tiles ahead, so the producers never wait on a global load
+__host__ __device__ inline FwdSmem fwd_smem_layout(int Kp, int Cout_pad, int NT, int raw_cin) {
   FwdSmem s;
   const uint32_t KA = (uint32_t)(Kp + 31) >> 5;
   s.w_off = 0;
@@ -96,10 +99,13 @@ __host__ __device__ inline FwdSmem fwd_smem_layout(int Kp, int Cout_pad, int NT)
   s.x_bytes = (uint32_t)NT * KA * 128u;
   s.x_off[0] = s.w_bytes;
   s.x_off[1] = s.w_bytes + s.x_bytes;
-  s.scale_off = s.x_off[1] + s.x_bytes;
+  s.raw_bytes = (uint32_t)NT * raw_cin * 4u;
+  s.raw_off[0] = s.x_off[1] + s.x_bytes;
+  s.raw_off[1] = s.raw_off[0] + s.raw_bytes;
+  s.scale_off = s.raw_off[1] + s.raw_bytes;
   s.idx_off = s.scale_off + 2u * Kp * 4u;
   s.bar_off = (s.idx_off + (uint32_t)NT * 4u + 15u) & ~15u;
-  s.total = s.bar_off + 9 * 8 + 16 + 1024;   // + alignment slack
+  s.total = s.bar_off + 11 * 8 + 16 + 1024;   // + alignment slack
   return s;
 }
 __device__ __forceinline__ void fwd_bar_epi() {
@@ -118,14 +124,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~(uintptr_t)1023);
-  const FwdSmem L = fwd_smem_layout(a.Kp, a.Cout_pad, NT);
+  const FwdSmem L = fwd_smem_layout(a.Kp, a.Cout_pad, NT, a.raw_stage ? a.Cin : 0);
   uint8_t *s_w = base + L.w_off;
   float *s_scale = reinterpret_cast<float *>(base + L.scale_off);
   float *s_shift = s_scale + a.Kp;
   int *s_idx = reinterpret_cast<int *>(base + L.idx_off);
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(base + L.bar_off);
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 9);
-  // mbarriers: [0,1] full  [2,3] empty  [4,5] mma_done  [6,7] d_free  [8] weights
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 11);
+  // mbarriers: [0,1] full  [2,3] empty  [4,5] mma_done  [6,7] d_free  [8] weights  [9,10] raw
   auto bar = [&](int i) { return smem_u32(&s_bar[i]); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -135,7 +141,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
   const int grid = (int)gridDim.x;
 
   if (tid == 0) {
-    for (int i = 0; i < 9; ++i) mbar_init(bar(i), 1);
+    for (int i = 0; i < 11; ++i) mbar_init(bar(i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) tmem_alloc(smem_u32(s_tmem), kTmemCols);
@@ -165,6 +171,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
     gsrc.N = a.N; gsrc.NP = a.NP; gsrc.NS = a.NS; gsrc.C = a.Cin - 3;
     gsrc.Cf4 = (a.Cin - 3 + 3) & ~3;
     gsrc.chf_shift = a.chf_shift; gsrc.radius = a.radius; gsrc.normalize_xyz = a.normalize_xyz;
+    if (a.raw_stage && ptid == 0) {   // prime the raw ring with this CTA's first two tiles
+      for (int k = 0; k < 2; ++k) {
+        const long long tile = (long long)blockIdx.x + (long long)k * grid;
+        if (tile < a.num_tiles) {
+          mbar_expect_tx(bar(9 + k), L.raw_bytes);
+          bulk_g2s(smem_u32(base + L.raw_off[k]), a.z_prev + (size_t)(tile * NT) * a.Cin,
+                   L.raw_bytes, bar(9 + k));
+        }
+      }
+    }
     for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k) {
       const int s = k & 1, n = k >> 1;
       mbar_wait(bar(2 + s), (uint32_t)((n & 1) ^ 1));   // MMAs of tile k-2 are done with stage s
@@ -177,9 +193,28 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
         const int in_scene0 = (int)(pos0 - (long long)b * per_scene);
         build_x_gather<NT, kFwdProdThreads>(gsrc, b, in_scene0, s_idx, sx, ptid,
                                             [](int row, int ch) { return sw128_off(row, ch, NT); });
+      } else if (a.raw_stage) {
+        // dense layer, TMA-staged: the tile (one contiguous block of z_prev) was bulk-copied into
+        // raw[s] two tiles ago; producers only transform smem -> smem (BN + ReLU + TF32 + swizzle)
+        const int CH = a.Cin >> 2;
+        const int total = NT * CH;
+        mbar_wait(bar(9 + s), (uint32_t)(n & 1));
+        const float4 *src = reinterpret_cast<const float4 *>(base + L.raw_off[s]);
+        for (int i = ptid; i < total; i += kFwdProdThreads) {
+          const float4 t = src[i];
+          const int row = i / CH, ch = i - row * CH;
+          const float4 sc = *reinterpret_cast<const float4 *>(s_scale + ch * 4);
+          const float4 sh = *reinterpret_cast<const float4 *>(s_shift + ch * 4);
+          uint4 out;
+          out.x = to_tf32(fmaxf(fmaf(t.x, sc.x, sh.x), 0.f));
+          out.y = to_tf32(fmaxf(fmaf(t.y, sc.y, sh.y), 0.f));
+          out.z = to_tf32(fmaxf(fmaf(t.z, sc.z, sh.z), 0.f));
+          out.w = to_tf32(fmaxf(fmaf(t.w, sc.w, sh.w), 0.f));
+          *reinterpret_cast<uint4 *>(sx + sw128_off(row, ch, NT)) = out;
+        }
       } else {
-        // dense layer: the tile is one contiguous block of z_prev; 8 independent 16-byte loads
-        // per thread in flight, tile k+2 pulled into L2 by one bulk-prefetch instruction
+        // dense layer, register-staged fallback (operands too large for the raw buffers):
+        // 8 independent 16-byte loads per thread in flight, tile k+2 prefetched into L2
         const int CH = a.Cin >> 2;
         const int total = NT * CH;
         if (ptid == 0 && tile + 2 * grid < a.num_tiles)
@@ -209,9 +244,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
           }
         }
       }
-      fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+      fence_async_smem();   // generic-proxy accesses ordered before the async proxy (MMA, TMA)
       fwd_bar_prod();
-      if (ptid == 0) mbar_arrive1(bar(0 + s));
+      if (ptid == 0) {
+        mbar_arrive1(bar(0 + s));
+        if (a.raw_stage && tile + 2 * grid < a.num_tiles) {   // refill raw[s] with tile k+2
+          mbar_expect_tx(bar(9 + s), L.raw_bytes);
+          bulk_g2s(smem_u32(base + L.raw_off[s]),
+                   a.z_prev + (size_t)(pos0 + 2ll * grid * NT) * a.Cin, L.raw_bytes, bar(9 + s));
+        }
+      }
     }
   } else if (warp == 4) {
     // =============================== MMA ISSUE (one thread) =====================================
@@ -469,23 +511,27 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
   // widest tile whose two smem stages + two TMEM stages fit; a gather tile must lie inside one
   // scene and a pooling tile must hold whole centres
   int NT = 0;
-  for (int nt : {128, 64, 32}) {
-    if (M % nt) continue;
-    if (d->mode == 0 && per_scene % nt) continue;
-    if (d->epilogue == 1 && (nt % d->NS) != 0) continue;
-    const FwdSmem L = fwd_smem_layout(a.Kp, a.Cout_pad, nt);
-    if (L.total <= 227u * 1024u && 2 * MT * nt <= 512) {
-      NT = nt;
-      break;
+  a.raw_stage = 0;
+  for (int raw = (d->mode == 1 ? 1 : 0); raw >= 0 && NT == 0; --raw)
+    for (int nt : {128, 64, 32}) {
+      if (M % nt) continue;
+      if (d->mode == 0 && per_scene % nt) continue;
+      if (d->epilogue == 1 && (nt % d->NS) != 0) continue;
+      if (raw && nt < 64) continue;   // prefer wider register-staged tiles over tiny TMA ones
+      const FwdSmem L = fwd_smem_layout(a.Kp, a.Cout_pad, nt, raw ? d->Cin : 0);
+      if (L.total <= 227u * 1024u && 2 * MT * nt <= 512) {
+        NT = nt;
+        a.raw_stage = raw;
+        break;
+      }
     }
-  }
   if (NT == 0) {
     set_error("b2r_sa_layer_fwd: layer Cin=%d Cout=%d M=%lld NP*NS=%lld does not fit (needs "
               "B*NP*NS %% 32 == 0, gather layers NP*NS %% 32 == 0, operands within 227 KB)",
               d->Cin, d->Cout, M, per_scene);
     return B2R_ERR_UNSUPPORTED;
   }
-  const FwdSmem L = fwd_smem_layout(a.Kp, a.Cout_pad, NT);
+  const FwdSmem L = fwd_smem_layout(a.Kp, a.Cout_pad, NT, a.raw_stage ? d->Cin : 0);
   a.num_tiles = (int)(M / NT);
   const int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
