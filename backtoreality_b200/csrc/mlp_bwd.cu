@@ -31,8 +31,8 @@
 // not double-buffer the 128->256 layers in 227 KB.)  BF16 operand rounding (2^-9) adds ~3e-3 to a
 // gradient whose TF32-forward noise floor is 3-4e-2 (profiles/r01/tf32_gradient_noise*.log).
 //
-// Warp roles (12 warps): 0-3 epilogue (one TMEM lane quadrant each), 4 MMA issue (one thread),
-// 5-11 producers (global loads -> transform -> swizzled smem).  Two smem stages and two TMEM
+// Warp roles (12 warps): EW = 4 (or 8, top layer) epilogue warps (one TMEM lane quadrant each),
+// then 1 MMA-issue warp (one thread), then the producers (global loads -> transform -> smem).  Two smem stages and two TMEM
 // stages for D1/D2, mbarrier hand-offs (full / empty / z_done / dz_ready / mma_done / d2_free):
 // producers run up to two tiles ahead of the tensor core, stores and scatters trail behind.
 #include <cuda_bf16.h>
@@ -43,9 +43,11 @@ namespace b2r {
 using namespace mlp;
 namespace {
 
-constexpr int kEpiWarps = 4, kProdWarps = 7;   // 12 warps = 3 per SM sub-partition -> 168 regs
-constexpr int kEpiThreads = kEpiWarps * 32, kProdThreads = kProdWarps * 32;
-constexpr int kBwdThreads = kEpiThreads + 32 + kProdThreads;   // 384
+// 12 warps = 3 per SM sub-partition -> 168 registers/thread.  EW epilogue warps (4, or 8 for the
+// pooled top layer whose epilogue warps also turn the recomputed z into DZ and are the critical
+// role there), 1 MMA warp, 11 - EW producer warps.
+constexpr int kBwdWarps = 12;
+constexpr int kBwdThreads = kBwdWarps * 32;   // 384
 
 struct BwdArgs {
   int B, N, NP, NS, Cin, Cout, mode, top;
@@ -133,8 +135,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t *>(&v);
 }
-__device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads)); }
-__device__ __forceinline__ void bar_prod() { asm volatile("bar.sync 2, %0;" ::"n"(kProdThreads)); }
+template <int N>
+__device__ __forceinline__ void bar_named(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(N));
+}
 
 // W (Cout, Cin) fp32 -> BF16 K-major SW128 image, rows = Cout (padded to 128), contraction
 // dimension = packed K (this kernel's order), WA 64-wide atoms (zero padded)
@@ -161,8 +165,11 @@ __global__ void pack_weight_bf16_kernel(const float *__restrict__ w, int Cout, i
   }
 }
 
-template <int NT>
+template <int NT, int EW>
 __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdArgs a) {
+  constexpr int kEpiThreads = EW * 32, kProdThreads = (kBwdWarps - 1 - EW) * 32;
+  auto bar_epi = [] { bar_named<kEpiThreads>(1); };
+  auto bar_prod = [] { bar_named<kProdThreads>(2); };
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~(uintptr_t)1023);
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
     for (int i = 0; i < 13; ++i) mbar_init(bar(i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) tmem_alloc(smem_u32(s_tmem), kTmemCols);
+  if (warp == EW) tmem_alloc(smem_u32(s_tmem), kTmemCols);
   {  // zero both stages of both tiles once: padding chunks are never written again
     const uint32_t zb = 2u * (L.x_bytes + L.dz_bytes);
     for (uint32_t i = tid * 16; i < zb; i += kBwdThreads * 16)
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
   }
   const int grid = (int)gridDim.x;
 
-  if (warp > 4) {
+  if (warp > EW) {
     // =============================== PRODUCERS (7 warps) ========================================
     const int ptid = tid - (kEpiThreads + 32);
     const int CH8 = a.Cout >> 3;     // 16-byte BF16 chunks per DZ row
@@ -399,7 +406,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
       bar_prod();
       if (ptid == 0) mbar_arrive(bar(0 + s));
     }
-  } else if (warp == 4) {
+  } else if (warp == EW) {
     // =============================== MMA ISSUE (one thread) =====================================
     if (lane == 0) {
       if (need_w) mbar_wait(bar(12), 0);
@@ -460,7 +467,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
     __syncwarp();
   } else {
     // =============================== EPILOGUE (4 warps, one TMEM lane quadrant each) ============
-    const int q = warp;
+    // warp w: TMEM lane quadrant q = w & 3; with 8 epilogue warps the two warps of a quadrant
+    // split the 32-column chunks by parity h = w >> 2
+    const int q = warp & 3, h = warp >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float s1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f};
     double d1[3] = {0.0, 0.0, 0.0}, d2[3] = {0.0, 0.0, 0.0};
@@ -500,6 +509,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
         const float ca = ok ? s_ca[co] : 0.f, cb = ok ? s_cb[co] : 0.f, cc = ok ? s_cc[co] : 0.f;
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
+          if (EW == 8 && (ch & 1) != h) continue;
           uint32_t r[32];
           cuda::ptx::tcgen05_ld_32x32b(r, d12 + lane_addr + (uint32_t)(ml * NT + ch * 32));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -548,6 +558,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
           if (m >= MTp) continue;
 #pragma unroll
           for (int cc = 0; cc < NCH; ++cc) {
+            if (EW == 8 && (cc & 1) != h) continue;
             uint32_t r[32];
             cuda::ptx::tcgen05_ld_32x32b(r, d12 + lane_addr + (uint32_t)(m * NT + cc * 32));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -632,7 +643,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
       tc_fence_after();
       for (int ml = 0; ml < MTl; ++ml) {
         const int co = ml * 128 + q * 32 + lane;
-        for (int at = 0; at < KA * 2; ++at) {
+        for (int at = (EW == 8 ? h : 0); at < KA * 2; at += (EW == 8 ? 2 : 1)) {
           uint32_t r[32];
           cuda::ptx::tcgen05_ld_32x32b(
               r, tmem_base + lane_addr + d3_col0 + (uint32_t)(ml * KA * 64 + at * 32));
@@ -657,7 +668,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == EW) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ---- max-pool / ReLU / BatchNorm backward of the pooled top layer: the sparse part ------------
@@ -855,15 +866,17 @@ extern "C" int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *d, void *stream) {
   a.num_tiles = (int)(M / NT);
   const int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define B2R_LAUNCH_BWD(NTV)                                                                     \
+#define B2R_LAUNCH_BWD(NTV, EWV)                                                                \
   do {                                                                                          \
-    B2R_CUDA(cudaFuncSetAttribute(sa_layer_bwd_kernel<NTV>,                                     \
+    B2R_CUDA(cudaFuncSetAttribute(sa_layer_bwd_kernel<NTV, EWV>,                                \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));  \
-    sa_layer_bwd_kernel<NTV><<<grid, kBwdThreads, L.total, st>>>(a);                            \
+    sa_layer_bwd_kernel<NTV, EWV><<<grid, kBwdThreads, L.total, st>>>(a);                       \
   } while (0)
-  if (NT == 128) B2R_LAUNCH_BWD(128);
-  else if (NT == 64) B2R_LAUNCH_BWD(64);
-  else B2R_LAUNCH_BWD(32);
+  // the pooled top layer runs 8 epilogue warps (they also build DZ from the recomputed z)
+  const bool wide_epi = a.top && NT >= 64;
+  if (NT == 128) { if (wide_epi) B2R_LAUNCH_BWD(128, 8); else B2R_LAUNCH_BWD(128, 4); }
+  else if (NT == 64) { if (wide_epi) B2R_LAUNCH_BWD(64, 8); else B2R_LAUNCH_BWD(64, 4); }
+  else B2R_LAUNCH_BWD(32, 4);
 #undef B2R_LAUNCH_BWD
   B2R_CHECK_LAUNCH();
   return B2R_OK;
