@@ -47,6 +47,7 @@ class SaLayer(ctypes.Structure):
         ("z_prev", _vp), ("scale_prev", _vp), ("shift_prev", _vp),
         ("w_image", _vp), ("z", _vp), ("stats", _vp),
         ("zmax", _vp), ("zmin", _vp), ("amax", _vp), ("amin", _vp),
+        ("sm_limit", _i),
     ]
 
 

@@ -10,7 +10,16 @@ layer (256 vs 288), selected with `fp2_out`.
 import torch
 import torch.nn as nn
 
+from . import fused_sa, pointnet2_utils
 from .pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
+
+# FPS, centre gather and ball query of ALL four levels depend only on xyz:
+# run them as a chain on a side stream so that FPS of level l+1 overlaps the MLP of level l.
+GEOMETRY_STREAM = True
+# FPS runs one CTA (N <= 4096) per scene and cannot share an SM with an MLP CTA (which owns the
+# whole register file), so the concurrent MLP kernels leave this many SMs free
+GEOMETRY_SMS = 8
+_GEO_STREAMS = {}   # device -> side stream (module-level: nn.Module copies stay picklable)
 
 
 class Pointnet2Backbone(nn.Module):
@@ -39,28 +48,56 @@ class Pointnet2Backbone(nn.Module):
         features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
         return xyz, features
 
+    def _geometry_prepass(self, xyz):
+        """inds / new_xyz / ball-query idx of sa1..sa4 on a side stream, one event per level."""
+        main = torch.cuda.current_stream()
+        side = _GEO_STREAMS.get(xyz.device)
+        if side is None:
+            side = _GEO_STREAMS[xyz.device] = torch.cuda.Stream(device=xyz.device)
+        side.wait_stream(main)
+        levels, cur = [], xyz
+        with torch.cuda.stream(side), torch.no_grad():
+            for sa in (self.sa1, self.sa2, self.sa3, self.sa4):
+                inds = pointnet2_utils.furthest_point_sample(cur, sa.npoint)
+                new_xyz = pointnet2_utils.gather_operation(
+                    cur.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
+                idx = pointnet2_utils.ball_query(sa.radius, sa.nsample, cur, new_xyz)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                for t in (inds, new_xyz, idx):
+                    t.record_stream(main)
+                levels.append({"inds": inds, "new_xyz": new_xyz, "idx": idx, "event": ev,
+                               "sm_limit": fused_sa.NUM_SMS - GEOMETRY_SMS})
+                cur = new_xyz
+        levels[-1]["sm_limit"] = 0   # nothing runs beside sa4's MLP
+        return levels
+
     def forward(self, pointcloud: torch.Tensor, end_points=None):
         """pointcloud (B,N,3+input_feature_dim) -> end_points dict (sa{1..4}_xyz/features,
         sa1_inds, sa2_inds, fp2_features, fp2_xyz, fp2_inds)."""
         if not end_points:
             end_points = {}
         xyz, features = self._break_up_pc(pointcloud)
+        geo = [None] * 4
+        if (GEOMETRY_STREAM and xyz.is_cuda and not xyz.requires_grad
+                and all(m.fusable(xyz) for m in (self.sa1, self.sa2, self.sa3, self.sa4))):
+            geo = self._geometry_prepass(xyz)
 
-        xyz, features, fps_inds = self.sa1(xyz, features)
+        xyz, features, fps_inds = self.sa1(xyz, features, geometry=geo[0])
         end_points['sa1_inds'] = fps_inds
         end_points['sa1_xyz'] = xyz
         end_points['sa1_features'] = features
 
-        xyz, features, fps_inds = self.sa2(xyz, features)
+        xyz, features, fps_inds = self.sa2(xyz, features, geometry=geo[1])
         end_points['sa2_inds'] = fps_inds
         end_points['sa2_xyz'] = xyz
         end_points['sa2_features'] = features
 
-        xyz, features, fps_inds = self.sa3(xyz, features)
+        xyz, features, fps_inds = self.sa3(xyz, features, geometry=geo[2])
         end_points['sa3_xyz'] = xyz
         end_points['sa3_features'] = features
 
-        xyz, features, fps_inds = self.sa4(xyz, features)
+        xyz, features, fps_inds = self.sa4(xyz, features, geometry=geo[3])
         end_points['sa4_xyz'] = xyz
         end_points['sa4_features'] = features
 

@@ -533,7 +533,11 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
   }
   const FwdSmem L = fwd_smem_layout(a.Kp, a.Cout_pad, NT, a.raw_stage ? d->Cin : 0);
   a.num_tiles = (int)(M / NT);
-  const int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
+  // persistent grid: one CTA per SM, or fewer when the caller keeps SMs free for kernels running
+  // concurrently on another stream (the geometry pre-pass: FPS needs whole SMs to itself)
+  int sms = kNumSMs;
+  if (d->sm_limit > 0 && d->sm_limit < kNumSMs) sms = d->sm_limit;
+  const int grid = a.num_tiles < sms ? a.num_tiles : sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (NT == 128) {
     B2R_CUDA(cudaFuncSetAttribute(sa_layer_fwd_kernel<128>,

@@ -115,7 +115,7 @@ def _layer_smem(cin, cout, gather, nt):
 
 
 def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module, training,
-                   want_point_major=True, save=None):
+                   want_point_major=True, save=None, sm_limit=0):
     """Run the fused block.
 
     xyz (B,N,3), new_xyz (B,NP,3), feat_t (B,N,C) POINT-major features or None, idx (B,NP,NS).
@@ -159,6 +159,7 @@ def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
         else:
             d.z_prev, d.scale_prev, d.shift_prev = _ptr(z_prev), _ptr(scale), _ptr(shift)
         d.w_image = _ptr(image)
+        d.sm_limit = int(sm_limit)
         z = None
         if last:
             zmax = torch.empty((B * NP, Cout), dtype=torch.float32, device=dev)
@@ -323,12 +324,13 @@ class _FusedSABlock(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xyz, new_xyz, features, idx, radius, normalize_xyz, mlp_module, training,
-                *params):
+                sm_limit, *params):
         feat_t = to_point_major(features.contiguous()) if features is not None else None
         need = any(ctx.needs_input_grad)
         save = {} if need else None
         out_cm, _ = sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
-                                   training, want_point_major=False, save=save)
+                                   training, want_point_major=False, save=save,
+                                   sm_limit=sm_limit)
         if need:
             ctx.saved = (xyz, new_xyz, feat_t, idx, float(radius), bool(normalize_xyz),
                          bool(training), save, params)
@@ -345,20 +347,24 @@ class _FusedSABlock(torch.autograd.Function):
             g_out.contiguous(), xyz, new_xyz, feat_t, idx, radius, normalize_xyz, weights, gammas,
             training, save, need_feat=nig[2], need_xyz=nig[0], need_new_xyz=nig[1])
         g_features = g_feat_t.transpose(1, 2).contiguous() if g_feat_t is not None else None
-        out = [g_xyz, g_new_xyz, g_features, None, None, None, None, None]
+        out = [g_xyz, g_new_xyz, g_features, None, None, None, None, None, None]
         for i in range(L):
             out += [dWs[i].view_as(params[3 * i]), dgs[i], dbs[i]]
         return tuple(out)
 
 
-def sa_block(xyz, new_xyz, features, idx, radius, normalize_xyz, mlp_module, training):
-    """Differentiable fused SA block: returns new_features (B, mlp[-1], npoint)."""
+def sa_block(xyz, new_xyz, features, idx, radius, normalize_xyz, mlp_module, training,
+             sm_limit=0):
+    """Differentiable fused SA block: returns new_features (B, mlp[-1], npoint).  sm_limit > 0
+    caps the forward kernels' persistent grid (SMs left to a concurrent geometry stream)."""
     params = []
     for blk in mlp_module:
         params += [blk.conv.weight, blk.bn.bn.weight, blk.bn.bn.bias]
     return _FusedSABlock.apply(xyz, new_xyz, features, idx, radius, normalize_xyz, mlp_module,
-                               training, *params)
+                               training, sm_limit, *params)
 
+
+NUM_SMS = 148   # B200
 
 # Set to False to route PointnetSAModuleVotes through the unfused path (QueryAndGroup kernel +
 # cuDNN SharedMLP + max_pool2d) -- used by the parity tests as the fp32 comparison arm.

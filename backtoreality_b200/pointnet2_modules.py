@@ -67,17 +67,22 @@ class _SAVotesBase(nn.Module):
             mlp_spec[0] += 3  # mutates the caller's list, exactly like the reference
         self.mlp_module = pt_utils.SharedMLP(mlp_spec, bn=bn)
 
-    def _abstract(self, xyz, new_xyz, features):
+    def fusable(self, xyz):
         g = self.grouper
-        if (fused_sa.ENABLED and xyz.is_cuda and self.pooling == 'max'
+        return (fused_sa.ENABLED and xyz.is_cuda and self.pooling == 'max'
                 and isinstance(g, pointnet2_utils.QueryAndGroup) and g.use_xyz
-                and not g.sample_uniformly and not g.ret_unique_cnt):
+                and not g.sample_uniformly and not g.ret_unique_cnt)
+
+    def _abstract(self, xyz, new_xyz, features, idx=None, sm_limit=0):
+        if self.fusable(xyz):
             # fused path: ball query, then ONE tcgen05 block for group -> relative xyz -> MLP ->
             # BN/ReLU -> max-pool (csrc/mlp.cu, csrc/mlp_bwd.cu); no (B,C,npoint,nsample) tensor
-            idx = pointnet2_utils.ball_query(self.radius, self.nsample, xyz, new_xyz)
+            if idx is None:
+                idx = pointnet2_utils.ball_query(self.radius, self.nsample, xyz, new_xyz)
             if fused_sa.supported(self.mlp_module, xyz, features, idx, self.pooling):
                 return fused_sa.sa_block(xyz, new_xyz, features, idx, self.radius,
-                                         self.normalize_xyz, self.mlp_module, self.training)
+                                         self.normalize_xyz, self.mlp_module, self.training,
+                                         sm_limit=sm_limit)
         grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features)
         new_features = self.mlp_module(grouped_features)  # (B, mlp[-1], npoint, nsample)
         return _pool(new_features, grouped_xyz, self.pooling, self.sigma, self.nsample)
@@ -91,7 +96,14 @@ class PointnetSAModuleVotes(_SAVotesBase):
     """
 
     def forward(self, xyz: torch.Tensor, features: torch.Tensor = None,
-                inds: torch.Tensor = None):
+                inds: torch.Tensor = None, geometry: dict = None):
+        if geometry is not None:
+            # FPS / centre gather / ball query were done ahead of time on a geometry stream
+            # (backbone_module.Pointnet2Backbone._geometry_prepass): wait for them, run the MLP
+            torch.cuda.current_stream().wait_event(geometry["event"])
+            new_features = self._abstract(xyz, geometry["new_xyz"], features, idx=geometry["idx"],
+                                          sm_limit=geometry.get("sm_limit", 0))
+            return geometry["new_xyz"], new_features, geometry["inds"]
         xyz_flipped = xyz.transpose(1, 2).contiguous()
         if inds is None:
             inds = pointnet2_utils.furthest_point_sample(xyz, self.npoint)

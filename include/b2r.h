@@ -184,6 +184,8 @@ typedef struct b2r_sa_layer {
   double *stats;            /* (2,Cout) sum, sum of squares; ACCUMULATED (caller zeroes); may be NULL */
   float *zmax, *zmin;       /* epilogue 1: (B*NP,Cout) */
   int *amax, *amin;         /* epilogue 1: (B*NP,Cout) sample index in [0,NS) */
+  int sm_limit;             /* 0 = one CTA on every SM; else at most this many CTAs, leaving the
+                               other SMs to kernels on concurrent streams (geometry pre-pass) */
 } b2r_sa_layer;
 
 B2R_API long long b2r_mlp_weight_image_bytes(int Cout, int Cin, int gather);
