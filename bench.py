@@ -108,6 +108,56 @@ def cpu_steps(a, steps, warmup, scenes_per_step):
     return scenes_per_step * steps / dt, 1e3 * dt / steps, max(cores, cpu_ops.num_threads())
 
 
+def reference_gpu_steps(a, dev, steps=3, warmup=1):
+    """The reference's OWN CUDA kernels (oracle/_ref/_ext.so: its _ext_src compiled for sm_100a by
+    oracle/Makefile) under the unfused restatement of its Python stack (oracle/cpu_modules.py:
+    group, -=, /=, cat, cuDNN SharedMLP with TF32 allowed, max_pool2d), same model / loss / Adam,
+    same batch size, on this GPU.  Reported beside the product arm; returns None when the
+    extension was not built."""
+    import importlib.util
+    path = os.path.join(ROOT, "oracle", "_ref", "_ext.so")
+    if not os.path.isfile(path):
+        return None
+    from backtoreality_b200 import scenes
+    from oracle import cpu_modules
+    spec = importlib.util.spec_from_file_location("_ext", path)
+    ref_ext = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_ext)
+    saved = cpu_modules._ext
+    cpu_modules._ext = ref_ext
+    try:
+        torch.manual_seed(0)
+        net = cpu_modules.VoteNetCPU(input_feature_dim=1, num_proposal=256).to(dev).train()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+        pool = [torch.from_numpy(scenes.batch(100 + i * a.batch, a.batch, a.npoints, C=1,
+                                              kind="room", dup=0.2)).to(dev) for i in range(2)]
+
+        def one(i):
+            ep = net({"point_clouds": pool[i % 2]})
+            ep["seed_xyz"] = ep["fp2_xyz"]
+            loss = synthetic_loss(ep)
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+
+        for i in range(warmup):
+            one(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            one(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": a.batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+                "what": "reference CUDA kernels (oracle/_ref/_ext.so, sm_100a build of its "
+                        "_ext_src) + unfused Python stack + cuDNN (TF32 allowed), eager, same "
+                        "model/loss/Adam, %d scenes x %d points" % (a.batch, a.npoints)}
+    finally:
+        cpu_modules._ext = saved
+
+
 def run_reference(a):
     """`--impl reference`: the CPU arm.  Rank 0 only; other ranks exit without work."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -339,7 +389,7 @@ def run_b2r(a):
         "metric": METRIC, "value": scenes_total / (ms_dev * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "tf32 fwd / bf16 bwd operands, f32 accumulate", "data": "synthetic",
         "config": workload_config(a, world),
         "e2e": {"value": scenes_total / (ms_e2e * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": int(host[0].numel() * 4), "d2h_bytes_per_step": 4,
@@ -404,6 +454,15 @@ def run_b2r(a):
                       "sa1_frac_of_fp32_issue_peak": 8 * upd / (sa1_ms * 1e-3) / fp32_peak}
 
     if world == 1 and not a.no_cpu_baseline:
+        try:
+            log("timing the reference's own CUDA kernels + cuDNN on this GPU ...")
+            del graphed
+            torch.cuda.empty_cache()
+            ref_gpu = reference_gpu_steps(a, dev)
+            if ref_gpu is not None:
+                out["reference_gpu"] = ref_gpu
+        except Exception as e:
+            log("reference GPU arm failed: %s: %s" % (type(e).__name__, e))
         log("timing the CPU port (oracle) on the host cores ...")
         val, ms, cores = cpu_steps(a, 3, 1, a.cpu_scenes)
         out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
