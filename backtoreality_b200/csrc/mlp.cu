@@ -181,13 +181,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
         }
       }
     }
+    int nidx = 0;   // prefetched ball-query index of the next tile (gather layers)
     for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k) {
       const int s = k & 1, n = k >> 1;
       mbar_wait(bar(2 + s), (uint32_t)((n & 1) ^ 1));   // MMAs of tile k-2 are done with stage s
       const long long pos0 = (long long)tile * NT;
       uint8_t *sx = base + L.x_off[s];
       if (a.mode == 0) {
-        if (ptid < NT) s_idx[ptid] = a.idx[pos0 + ptid];
+        // ball-query indices of this tile were requested one tile ago (nidx): the gathers below
+        // start without waiting on a dependent global load
+        if (ptid < NT) {
+          s_idx[ptid] = (k == 0) ? a.idx[pos0 + ptid] : nidx;
+          if (tile + grid < a.num_tiles) nidx = __ldg(a.idx + pos0 + (long long)grid * NT + ptid);
+        }
         fwd_bar_prod();
         const int b = (int)(pos0 / per_scene);
         const int in_scene0 = (int)(pos0 - (long long)b * per_scene);

@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
     // =============================== PRODUCERS (7 warps) ========================================
     const int ptid = tid - (kEpiThreads + 32);
     const int CH8 = a.Cout >> 3;     // 16-byte BF16 chunks per DZ row
+    int nidx = 0;   // prefetched ball-query index of the next tile (gather layers)
     for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k) {
       const int s = k & 1, n = k >> 1;
       mbar_wait(bar(2 + s), (uint32_t)((n & 1) ^ 1));   // MMAs of tile k-2 are done with stage s
@@ -307,7 +308,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
       }
       // ---- X tile ---------------------------------------------------------------------------
       if (a.mode == 0) {
-        if (ptid < NT) s_idx[ptid] = a.idx[pos0 + ptid];
+        // indices of this tile were requested one tile ago (nidx): no dependent global wait here
+        if (ptid < NT) {
+          s_idx[ptid] = (k == 0) ? a.idx[pos0 + ptid] : nidx;
+          if (tile + grid < a.num_tiles) nidx = __ldg(a.idx + pos0 + (long long)grid * NT + ptid);
+        }
         bar_prod();
         const int b = (int)(pos0 / per_scene);
         const int in_scene0 = (int)(pos0 - (long long)b * per_scene);
