@@ -366,14 +366,18 @@ bool make_plan(int B, int N, FpsPlan *pl) {
       c = 1;
       while (c * 2 <= max_c && (long long)B * (c * 2) <= kNumSMs && rows / (c * 2) >= 2) c *= 2;
       while (c < max_c && (rows + c - 1) / c > kPMax) c *= 2;  // capacity wins over residency
-      // Measured on B200 (scripts/fps_sweep.py, profiles/r01/fps_cluster_sweep.log): at N = 40000
-      // an 8-CTA cluster with 10 points per thread beats 16 CTAs x 5 points by 11 % (744 vs 834
-      // ns per iteration) -- the per-iteration cost is the DSMEM fan-out (one st.async pair per
-      // peer) and the mbarrier round trip, not the register-resident distance updates.
-      if (c == 16 && (rows + 7) / 8 <= 10) c = 8;
+      // Measured on B200 (scripts/fps_sweep.py, profiles/r01/fps_cluster_sweep.log), ns per
+      // dependent iteration at N = 40000 / 50000:  c=8: 739 / 823,  c=10: 707 / 746,
+      // c=12: 949 / 1500,  c=16: 853 / 944.  The per-iteration cost is the DSMEM fan-out (one
+      // st.async pair per peer) plus the mbarrier round trip, not the register-resident distance
+      // updates, so fewer, fatter CTAs win until the per-thread work (> 10 points) takes over;
+      // 10 CTAs x 512 threads is the sweet spot (cluster sizes need not be powers of two: thread
+      // ownership only needs c*512 to be a multiple of the reference's 512-lane stride).
+      if (c >= 8 && max_c >= 10 && (long long)B * 10 <= kNumSMs && (rows + 9) / 10 <= 10) c = 10;
+      else if (c == 16 && (rows + 7) / 8 <= 10) c = 8;
     }
     const int forced = env_int("B2R_FPS_CLUSTER", 0);
-    if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) c = forced;
+    if (forced >= 1 && forced <= 16) c = forced;   // any size: ownership only needs c*512 % 2^L == 0
     pl->csize = c;
     pl->NT = 512;
     const int p = (rows + c - 1) / c;

@@ -10,11 +10,11 @@ from backtoreality_b200 import _ext, scenes  # noqa: E402
 
 dev = torch.device("cuda:0")
 B = 8
-for N, npnt in ((40000, 2048), (50000, 2048), (20000, 2048)):
+for N, npnt in ((40000, 2048), (50000, 2048)):
     pc = torch.from_numpy(scenes.batch(1000, B, N, C=0, kind="room", dup=0.2)).to(dev)
     xyz = pc[..., :3].contiguous()
     ref = None
-    for c in (0, 4, 8, 16):
+    for c in (0, 6, 8, 10, 12, 14, 16):
         os.environ["B2R_FPS_CLUSTER"] = str(c)
         for _ in range(2):
             out = _ext.furthest_point_sampling(xyz, npnt)
