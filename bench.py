@@ -37,8 +37,15 @@ METRIC = "Pointnet2Backbone fwd+bwd scenes/sec @40k pts"
 UNIT = "scenes/s"
 
 
+_RESULT_OUT = sys.stdout
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def emit(obj):
+    print(json.dumps(obj), file=_RESULT_OUT, flush=True)
 
 
 def parse():
@@ -168,7 +175,7 @@ def run_reference(a):
     cfg["parallelism"] = "host CPU, %d threads" % cores
     cfg["l2"] = "n/a (CPU)"
     sample = "%d scenes of %d points per step, %d steps" % (per, a.npoints, a.steps)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -177,7 +184,7 @@ def run_reference(a):
                          "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
 
 
 # ------------------------------------------------------------------------- clocks ----------
@@ -470,13 +477,19 @@ def run_b2r(a):
                                "sample": "%d scenes of %d points per step, 3 timed steps after 1 "
                                          "warm-up (same model, loss, optimizer)" % (a.cpu_scenes,
                                                                                      a.npoints)}
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     a = parse()
+    # stdout carries exactly ONE line, the JSON result: anything a library prints to fd 1 (NCCL
+    # writes "NCCL version ..." there) is sent to stderr instead
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:
