@@ -81,7 +81,7 @@ __host__ __device__ inline int packed_k16(int Cin, int gather) {
 
 struct BwdSmem {
   uint32_t w_off, w_bytes, x_off[2], dz_off[2], x_bytes, dz_bytes, coef_off, scale_off, idx_off,
-      route_off, bar_off, total;
+      route_off, flush_off, bar_off, total;
 };
 __host__ __device__ inline BwdSmem bwd_smem_layout(int Kp, int KA, int WA, int Cout, int Cout_pad,
                                                    int NT, int top) {
@@ -101,7 +101,8 @@ __host__ __device__ inline BwdSmem bwd_smem_layout(int Kp, int KA, int WA, int C
   s.scale_off = s.coef_off + 3u * Cout * 4u;
   s.idx_off = s.scale_off + 2u * Kp * 4u;
   s.route_off = (s.idx_off + 4u * (uint32_t)NT * 4u + 15u) & ~15u;   // idx: 4 buffers (below)
-  s.bar_off = s.route_off + (top ? 4u * (uint32_t)(NT / 16) * Cout_pad * 4u : 0u);   // 2 stages
+  s.flush_off = s.route_off + (top ? 4u * (uint32_t)(NT / 16) * Cout_pad * 4u : 0u);   // 2 stages
+  s.bar_off = s.flush_off + 8u * 32u * 33u * 4u;   // wgrad flush: a padded 32x32 tile per warp
   s.total = s.bar_off + 13 * 8 + 16 + 1024;                        // + alignment slack
   return s;
 }
@@ -644,29 +645,38 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
       }
     }
     // ---- wgrad accumulator -> dW (Cout, Cin): the last mma_done wait covered every MMA ----------
+    // TMEM hands each thread one ROW (output channel) of a 32x32 chunk; adding it to dW as it is
+    // would make every warp-wide red.global touch 32 rows = 32 cache lines.  Each warp transposes
+    // its chunk through a private padded smem tile so that one instruction adds 32 CONSECUTIVE
+    // input channels of one row: one 128-byte line per instruction (32x fewer L2 transactions --
+    // this flush is a fixed cost per CTA and dominated the small SA3/SA4/vote layers).
     if (ntiles > 0) {
       tc_fence_after();
+      float *stg = reinterpret_cast<float *>(base + L.flush_off) + warp * (32 * 33);
       for (int ml = 0; ml < MTl; ++ml) {
-        const int co = ml * 128 + q * 32 + lane;
+        const int co0 = ml * 128 + q * 32;
         for (int at = (EW == 8 ? h : 0); at < KA * 2; at += (EW == 8 ? 2 : 1)) {
           uint32_t r[32];
           cuda::ptx::tcgen05_ld_32x32b(
               r, tmem_base + lane_addr + d3_col0 + (uint32_t)(ml * KA * 64 + at * 32));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (co < a.Cout) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int kp = at * 32 + i;
-              int kk = -1;
-              if (a.mode == 0) {
-                if (kp < C) kk = 3 + kp;
-                else if (kp >= Cf8 && kp < Cf8 + 3) kk = kp - Cf8;
-              } else if (kp < a.Cin) {
-                kk = kp;
-              }
-              if (kk >= 0) atomicAdd(a.dW + (size_t)co * a.Cin + kk, __uint_as_float(r[i]));
-            }
+          for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(r[i]);
+          __syncwarp();
+          const int kp = at * 32 + lane;   // this lane's packed input channel
+          int kk = -1;
+          if (a.mode == 0) {
+            if (kp < C) kk = 3 + kp;
+            else if (kp >= Cf8 && kp < Cf8 + 3) kk = kp - Cf8;
+          } else if (kp < a.Cin) {
+            kk = kp;
           }
+          if (kk >= 0) {
+            const int rows = min(32, a.Cout - co0);
+            for (int rr = 0; rr < rows; ++rr)
+              atomicAdd(a.dW + (size_t)(co0 + rr) * a.Cin + kk, stg[rr * 33 + lane]);
+          }
+          __syncwarp();
         }
       }
     }
