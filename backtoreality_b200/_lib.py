@@ -82,6 +82,7 @@ SIGNATURES.update({
     "b2r_mlp_weight_bf16_image_bytes": [_i, _i, _i],
     "b2r_mlp_pack_weight_bf16": [_vp, _i, _i, _i, _vp, _vp],
     "b2r_sa_layer_bwd": [ctypes.POINTER(SaLayerBwd), _vp],
+    "b2r_sa_layer_bwd_supported": [_i, _i, _i, _i, _i, _i, _i],
     "b2r_pool_bwd_prep": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp],
     "b2r_bn_bwd_finalize": [_vp, _i, ctypes.c_double, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp,
                             _vp, _vp, _vp, _vp],

@@ -789,6 +789,37 @@ Geometry bwd_geometry(int Cout, int Cin, int gather) {
 }
 }  // namespace
 
+namespace {
+// positions per tile for one backward launch: the widest tile whose two smem stages and two TMEM
+// stages fit; 0 = the layer does not fit at all
+int bwd_pick_nt(const Geometry &g, int Cout, int mode, int top, int do_dgrad, int NS, long long M,
+                long long per_scene) {
+  const int MTp = (g.KA + 1) >> 1, MTl = g.Cout_pad >> 7;
+  if (MTp > 3) return 0;
+  for (int nt : {128, 64, 32}) {
+    if (M % nt) continue;
+    if (mode == 0 && per_scene % nt) continue;       // a tile must lie inside one scene
+    if (top && (nt % NS) != 0 && (NS % nt) != 0) continue;
+    const BwdSmem L = bwd_smem_layout(g.Kp, g.KA, g.WA, Cout, g.Cout_pad, nt, top);
+    const int w12 = ((top && MTl > (do_dgrad ? MTp : 0)) ? MTl : (do_dgrad ? MTp : 0)) * nt;
+    const int cols = 2 * w12 + MTl * g.KA * 64;
+    if (L.total <= 227u * 1024u && cols <= 512) return nt;
+  }
+  return 0;
+}
+}  // namespace
+
+extern "C" int b2r_sa_layer_bwd_supported(int B, int NP, int NS, int Cin, int Cout, int gather,
+                                          int top) {
+  if (B <= 0 || NP <= 0 || NS <= 0 || Cin <= 0 || Cout <= 0) return 0;
+  if (Cout > 256 || (Cout % 8) != 0 || (!gather && (Cin % 8) != 0) || (gather && Cin < 3)) return 0;
+  if (top && pow2_shift(NS) < 0) return 0;
+  const Geometry g = bwd_geometry(Cout, Cin, gather);
+  const long long per_scene = (long long)NP * NS, M = (long long)B * per_scene;
+  // worst case for the tile choice: every gradient requested (dgrad on)
+  return bwd_pick_nt(g, Cout, gather ? 0 : 1, top, 1, NS, M, per_scene) > 0 ? 1 : 0;
+}
+
 extern "C" long long b2r_mlp_weight_bf16_image_bytes(int Cout, int Cin, int gather) {
   if (Cout <= 0 || Cin <= 0) return 0;
   const Geometry g = bwd_geometry(Cout, Cin, gather);
@@ -858,20 +889,7 @@ extern "C" int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *d, void *stream) {
               "(Cin=%d Cout=%d)", d->Cin, d->Cout);
     return B2R_ERR_UNSUPPORTED;
   }
-  const int MTp = (a.KA + 1) >> 1, MTl = a.Cout_pad >> 7;
-  int NT = 0;
-  for (int nt : {128, 64, 32}) {
-    if (M % nt) continue;
-    if (d->mode == 0 && per_scene % nt) continue;       // a tile must lie inside one scene
-    if (a.top && (nt % d->NS) != 0 && (d->NS % nt) != 0) continue;
-    const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, nt, a.top);
-    const int w12 = ((a.top && MTl > (a.do_dgrad ? MTp : 0)) ? MTl : (a.do_dgrad ? MTp : 0)) * nt;
-    const int cols = 2 * w12 + MTl * a.KA * 64;
-    if (L.total <= 227u * 1024u && cols <= 512 && MTp <= 3) {
-      NT = nt;
-      break;
-    }
-  }
+  const int NT = bwd_pick_nt(g, d->Cout, d->mode, a.top, a.do_dgrad, d->NS, M, per_scene);
   if (NT == 0) {
     set_error("b2r_sa_layer_bwd: layer Cin=%d Cout=%d M=%lld does not fit shared memory / TMEM",
               d->Cin, d->Cout, M);

@@ -72,6 +72,11 @@ def supported(mlp_module, xyz, features, idx, pooling="max"):
             return False
         if _layer_smem(cin, cout, gather=(i == 0), nt=32) > 227 * 1024:
             return False
+        # the backward kernel has its own shared-memory / TMEM budget: ask the library now, so a
+        # block never takes the fused forward and then fails in backward
+        if not _lib.lib().b2r_sa_layer_bwd_supported(B, NP, NS, cin, cout, 1 if i == 0 else 0,
+                                                     1 if i == len(blocks) - 1 else 0):
+            return False
     return True
 
 

@@ -260,6 +260,10 @@ B2R_API long long b2r_mlp_weight_bf16_image_bytes(int Cout, int Cin, int gather)
 B2R_API int b2r_mlp_pack_weight_bf16(const float *w, int Cout, int Cin, int gather, void *image,
                                      void *stream);
 B2R_API int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *desc, void *stream);
+/* 1 when b2r_sa_layer_bwd covers a layer of this shape (shared memory, TMEM columns, divisibility),
+ * 0 otherwise: lets the host decide BEFORE the forward whether to take the fused path. */
+B2R_API int b2r_sa_layer_bwd_supported(int B, int NP, int NS, int Cin, int Cout, int gather,
+                                       int top);
 
 /* dout_cm (B,C,NP) and/or dout_pm (B,NP,C) (summed; either may be NULL) -> dysel (B*NP,C),
  * asel (B*NP,C), stats (2,C) double ACCUMULATED: sum(dysel), sum(dysel * zsel). */

@@ -41,7 +41,7 @@ def test_host_only_entry_points():
         assert l.b2r_ref_block_threads(n) == cpu_ops.block_threads(n)
     c, t, p, s = (ctypes.c_int() for _ in range(4))
     assert l.b2r_fps_plan(8, 40000, c, t, p, s) == 0
-    assert c.value * t.value * p.value >= 40000 and c.value in (1, 2, 4, 8, 16)
+    assert c.value * t.value * p.value >= 40000 and 1 <= c.value <= 16  # any cluster size <= 16
     assert l.b2r_fps_plan(1, 10_000_000, c, t, p, s) == -3       # B2R_ERR_UNSUPPORTED
     assert b"capacity" in l.b2r_last_error()
     # argument validation happens before any CUDA call
