@@ -282,3 +282,37 @@ def test_captured_train_step_matches_eager(cuda):
     bn_e = net_e.backbone_net.sa1.mlp_module.layer0.bn.bn
     bn_g = net_g.backbone_net.sa1.mlp_module.layer0.bn.bn
     assert int(bn_e.num_batches_tracked) == 4 and int(bn_g.num_batches_tracked) == 7
+
+
+def test_geometry_stream_matches_serial_path(cuda):
+    """Pointnet2Backbone with the geometry pre-pass on a side stream (FPS / centre gather / ball
+    query of all levels ahead of the MLPs, MLP grids capped to leave SMs free) must compute what
+    the serial path computes: identical indices and centres, features equal up to the summation
+    order of the BatchNorm statistics (a different persistent grid), same gradients within the
+    run-to-run noise of the atomics."""
+    from backtoreality_b200 import backbone_module
+    from backtoreality_b200.backbone_module import Pointnet2Backbone
+    torch.manual_seed(21)
+    net = Pointnet2Backbone(input_feature_dim=1).to(cuda).train()
+    pc = torch.from_numpy(scenes.batch(400, 2, 20000, C=1, kind="room", dup=0.2)).to(cuda)
+    outs = []
+    old = backbone_module.GEOMETRY_STREAM
+    try:
+        for flag in (True, False):
+            backbone_module.GEOMETRY_STREAM = flag
+            for p in net.parameters():
+                p.grad = None
+            ep = net(pc)
+            (ep["fp2_features"] * pattern_like(ep["fp2_features"])).sum().backward()
+            torch.cuda.synchronize()
+            outs.append(({k: v.detach().clone() for k, v in ep.items()},
+                         {n: p.grad.clone() for n, p in net.named_parameters()}))
+    finally:
+        backbone_module.GEOMETRY_STREAM = old
+    (ea, ga), (eb, gb) = outs
+    for k in ("sa1_inds", "sa2_inds", "fp2_inds", "sa1_xyz", "sa2_xyz", "sa3_xyz", "sa4_xyz"):
+        assert torch.equal(ea[k], eb[k]), k
+    for k in ("sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features"):
+        assert rel_l2(ea[k].cpu().numpy(), eb[k].cpu().numpy()) < 1e-5, k
+    for n in ga:
+        assert rel_l2(ga[n].cpu().numpy(), gb[n].cpu().numpy()) < 3e-2, n
