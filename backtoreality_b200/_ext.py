@@ -26,6 +26,9 @@ LAUNCHES = 0   # number of libb2r kernel launches issued through this module
 TIMED = {}     # op name -> list of (start_event, stop_event, algorithmic_bytes); only TIME_OPS
 TIME_OPS = set()
 
+# scenes with at least this many points take the grid-accelerated ball query (same output)
+BALL_QUERY_GRID_MIN_N = 8192
+
 
 class _timed:
     """Counts the launch and, for ops listed in TIME_OPS, brackets it with CUDA events recorded
@@ -148,9 +151,19 @@ def ball_query(new_xyz, xyz, radius, nsample):
     N = xyz.size(1)
     out = torch.empty((B, M, int(nsample)), dtype=torch.int32, device=new_xyz.device)
     with _on_device(new_xyz), _timed("ball_query"):
-        _lib.check(_lib.lib().b2r_ball_query(new_xyz.data_ptr(), xyz.data_ptr(), B, N, M,
-                                             float(radius), int(nsample), out.data_ptr(),
-                                             _stream()), "ball_query")
+        if N >= BALL_QUERY_GRID_MIN_N:
+            # large scenes: hashed uniform grid, 27 cells per centre instead of all N points
+            # (identical output; b2r_ball_query_grid in include/b2r.h)
+            nbytes = _lib.lib().b2r_ball_query_workspace_bytes(B, N)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=new_xyz.device)
+            _lib.check(_lib.lib().b2r_ball_query_grid(new_xyz.data_ptr(), xyz.data_ptr(), B, N, M,
+                                                      float(radius), int(nsample), out.data_ptr(),
+                                                      ws.data_ptr(), nbytes, _stream()),
+                       "ball_query_grid")
+        else:
+            _lib.check(_lib.lib().b2r_ball_query(new_xyz.data_ptr(), xyz.data_ptr(), B, N, M,
+                                                 float(radius), int(nsample), out.data_ptr(),
+                                                 _stream()), "ball_query")
     return out
 
 

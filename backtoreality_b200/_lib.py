@@ -25,6 +25,8 @@ SIGNATURES = {
     "b2r_gather_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "b2r_gather_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "b2r_ball_query": [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp],
+    "b2r_ball_query_workspace_bytes": [_i, _i],
+    "b2r_ball_query_grid": [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, ctypes.c_longlong, _vp],
     "b2r_group_fwd": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "b2r_group_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "b2r_three_nn": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
@@ -34,6 +36,7 @@ SIGNATURES = {
     "b2r_query_group_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp],
 }
 _RESTYPES = {"b2r_status_string": ctypes.c_char_p, "b2r_last_error": ctypes.c_char_p,
+             "b2r_ball_query_workspace_bytes": ctypes.c_longlong,
              "b2r_mlp_weight_image_bytes": ctypes.c_longlong}
 
 

@@ -91,6 +91,15 @@ B2R_API int b2r_gather_bwd(const float *grad_out, const int *idx, int B, int C, 
 B2R_API int b2r_ball_query(const float *new_xyz, const float *xyz, int B, int N, int M, float radius,
                    int nsample, int *idx, void *stream);
 
+/* Same result, bit for bit, through a hashed uniform grid (cell = radius): a centre visits the 27
+ * cells around it instead of all N points, collects the hits and sorts them by index.  Needs a
+ * caller-provided device workspace of b2r_ball_query_workspace_bytes(B, N) bytes (contents are
+ * scratch).  Falls back to b2r_ball_query for N < 1024 or nsample > 480. */
+B2R_API long long b2r_ball_query_workspace_bytes(int B, int N);
+B2R_API int b2r_ball_query_grid(const float *new_xyz, const float *xyz, int B, int N, int M,
+                                float radius, int nsample, int *idx, void *workspace,
+                                long long workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * group_points(points, idx)                             src/group_points.cpp:17-40,
  *                                                       kernel src/group_points_gpu.cu:13-33

@@ -113,6 +113,45 @@ def test_ball_query_dense_uniform_early_exit(cuda):
     _bq_check(new_xyz, xyz, 0.2, 64, cuda)
 
 
+@pytest.mark.parametrize("case", ["room", "negative", "cluster", "huge_radius", "far_aliasing",
+                                  "nan", "ragged"])
+def test_ball_query_grid_path_matches_oracle(cuda, case, monkeypatch):
+    """The hashed-grid ball query (b2r_ball_query_grid, taken for N >= 8192; forced here from
+    N >= 1024) must return exactly what the brute-force scan returns: against the C oracle, on
+    inputs that stress the grid -- negative coordinates, thousands of hits per centre (buffer
+    compaction), scenes wider than the 64-cell hash period (aliasing), NaN points, N % 32 != 0."""
+    from backtoreality_b200 import _ext
+    monkeypatch.setattr(_ext, "BALL_QUERY_GRID_MIN_N", 0)
+    rng = np.random.default_rng(11)
+    if case == "room":
+        xyz = scenes.batch(3, 2, 40000, C=0, kind="room", dup=0.2)[..., :3]
+        new_xyz, r, ns = xyz[:, ::37][:, :1000].copy(), 0.2, 64
+    elif case == "negative":
+        xyz = (rng.random((2, 9000, 3), dtype=np.float32) - 0.5) * 6.0
+        new_xyz, r, ns = xyz[:, :700].copy() + np.float32(0.01), 0.3, 32
+    elif case == "cluster":      # 6000 identical points + a tight blob: > 512 hits per centre
+        xyz = rng.random((2, 12000, 3), dtype=np.float32)
+        xyz[:, 1000:7000] = np.float32([0.5, 0.5, 0.5])
+        xyz[:, 7000:9000] = 0.5 + (rng.random((2, 2000, 3), dtype=np.float32) - 0.5) * 0.05
+        new_xyz, r, ns = xyz[:, 900:1100].copy(), 0.2, 64
+    elif case == "huge_radius":  # every centre sees a large share of the scene
+        xyz = rng.random((2, 8192, 3), dtype=np.float32)
+        new_xyz, r, ns = xyz[:, :64].copy(), 1.2, 16
+    elif case == "far_aliasing":  # 40 m wide scene at r = 0.2: 200 cells > the 64-cell hash period
+        xyz = rng.random((2, 20000, 3), dtype=np.float32) * np.float32([40.0, 40.0, 10.0])
+        new_xyz, r, ns = xyz[:, :512].copy(), 0.2, 16
+    elif case == "nan":
+        xyz = rng.random((2, 5000, 3), dtype=np.float32)
+        xyz[:, 17] = np.nan
+        xyz[:, 4000, 1] = np.inf
+        new_xyz = xyz[:, :300].copy()
+        r, ns = 0.25, 32
+    else:
+        xyz = rng.random((2, 1025, 3), dtype=np.float32)
+        new_xyz, r, ns = rng.random((2, 9, 3), dtype=np.float32), 0.35, 5
+    _bq_check(new_xyz, xyz, r, ns, cuda)
+
+
 @pytest.mark.parametrize("N", [1, 3, 4, 5, 127, 128, 129, 1023, 1024, 1025, 2050])
 def test_ball_query_ragged_sizes(cuda, N):
     rng = np.random.default_rng(N)
