@@ -160,6 +160,8 @@ def ball_query(new_xyz, xyz, radius, nsample):
                                                       float(radius), int(nsample), out.data_ptr(),
                                                       ws.data_ptr(), nbytes, _stream()),
                        "ball_query_grid")
+            global LAUNCHES
+            LAUNCHES += 3   # count, scan, fill (+ the query counted by _timed)
         else:
             _lib.check(_lib.lib().b2r_ball_query(new_xyz.data_ptr(), xyz.data_ptr(), B, N, M,
                                                  float(radius), int(nsample), out.data_ptr(),
