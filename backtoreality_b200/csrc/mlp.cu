@@ -403,23 +403,34 @@ __global__ void bn_finalize_kernel(const double *__restrict__ stats, int Cch, do
 }
 
 // out = relu(scale * (scale >= 0 ? zmax : zmin) + shift), written channel-major (B,C,NP) for the
-// reference API and point-major (B,NP,C) for the next layer's gather.  One thread per (centre, c).
+// reference API and point-major (B,NP,C) for the next layer's gather.  One 32 x 32 (centre,
+// channel) tile per CTA, transposed through shared memory so that BOTH layouts are read and
+// written with 128-byte coalesced rows.
 __global__ void pool_finalize_kernel(const float *__restrict__ zmax, const float *__restrict__ zmin,
                                      const float *__restrict__ scale,
-                                     const float *__restrict__ shift, int B, int NP, int Cch,
+                                     const float *__restrict__ shift, int NP, int Cch,
                                      float *__restrict__ out_cm, float *__restrict__ out_pm) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)B * NP * Cch;
-  if (e >= total) return;
-  const int ch = (int)(e % Cch);
-  const long long centre = e / Cch;
-  const float s = scale[ch];
-  const float z = s >= 0.f ? zmax[e] : zmin[e];
-  const float y = fmaxf(fmaf(z, s, shift[ch]), 0.f);
-  if (out_pm) out_pm[e] = y;
-  if (out_cm) {
-    const int b = (int)(centre / NP), j = (int)(centre % NP);
-    out_cm[((size_t)b * Cch + ch) * NP + j] = y;
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int ch = c0 + threadIdx.x;
+  const float s = ch < Cch ? scale[ch] : 0.f, sh = ch < Cch ? shift[ch] : 0.f;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int j = j0 + i;
+    float y = 0.f;
+    if (j < NP && ch < Cch) {
+      const size_t e = ((size_t)b * NP + j) * Cch + ch;
+      const float z = s >= 0.f ? zmax[e] : zmin[e];
+      y = fmaxf(fmaf(z, s, sh), 0.f);
+      if (out_pm) out_pm[e] = y;
+    }
+    t[i][threadIdx.x] = y;
+  }
+  if (out_cm == nullptr) return;
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int cc = c0 + i, j = j0 + threadIdx.x;
+    if (cc < Cch && j < NP) out_cm[((size_t)b * Cch + cc) * NP + j] = t[threadIdx.x][i];
   }
 }
 
@@ -579,9 +590,10 @@ extern "C" int b2r_pool_finalize(const float *zmax, const float *zmin, const flo
                                  float *out_pm, void *stream) {
   B2R_REQUIRE(zmax && zmin && scale && shift && B > 0 && NP > 0 && C > 0,
               "b2r_pool_finalize: bad argument");
-  const long long total = (long long)B * NP * C;
-  pool_finalize_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      zmax, zmin, scale, shift, B, NP, C, out_cm, out_pm);
+  B2R_REQUIRE(B <= 65535, "b2r_pool_finalize: B=%d exceeds gridDim.z", B);
+  dim3 grid(ceil_div(NP, 32), ceil_div(C, 32), B), block(32, 8);
+  pool_finalize_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      zmax, zmin, scale, shift, NP, C, out_cm, out_pm);
   B2R_CHECK_LAUNCH();
   return B2R_OK;
 }

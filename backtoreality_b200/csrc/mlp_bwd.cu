@@ -693,43 +693,60 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
 //   dysel = dout * [y > 0],  asel = arg of zsel
 // and the BatchNorm-backward sums over all positions reduce to sums over centres:
 //   sum(gr) = sum(dysel),   sum(gr * z) = sum(dysel * zsel).
+// One 32 x 32 (centre, channel) tile per CTA: the channel-major output gradient is read with
+// coalesced rows along the centres, transposed through shared memory, and everything else
+// (zmax / zmin / arg reads, dysel / asel writes) runs coalesced along the channels; the tile's
+// contribution to the two per-channel sums is reduced in shared memory: one double atomic pair
+// per channel per CTA.
 __global__ void pool_bwd_prep_kernel(const float *__restrict__ dout_cm,
                                      const float *__restrict__ dout_pm,
                                      const float *__restrict__ zmax, const float *__restrict__ zmin,
                                      const int *__restrict__ amax, const int *__restrict__ amin,
                                      const float *__restrict__ scale,
-                                     const float *__restrict__ shift, int B, int NP, int Cch,
+                                     const float *__restrict__ shift, int NP, int Cch,
                                      float *__restrict__ dysel, int *__restrict__ asel,
                                      double *__restrict__ stats) {
-  // thread <-> fixed channel, strided over centres: coalesced on the (centre, c) arrays
-  const int c = threadIdx.x % Cch;
-  const int lanes_per_block = blockDim.x / Cch;        // centres handled side by side
-  const int sub = threadIdx.x / Cch;
-  if (sub >= lanes_per_block) return;
-  const long long ncentres = (long long)B * NP;
-  const float s = scale[c], sh = shift[c];
-  double a1 = 0.0, a2 = 0.0;
-  for (long long ce = (long long)blockIdx.x * lanes_per_block + sub; ce < ncentres;
-       ce += (long long)gridDim.x * lanes_per_block) {
-    const size_t o = (size_t)ce * Cch + c;
-    const bool pos = s >= 0.f;
-    const float zs = pos ? zmax[o] : zmin[o];
-    const int as = pos ? amax[o] : amin[o];
-    const float y = fmaf(zs, s, sh);
-    float g = 0.f;
-    if (dout_cm != nullptr) {
-      const int b = (int)(ce / NP), j = (int)(ce % NP);
-      g += dout_cm[((size_t)b * Cch + c) * NP + j];
+  __shared__ float t[32][33];
+  __shared__ double r1[8][32], r2[8][32];
+  const int b = blockIdx.z;
+  const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  if (dout_cm != nullptr) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {   // rows = channels, lanes = centres
+      const int cc = c0 + i, j = j0 + threadIdx.x;
+      t[i][threadIdx.x] = (cc < Cch && j < NP) ? dout_cm[((size_t)b * Cch + cc) * NP + j] : 0.f;
     }
-    if (dout_pm != nullptr) g += dout_pm[o];
-    g = y > 0.f ? g : 0.f;
-    dysel[o] = g;
-    asel[o] = as;
-    a1 += (double)g;
-    a2 += (double)g * (double)zs;
+    __syncthreads();
   }
-  atomicAdd(stats + c, a1);
-  atomicAdd(stats + Cch + c, a2);
+  const int ch = c0 + threadIdx.x;
+  const float s = ch < Cch ? scale[ch] : 0.f, sh = ch < Cch ? shift[ch] : 0.f;
+  const bool pos = s >= 0.f;
+  double a1 = 0.0, a2 = 0.0;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {     // rows = centres, lanes = channels
+    const int j = j0 + i;
+    if (j < NP && ch < Cch) {
+      const size_t o = ((size_t)b * NP + j) * Cch + ch;
+      const float zs = pos ? zmax[o] : zmin[o];
+      const int as = pos ? amax[o] : amin[o];
+      float g = dout_cm != nullptr ? t[threadIdx.x][i] : 0.f;
+      if (dout_pm != nullptr) g += dout_pm[o];
+      g = fmaf(zs, s, sh) > 0.f ? g : 0.f;
+      dysel[o] = g;
+      asel[o] = as;
+      a1 += (double)g;
+      a2 += (double)g * (double)zs;
+    }
+  }
+  r1[threadIdx.y][threadIdx.x] = a1;
+  r2[threadIdx.y][threadIdx.x] = a2;
+  __syncthreads();
+  if (threadIdx.y == 0 && ch < Cch) {
+    for (int k = 1; k < 8; ++k) {
+      a1 += r1[k][threadIdx.x];
+      a2 += r2[k][threadIdx.x];
+    }
+    atomicAdd(stats + ch, a1);
+    atomicAdd(stats + Cch + ch, a2);
+  }
 }
 
 // BatchNorm backward bookkeeping of one layer from  S1 = sum(gr), S2 = sum(gr*z)  (one thread per
@@ -922,12 +939,10 @@ extern "C" int b2r_pool_bwd_prep(const float *dout_cm, const float *dout_pm, con
   B2R_REQUIRE((dout_cm || dout_pm) && zmax && zmin && amax && amin && scale && shift && dysel &&
                   asel && stats && B > 0 && NP > 0 && C > 0 && C <= 1024,
               "b2r_pool_bwd_prep: bad argument");
-  const int threads = C <= 256 ? 256 : 1024;
-  const int per_block = threads / C;
-  int grid = ceil_div((long long)B * NP, per_block);
-  if (grid > kNumSMs * 4) grid = kNumSMs * 4;
-  pool_bwd_prep_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      dout_cm, dout_pm, zmax, zmin, amax, amin, scale, shift, B, NP, C, dysel, asel, stats);
+  B2R_REQUIRE(B <= 65535, "b2r_pool_bwd_prep: B=%d exceeds gridDim.z", B);
+  dim3 grid(ceil_div(NP, 32), ceil_div(C, 32), B), block(32, 8);
+  pool_bwd_prep_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      dout_cm, dout_pm, zmax, zmin, amax, amin, scale, shift, NP, C, dysel, asel, stats);
   B2R_CHECK_LAUNCH();
   return B2R_OK;
 }
