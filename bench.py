@@ -258,6 +258,10 @@ def run_b2r(a):
         dist.init_process_group("nccl", device_id=dev)
     assert world == a.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % a.gpus
 
+    # the FP / voting / proposal heads are cuDNN 1x1 convolutions: let cuDNN pick its fastest
+    # algorithms during the warm-up steps (the reference's trainers leave the default heuristics;
+    # this only changes which library kernel runs, e.g. it avoids a 56 us grouped-direct wgrad)
+    torch.backends.cudnn.benchmark = True
     torch.manual_seed(0)  # identical replicas
     net = VoteNet(22, 1, 22, np.ones((22, 3), np.float32), input_feature_dim=1, num_proposal=256,
                   vote_factor=1, sampling="vote_fps").to(dev).train()
