@@ -371,3 +371,55 @@ def test_fused_block_backward_vs_unfused_module(cuda, cfg, training):
             assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < tol, n
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_center_refine_head_single_layer_block(cuda, training):
+    """the CenterRefine head of the `_jitter` backbones
+    (reference models/backbone_module.py:188-195): PointnetSAModuleCenters(npoint=64, radius=0.8,
+    nsample=16, mlp=[256,128], normalize_xyz=False) around EXTERNALLY supplied centres.  A
+    one-layer MLP: the gather layer is also the pooled top layer, in forward and backward."""
+    import copy
+    from backtoreality_b200 import fused_sa
+    from backtoreality_b200.pointnet2_modules import PointnetSAModuleCenters
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(17)
+        head = PointnetSAModuleCenters(npoint=64, radius=0.8, nsample=16, mlp=[256, 128],
+                                       use_xyz=True, normalize_xyz=False).to(cuda).train(training)
+        bn = head.mlp_module[0].bn.bn
+        bn.weight.data = torch.randn_like(bn.weight) * 0.5 + 0.8
+        bn.bias.data = torch.randn_like(bn.bias) * 0.2
+        ref = copy.deepcopy(head)
+        g = torch.Generator(device="cpu").manual_seed(3)
+        xyz0 = (torch.rand(2, 1024, 3, generator=g) * 4.0).to(cuda)
+        cen0 = (xyz0[:, :64] + 0.05 * torch.randn(2, 64, 3, generator=g).to(cuda)).contiguous()
+        f0 = torch.randn(2, 256, 1024, generator=g).to(cuda)
+        outs = []
+        for mod, fused in ((head, True), (ref, False)):
+            fused_sa.ENABLED = fused
+            try:
+                xyz = xyz0.clone().requires_grad_(True)
+                cen = cen0.clone().requires_grad_(True)
+                feats = f0.clone().requires_grad_(True)
+                if fused:
+                    idx = torch.zeros(2, 64, 16, dtype=torch.int32, device=cuda)
+                    assert fused_sa.supported(mod.mlp_module, xyz, feats, idx)
+                y = mod(xyz, feats, cen)
+                patt = torch.sin(torch.arange(y.numel(), device=cuda, dtype=torch.float64) * 12.9898)
+                (y * patt.float().view_as(y)).sum().backward()
+                outs.append((y.detach(), xyz.grad, cen.grad, feats.grad,
+                             [p.grad for p in mod.parameters()]))
+            finally:
+                fused_sa.ENABLED = True
+        (y1, gx1, gc1, gf1, gp1), (y0, gx0, gc0, gf0, gp0) = outs
+        assert y1.shape == (2, 128, 64)
+        assert rel_l2(y1.cpu().numpy(), y0.cpu().numpy()) < 5e-3
+        tol = 8e-2   # one TF32/BF16 block vs fp32 (see test_fused_block_backward_vs_unfused_module)
+        for a, b, n in ((gx1, gx0, "xyz"), (gc1, gc0, "centers"), (gf1, gf0, "features")):
+            assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < tol, n
+        for (n, _), a, b in zip(head.named_parameters(), gp1, gp0):
+            assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < tol, n
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
