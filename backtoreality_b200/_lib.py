@@ -32,6 +32,7 @@ SIGNATURES = {
     "b2r_three_nn": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "b2r_three_interp_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "b2r_three_interp_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "b2r_nn_argmin": [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp],
     "b2r_query_group_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp],
     "b2r_query_group_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp],
 }

@@ -1,0 +1,54 @@
+"""Chamfer / nearest-neighbour distances of the detection losses on the B200-native arg-min.
+
+Mirrors /root/reference/detection/Votenet/utils/nn_distance.py (`huber_loss` :15-32,
+`nn_distance` :34-61): same signature, same four return values (dist1 (B,N) f32, idx1 (B,N) i64,
+dist2 (B,M) f32, idx2 (B,M) i64).  The reference tiles both clouds to (B,N,M,C); here
+`b2r_nn_argmin` finds the two index vectors without any N*M tensor, and the distances are
+evaluated on the matched pairs with the reference's own elementwise formula, so values and
+gradients (which torch.min's backward sends to the arg-min pair only) are the same.
+CPU tensors take the reference formulation unchanged (the losses are also used in CPU tests).
+"""
+import torch
+
+from . import _ext, _lib
+
+
+def huber_loss(error, delta=1.0):
+    abs_error = torch.abs(error)
+    quadratic = torch.clamp(abs_error, max=delta)
+    linear = abs_error - quadratic
+    return 0.5 * quadratic ** 2 + delta * linear
+
+
+def _pair_cost(diff, l1smooth, delta, l1):
+    if l1smooth:
+        return torch.sum(huber_loss(diff, delta), dim=-1)
+    if l1:
+        return torch.sum(torch.abs(diff), dim=-1)
+    return torch.sum(diff ** 2, dim=-1)
+
+
+def nn_distance(pc1, pc2, l1smooth=False, delta=1.0, l1=False):
+    if not pc1.is_cuda or pc1.size(-1) > 4:
+        N, M = pc1.shape[1], pc2.shape[1]
+        diff = pc1.unsqueeze(2).repeat(1, 1, M, 1) - pc2.unsqueeze(1).repeat(1, N, 1, 1)
+        pc_dist = _pair_cost(diff, l1smooth, delta, l1)
+        dist1, idx1 = torch.min(pc_dist, dim=2)
+        dist2, idx2 = torch.min(pc_dist, dim=1)
+        return dist1, idx1, dist2, idx2
+    B, N, C = pc1.shape
+    M = pc2.shape[1]
+    a = pc1.detach().contiguous().float()
+    b = pc2.detach().contiguous().float()
+    idx1 = torch.empty((B, N), dtype=torch.int64, device=pc1.device)
+    idx2 = torch.empty((B, M), dtype=torch.int64, device=pc1.device)
+    mode = 2 if l1smooth else (1 if l1 else 0)
+    _lib.check(_lib.lib().b2r_nn_argmin(a.data_ptr(), b.data_ptr(), B, N, M, C, mode, float(delta),
+                                        idx1.data_ptr(), idx2.data_ptr(), _ext._stream()),
+               "nn_argmin")
+    _ext.LAUNCHES += 2
+    m1 = torch.gather(pc2, 1, idx1.unsqueeze(-1).expand(-1, -1, C))     # (B,N,C) match of pc1[n]
+    m2 = torch.gather(pc1, 1, idx2.unsqueeze(-1).expand(-1, -1, C))     # (B,M,C) match of pc2[m]
+    dist1 = _pair_cost(pc1 - m1, l1smooth, delta, l1)
+    dist2 = _pair_cost(m2 - pc2, l1smooth, delta, l1)
+    return dist1, idx1, dist2, idx2

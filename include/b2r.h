@@ -289,6 +289,18 @@ B2R_API int b2r_bn_bwd_finalize(const double *stats, int C, double count, const 
                                 float *coef_a, float *coef_b, float *coef_c, float *k1, float *k2,
                                 float *gs, float *dgamma, float *dbeta, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Loss-side nearest-neighbour matching: the two arg-min vectors of
+ * nn_distance(pc1, pc2)  (reference detection/Votenet/utils/nn_distance.py:34-61) without the
+ * four (B,N,M,C) tiled tensors it materialises.  pc1 (B,N,C), pc2 (B,M,C), C <= 4;
+ * mode 0: sum d^2, 1: sum |d| (l1=True), 2: sum huber(d, delta) (l1smooth=True).
+ * idx1 (B,N) / idx2 (B,M) int64 like torch.min's indices (either may be NULL); lowest index on
+ * ties.  The host mirror recomputes the matched distances with torch ops so that autograd
+ * routes gradients to the matched pairs exactly like torch.min's backward.
+ */
+B2R_API int b2r_nn_argmin(const float *pc1, const float *pc2, int B, int N, int M, int C, int mode,
+                          float delta, long long *idx1, long long *idx2, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
