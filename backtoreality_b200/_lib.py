@@ -59,6 +59,7 @@ SIGNATURES.update({
     "b2r_mlp_weight_image_bytes": [_i, _i, _i],
     "b2r_mlp_pack_weight": [_vp, _i, _i, _i, _vp, _vp],
     "b2r_sa_layer_fwd": [ctypes.POINTER(SaLayer), _vp],
+    "b2r_sa_layer_fwd_supported": [_i, _i, _i, _i, _i, _i, _i],
     "b2r_bn_finalize": [_vp, _i, ctypes.c_double, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp,
                         _vp, _vp],
     "b2r_pool_finalize": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],

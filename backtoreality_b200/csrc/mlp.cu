@@ -480,6 +480,41 @@ extern "C" int b2r_mlp_pack_weight(const float *w, int Cout, int Cin, int gather
   return B2R_OK;
 }
 
+namespace {
+// positions per tile for one forward launch (0 = does not fit) and whether dense tiles are
+// TMA-staged: the widest tile whose two smem stages + two TMEM stages fit; a gather tile must lie
+// inside one scene and a pooling tile must hold whole centres
+int fwd_pick_nt(int Kp, int Cout_pad, int Cin, int mode, int epilogue, int NS, long long M,
+                long long per_scene, int *raw_stage) {
+  const int MT = Cout_pad >> 7;
+  for (int raw = (mode == 1 ? 1 : 0); raw >= 0; --raw)
+    for (int nt : {128, 64, 32}) {
+      if (M % nt) continue;
+      if (mode == 0 && per_scene % nt) continue;
+      if (epilogue == 1 && (nt % NS) != 0) continue;
+      if (raw && nt < 64) continue;   // prefer wider register-staged tiles over tiny TMA ones
+      const FwdSmem L = fwd_smem_layout(Kp, Cout_pad, nt, raw ? Cin : 0);
+      if (L.total <= 227u * 1024u && 2 * MT * nt <= 512) {
+        *raw_stage = raw;
+        return nt;
+      }
+    }
+  *raw_stage = 0;
+  return 0;
+}
+}  // namespace
+
+extern "C" int b2r_sa_layer_fwd_supported(int B, int NP, int NS, int Cin, int Cout, int gather,
+                                          int pooled) {
+  if (B <= 0 || NP <= 0 || NS <= 0 || Cin <= 0 || Cout <= 0 || Cout > 256) return 0;
+  if (gather ? Cin < 3 : (Cin % 4) != 0) return 0;
+  if (pooled && !(NS == 16 || NS == 32 || NS == 64)) return 0;
+  const long long per_scene = (long long)NP * NS, M = (long long)B * per_scene;
+  int raw = 0;
+  return fwd_pick_nt(packed_k(Cin, gather), (Cout + 127) & ~127, Cin, gather ? 0 : 1,
+                     pooled ? 1 : 0, NS, M, per_scene, &raw) > 0 ? 1 : 0;
+}
+
 extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
   B2R_REQUIRE(d != nullptr, "b2r_sa_layer_fwd: null descriptor");
   B2R_REQUIRE(d->B > 0 && d->NP > 0 && d->NS > 0 && d->Cin > 0 && d->Cout > 0,
@@ -524,24 +559,8 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
     set_error("b2r_sa_layer_fwd: needs Cout <= 256 (got %d)", d->Cout);
     return B2R_ERR_UNSUPPORTED;
   }
-  const int MT = a.Cout_pad >> 7;
-  // widest tile whose two smem stages + two TMEM stages fit; a gather tile must lie inside one
-  // scene and a pooling tile must hold whole centres
-  int NT = 0;
-  a.raw_stage = 0;
-  for (int raw = (d->mode == 1 ? 1 : 0); raw >= 0 && NT == 0; --raw)
-    for (int nt : {128, 64, 32}) {
-      if (M % nt) continue;
-      if (d->mode == 0 && per_scene % nt) continue;
-      if (d->epilogue == 1 && (nt % d->NS) != 0) continue;
-      if (raw && nt < 64) continue;   // prefer wider register-staged tiles over tiny TMA ones
-      const FwdSmem L = fwd_smem_layout(a.Kp, a.Cout_pad, nt, raw ? d->Cin : 0);
-      if (L.total <= 227u * 1024u && 2 * MT * nt <= 512) {
-        NT = nt;
-        a.raw_stage = raw;
-        break;
-      }
-    }
+  const int NT = fwd_pick_nt(a.Kp, a.Cout_pad, d->Cin, d->mode, d->epilogue, d->NS, M, per_scene,
+                             &a.raw_stage);
   if (NT == 0) {
     set_error("b2r_sa_layer_fwd: layer Cin=%d Cout=%d M=%lld NP*NS=%lld does not fit (needs "
               "B*NP*NS %% 32 == 0, gather layers NP*NS %% 32 == 0, operands within 227 KB)",

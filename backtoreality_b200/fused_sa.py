@@ -52,15 +52,16 @@ def pack_weight(weight, gather):
 
 
 def supported(mlp_module, xyz, features, idx, pooling="max"):
-    """True when the fused kernels cover this block (otherwise callers use the unfused path)."""
+    """True when the fused kernels cover this block, forward AND backward (otherwise callers use
+    the unfused path).  The shape rules live in the library: b2r_sa_layer_fwd_supported /
+    b2r_sa_layer_bwd_supported apply exactly the checks the launches apply."""
     if pooling != "max" or not xyz.is_cuda:
         return False
     B, NP, NS = idx.shape
-    if NS not in (16, 32, 64) or (NP * NS) % 128 != 0:
-        return False
     blocks = list(mlp_module)
     if len(blocks) == 0:
         return False
+    lib = _lib.lib()
     for i, blk in enumerate(blocks):
         if not hasattr(blk, "bn") or blk.conv.bias is not None:
             return False
@@ -68,14 +69,10 @@ def supported(mlp_module, xyz, features, idx, pooling="max"):
         if bn.momentum is None or not bn.track_running_stats or not bn.affine:
             return False
         cout, cin = blk.conv.out_channels, blk.conv.in_channels
-        if cout > 256 or cout % 8 != 0 or cin > 380 or (i > 0 and cin % 8 != 0):
+        gather, top = (1 if i == 0 else 0), (1 if i == len(blocks) - 1 else 0)
+        if not lib.b2r_sa_layer_fwd_supported(B, NP, NS, cin, cout, gather, top):
             return False
-        if _layer_smem(cin, cout, gather=(i == 0), nt=32) > 227 * 1024:
-            return False
-        # the backward kernel has its own shared-memory / TMEM budget: ask the library now, so a
-        # block never takes the fused forward and then fails in backward
-        if not _lib.lib().b2r_sa_layer_bwd_supported(B, NP, NS, cin, cout, 1 if i == 0 else 0,
-                                                     1 if i == len(blocks) - 1 else 0):
+        if not lib.b2r_sa_layer_bwd_supported(B, NP, NS, cin, cout, gather, top):
             return False
     return True
 
@@ -108,15 +105,6 @@ def _bwd_bytes(B, N, NP, NS, Cin, Cout, gather, top, dgrad):
         rd += 4 * M * Cin
         wr = 4 * M * Cin
     return rd + wr
-
-
-def _layer_smem(cin, cout, gather, nt):
-    """Shared memory of sa_layer_fwd_kernel (csrc/mlp.cu fwd_smem_layout): the TF32 weight image
-    plus TWO stages of the X tile."""
-    kp = (((cin - 3 + 3) & ~3) + 4) if gather else ((cin + 3) & ~3)
-    ka = (kp + 31) >> 5
-    cout_pad = (cout + 127) & ~127
-    return cout_pad * ka * 128 + 2 * nt * ka * 128 + 2 * kp * 4 + nt * 4 + 1024 + 128
 
 
 def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module, training,

@@ -172,7 +172,7 @@ B2R_API int b2r_query_group_bwd(const float *grad_out, const int *idx, int B, in
  *               b2r_pool_finalize turns them into max_pool(relu(bn(z))) exactly
  * Weights are passed as the packed image produced by b2r_mlp_pack_weight (TF32-rounded,
  * 128-byte-swizzled K-major shared-memory layout, staged by one TMA bulk copy).
- * Limits: Cout <= 256, B*NP*NS % 64 == 0 (gather layers: NP*NS % 64 == 0), NS in {16,32,64}
+ * Limits: Cout <= 256, B*NP*NS % 32 == 0 (gather layers: NP*NS % 32 == 0), NS in {16,32,64}
  * for epilogue 1; otherwise B2R_ERR_UNSUPPORTED (callers then use the unfused path).
  */
 typedef struct b2r_sa_layer {
@@ -202,6 +202,9 @@ B2R_API long long b2r_mlp_weight_image_bytes(int Cout, int Cin, int gather);
 B2R_API int b2r_mlp_pack_weight(const float *w, int Cout, int Cin, int gather, float *image,
                                 void *stream);
 B2R_API int b2r_sa_layer_fwd(const b2r_sa_layer *desc, void *stream);
+/* 1 when b2r_sa_layer_fwd covers a layer of this shape, 0 otherwise (same rules as the launch). */
+B2R_API int b2r_sa_layer_fwd_supported(int B, int NP, int NS, int Cin, int Cout, int gather,
+                                       int pooled);
 
 /* BatchNorm bookkeeping from accumulated statistics (replaces the statistics half of
  * nn.BatchNorm2d in training mode, reference pytorch_utils.py:55-58): scale = gamma*invstd,
