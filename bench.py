@@ -202,7 +202,7 @@ class ClockSampler:
                 uuid = "GPU-" + uuid
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", uuid, "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -386,8 +386,10 @@ def run_b2r(a):
 
     for i in range(2):
         e2e_step(i)
-    ms_e2e, _, _ = timed_loop(e2e_step)
+    ms_e2e, _, t1e = timed_loop(e2e_step)
     if sampler:
+        # clocks over both timed regions (device-resident and end-to-end loops, back to back)
+        clocks = sampler.window(t0, t1e)
         sampler.stop()
 
     if rank != 0:
