@@ -10,7 +10,6 @@
 namespace b2r {
 namespace mlp {
 
-constexpr int kMlpThreads = 256;  // 8 warps: all load, thread 0 issues MMAs, all run the epilogue
 
 // ----------------------------------------------------------------------------- PTX helpers --
 __device__ __forceinline__ uint32_t to_tf32(float x) {
@@ -104,8 +103,10 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-// The same swizzled bytes seen MN-major (the "transposed" operand view): groups of 32 contiguous
-// MN elements (128 B) are `lbo` bytes apart, consecutive 8-deep K groups `sbo` bytes apart.
+// The same swizzled bytes seen MN-major (the "transposed" operand view): 128-byte groups of
+// contiguous MN elements are `lbo` bytes apart, consecutive 8-deep K groups `sbo` bytes apart.
+// Valid for 16-bit operands (BF16: mlp_bwd.cu); 32-bit (TF32) data needs the BASE32B layout
+// instead (scripts/probe/umma_probe.cu).
 __device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fffu);
@@ -115,12 +116,6 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t saddr, uint32_t 
   d |= (uint64_t)2 << 61;
   return d;
 }
-// general kind::tf32 instruction descriptor: a_mn / b_mn = 1 selects the MN-major operand view
-__host__ __device__ constexpr uint32_t idesc_tf32_ex(int n, int a_mn, int b_mn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
-}
-
 // byte offset of 16-byte chunk `chunk` (4 consecutive K elements) of row `row` inside a K-major
 // SW128 operand with `rows` rows: K-atom (32 elements) major, then 8-row group, then row, chunk
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk, int rows) {
