@@ -96,16 +96,18 @@ class _on_device:
             torch.cuda.set_device(self.prev)
 
 
-def furthest_point_sampling(points, nsamples):
-    """(B,N,3) f32 -> (B,nsamples) i32.  Replaces sampling.cpp:70-91."""
+def furthest_point_sampling(points, nsamples, cluster=0):
+    """(B,N,3) f32 -> (B,nsamples) i32.  Replaces sampling.cpp:70-91.  `cluster` (not in the
+    reference's signature, default 0 = lowest latency) caps the CTAs one scene holds; the
+    indices do not depend on it (include/b2r.h: b2r_fps_ex)."""
     _chk_contig(points, "points")
     _chk_float(points, "points")
     _chk_cuda(points, [])
     B, N = points.size(0), points.size(1)
     out = torch.empty((B, nsamples), dtype=torch.int32, device=points.device)
     with _on_device(points), _timed("furthest_point_sampling"):
-        _lib.check(_lib.lib().b2r_fps(points.data_ptr(), B, N, int(nsamples), out.data_ptr(),
-                                      _stream()), "furthest_point_sampling")
+        _lib.check(_lib.lib().b2r_fps_ex(points.data_ptr(), B, N, int(nsamples), out.data_ptr(),
+                                         int(cluster), _stream()), "furthest_point_sampling")
     return out
 
 

@@ -21,6 +21,7 @@ SIGNATURES = {
     "b2r_last_error": [],
     "b2r_ref_block_threads": [_i],
     "b2r_fps": [_vp, _i, _i, _i, _vp, _vp],
+    "b2r_fps_ex": [_vp, _i, _i, _i, _vp, _i, _vp],
     "b2r_fps_plan": [_i, _i, _ip, _ip, _ip, _ip],
     "b2r_gather_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "b2r_gather_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
@@ -80,6 +81,7 @@ class SaLayerBwd(ctypes.Structure):
         ("coef_a", _vp), ("coef_b", _vp), ("coef_c", _vp),
         ("dW", _vp), ("gr_prev", _vp), ("stats_prev", _vp),
         ("g_feat_t", _vp), ("g_xyz", _vp), ("g_new_xyz", _vp),
+        ("sm_limit", _i),
     ]
 
 

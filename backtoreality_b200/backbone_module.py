@@ -10,7 +10,7 @@ layer (256 vs 288), selected with `fp2_out`.
 import torch
 import torch.nn as nn
 
-from . import fused_sa, pointnet2_utils
+from . import _ext, fused_sa, pointnet2_utils
 from .pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
 
 # FPS, centre gather and ball query of ALL four levels depend only on xyz:
@@ -48,17 +48,26 @@ class Pointnet2Backbone(nn.Module):
         features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
         return xyz, features
 
-    def _geometry_prepass(self, xyz):
-        """inds / new_xyz / ball-query idx of sa1..sa4 on a side stream, one event per level."""
+    def geometry_prepass(self, xyz, fps_cluster=0, sm_limit=None, side=None):
+        """inds / new_xyz / ball-query idx of sa1..sa4 for xyz (B,N,3), issued as one chain on a
+        side stream with one event per level.  Returns the list of four per-level dicts that
+        `forward(..., geometry=)` and `PointnetSAModuleVotes.forward(..., geometry=)` take.
+
+        fps_cluster: CTAs per scene for the FPS launches (0 = lowest latency; a small number when
+        the pre-pass belongs to the NEXT batch and runs beside this batch's step,
+        train_step.PipelinedTrainStep).  sm_limit: cap of the MLP kernels that will consume each
+        level (int, or (forward, backward) tuple); default leaves GEOMETRY_SMS free while a later
+        level's FPS may still be running."""
         main = torch.cuda.current_stream()
-        side = _GEO_STREAMS.get(xyz.device)
         if side is None:
-            side = _GEO_STREAMS[xyz.device] = torch.cuda.Stream(device=xyz.device)
+            side = _GEO_STREAMS.get(xyz.device)
+            if side is None:
+                side = _GEO_STREAMS[xyz.device] = torch.cuda.Stream(device=xyz.device)
         side.wait_stream(main)
         levels, cur = [], xyz
         with torch.cuda.stream(side), torch.no_grad():
             for sa in (self.sa1, self.sa2, self.sa3, self.sa4):
-                inds = pointnet2_utils.furthest_point_sample(cur, sa.npoint)
+                inds = _ext.furthest_point_sampling(cur, sa.npoint, cluster=fps_cluster)
                 new_xyz = pointnet2_utils.gather_operation(
                     cur.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
                 idx = pointnet2_utils.ball_query(sa.radius, sa.nsample, cur, new_xyz)
@@ -67,21 +76,27 @@ class Pointnet2Backbone(nn.Module):
                 for t in (inds, new_xyz, idx):
                     t.record_stream(main)
                 levels.append({"inds": inds, "new_xyz": new_xyz, "idx": idx, "event": ev,
-                               "sm_limit": fused_sa.NUM_SMS - GEOMETRY_SMS})
+                               "sm_limit": (fused_sa.NUM_SMS - GEOMETRY_SMS) if sm_limit is None
+                               else sm_limit})
                 cur = new_xyz
-        levels[-1]["sm_limit"] = 0   # nothing runs beside sa4's MLP
+        if sm_limit is None:
+            levels[-1]["sm_limit"] = 0   # nothing runs beside sa4's MLP
         return levels
 
-    def forward(self, pointcloud: torch.Tensor, end_points=None):
+    def forward(self, pointcloud: torch.Tensor, end_points=None, geometry=None):
         """pointcloud (B,N,3+input_feature_dim) -> end_points dict (sa{1..4}_xyz/features,
-        sa1_inds, sa2_inds, fp2_features, fp2_xyz, fp2_inds)."""
+        sa1_inds, sa2_inds, fp2_features, fp2_xyz, fp2_inds).  `geometry` (not in the reference's
+        signature): the result of `geometry_prepass` for this point cloud when it was computed
+        ahead of time (e.g. during the previous step)."""
         if not end_points:
             end_points = {}
         xyz, features = self._break_up_pc(pointcloud)
         geo = [None] * 4
-        if (GEOMETRY_STREAM and xyz.is_cuda and not xyz.requires_grad
+        if geometry is not None:
+            geo = geometry
+        elif (GEOMETRY_STREAM and xyz.is_cuda and not xyz.requires_grad
                 and all(m.fusable(xyz) for m in (self.sa1, self.sa2, self.sa3, self.sa4))):
-            geo = self._geometry_prepass(xyz)
+            geo = self.geometry_prepass(xyz)
 
         xyz, features, fps_inds = self.sa1(xyz, features, geometry=geo[0])
         end_points['sa1_inds'] = fps_inds

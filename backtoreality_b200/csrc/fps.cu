@@ -344,7 +344,7 @@ int g_max_cluster = []() {
 
 // Chooses cluster size / threads / points-per-thread for (B, N).  Returns false if N exceeds what
 // 16 CTAs x 512 threads x 24 register-resident points can hold.
-bool make_plan(int B, int N, FpsPlan *pl) {
+bool make_plan(int B, int N, FpsPlan *pl, int cluster_hint = 0) {
   const int bs = b2r_ref_block_threads(N > 0 ? N : 1);
   int L = 0;
   while ((1 << L) < bs) ++L;
@@ -376,8 +376,14 @@ bool make_plan(int B, int N, FpsPlan *pl) {
       if (c >= 8 && max_c >= 10 && (long long)B * 10 <= kNumSMs && (rows + 9) / 10 <= 10) c = 10;
       else if (c == 16 && (rows + 7) / 8 <= 10) c = 8;
     }
-    const int forced = env_int("B2R_FPS_CLUSTER", 0);
-    if (forced >= 1 && forced <= 16) c = forced;   // any size: ownership only needs c*512 % 2^L == 0
+    // any size: ownership only needs c*512 % 2^L == 0.  A caller's hint (b2r_fps_ex) narrows the
+    // cluster when FPS runs beside other kernels and latency matters less than the SMs it holds.
+    int forced = env_int("B2R_FPS_CLUSTER", 0);
+    if (cluster_hint >= 1 && cluster_hint <= max_c && rows > 8) {
+      forced = cluster_hint;
+      while (forced < max_c && (rows + forced - 1) / forced > kPMax) ++forced;  // capacity first
+    }
+    if (forced >= 1 && forced <= 16) c = forced;
     pl->csize = c;
     pl->NT = 512;
     const int p = (rows + c - 1) / c;
@@ -408,8 +414,15 @@ extern "C" int b2r_fps_plan(int B, int N, int *cluster_size, int *threads, int *
 }
 
 extern "C" int b2r_fps(const float *xyz, int B, int N, int npoint, int *idx, void *stream) {
+  return b2r_fps_ex(xyz, B, N, npoint, idx, 0, stream);
+}
+
+extern "C" int b2r_fps_ex(const float *xyz, int B, int N, int npoint, int *idx, int cluster_hint,
+                          void *stream) {
   B2R_REQUIRE(B >= 0 && N >= 0 && npoint >= 0, "b2r_fps: negative size (B=%d N=%d npoint=%d)", B, N,
               npoint);
+  B2R_REQUIRE(cluster_hint >= 0 && cluster_hint <= 16, "b2r_fps_ex: cluster_hint=%d not in [0,16]",
+              cluster_hint);
   if (B == 0 || npoint == 0) return B2R_OK;
   B2R_REQUIRE(xyz != nullptr && idx != nullptr, "b2r_fps: null pointer");
   B2R_REQUIRE(B <= 65535, "b2r_fps: B=%d exceeds gridDim.y", B);
@@ -419,7 +432,7 @@ extern "C" int b2r_fps(const float *xyz, int B, int N, int npoint, int *idx, voi
     return B2R_OK;
   }
   b2r::FpsPlan pl;
-  if (!b2r::make_plan(B, N, &pl)) {
+  if (!b2r::make_plan(B, N, &pl, cluster_hint)) {
     b2r::set_error("b2r_fps: N=%d exceeds the register-resident capacity (%d points)", N,
                    b2r::kMaxCluster * 512 * b2r::kPMax);
     return B2R_ERR_UNSUPPORTED;
@@ -437,7 +450,7 @@ extern "C" int b2r_fps(const float *xyz, int B, int N, int npoint, int *idx, voi
     // a 16-CTA (non-portable) cluster was refused: fall back to the portable maximum, once
     (void)cudaGetLastError();
     b2r::g_max_cluster = 8;
-    if (!b2r::make_plan(B, N, &pl)) {
+    if (!b2r::make_plan(B, N, &pl, cluster_hint)) {
       b2r::set_error("b2r_fps: N=%d needs a 16-CTA cluster, which this device refused", N);
       return B2R_ERR_UNSUPPORTED;
     }

@@ -914,7 +914,9 @@ extern "C" int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *d, void *stream) {
   }
   const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, NT, a.top);
   a.num_tiles = (int)(M / NT);
-  const int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
+  int sms = kNumSMs;
+  if (d->sm_limit > 0 && d->sm_limit < kNumSMs) sms = d->sm_limit;
+  const int grid = a.num_tiles < sms ? a.num_tiles : sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define B2R_LAUNCH_BWD(NTV, EWV)                                                                \
   do {                                                                                          \

@@ -213,7 +213,7 @@ def pack_weight_bf16(weight, gather):
 
 
 def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, weights, gammas,
-                    training, saved, need_feat, need_xyz, need_new_xyz):
+                    training, saved, need_feat, need_xyz, need_new_xyz, sm_limit=0):
     """Backward of sa_mlp_forward through csrc/mlp_bwd.cu.
 
     g_out_cm (B,Cl,NP) gradient of the pooled output.  Returns
@@ -265,6 +265,7 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
         b = _lib.SaLayerBwd()
         b.B, b.N, b.NP, b.NS, b.Cin, b.Cout = B, N, NP, NS, Cin, Cout
         b.mode = 0 if l == 0 else 1
+        b.sm_limit = int(sm_limit)
         if l == top:   # z is recomputed inside the kernel from the layer's input
             b.dysel, b.asel = _ptr(dysel), _ptr(asel)
         else:
@@ -321,12 +322,15 @@ class _FusedSABlock(torch.autograd.Function):
         feat_t = to_point_major(features.contiguous()) if features is not None else None
         need = any(ctx.needs_input_grad)
         save = {} if need else None
+        # sm_limit: one cap for both directions, or (forward cap, backward cap)
+        fwd_limit, bwd_limit = sm_limit if isinstance(sm_limit, tuple) else (sm_limit, 0)
         out_cm, _ = sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
                                    training, want_point_major=False, save=save,
-                                   sm_limit=sm_limit)
+                                   sm_limit=fwd_limit)
         if need:
             ctx.saved = (xyz, new_xyz, feat_t, idx, float(radius), bool(normalize_xyz),
                          bool(training), save, params)
+            ctx.bwd_sm_limit = int(bwd_limit)
         return out_cm
 
     @staticmethod
@@ -338,7 +342,8 @@ class _FusedSABlock(torch.autograd.Function):
         nig = ctx.needs_input_grad
         g_feat_t, g_xyz, g_new_xyz, dWs, dgs, dbs = sa_mlp_backward(
             g_out.contiguous(), xyz, new_xyz, feat_t, idx, radius, normalize_xyz, weights, gammas,
-            training, save, need_feat=nig[2], need_xyz=nig[0], need_new_xyz=nig[1])
+            training, save, need_feat=nig[2], need_xyz=nig[0], need_new_xyz=nig[1],
+            sm_limit=ctx.bwd_sm_limit)
         g_features = g_feat_t.transpose(1, 2).contiguous() if g_feat_t is not None else None
         out = [g_xyz, g_new_xyz, g_features, None, None, None, None, None, None]
         for i in range(L):
@@ -349,7 +354,9 @@ class _FusedSABlock(torch.autograd.Function):
 def sa_block(xyz, new_xyz, features, idx, radius, normalize_xyz, mlp_module, training,
              sm_limit=0):
     """Differentiable fused SA block: returns new_features (B, mlp[-1], npoint).  sm_limit > 0
-    caps the forward kernels' persistent grid (SMs left to a concurrent geometry stream)."""
+    caps the forward kernels' persistent grid (SMs left to a concurrent geometry stream); a tuple
+    (forward cap, backward cap) also caps the backward kernels (the pipelined step, where the
+    NEXT batch's geometry runs beside this batch's whole forward and backward)."""
     params = []
     for blk in mlp_module:
         params += [blk.conv.weight, blk.bn.bn.weight, blk.bn.bn.bias]

@@ -53,6 +53,9 @@ class _SAVotesBase(nn.Module):
             self.sigma = self.radius / 2
         self.normalize_xyz = normalize_xyz
         self.ret_unique_cnt = ret_unique_cnt
+        # cap of the fused kernels' persistent grids when no `geometry` carries one: 0 = every
+        # SM, int or (forward, backward) otherwise (see fused_sa.sa_block)
+        self.sm_limit = 0
 
         if npoint is not None:
             self.grouper = pointnet2_utils.QueryAndGroup(
@@ -99,8 +102,9 @@ class PointnetSAModuleVotes(_SAVotesBase):
                 inds: torch.Tensor = None, geometry: dict = None):
         if geometry is not None:
             # FPS / centre gather / ball query were done ahead of time on a geometry stream
-            # (backbone_module.Pointnet2Backbone._geometry_prepass): wait for them, run the MLP
-            torch.cuda.current_stream().wait_event(geometry["event"])
+            # (backbone_module.Pointnet2Backbone.geometry_prepass): wait for them, run the MLP
+            if geometry.get("event") is not None:
+                torch.cuda.current_stream().wait_event(geometry["event"])
             new_features = self._abstract(xyz, geometry["new_xyz"], features, idx=geometry["idx"],
                                           sm_limit=geometry.get("sm_limit", 0))
             return geometry["new_xyz"], new_features, geometry["inds"]
@@ -112,7 +116,7 @@ class PointnetSAModuleVotes(_SAVotesBase):
         new_xyz = pointnet2_utils.gather_operation(
             xyz_flipped, inds
         ).transpose(1, 2).contiguous() if self.npoint is not None else None
-        new_features = self._abstract(xyz, new_xyz, features)
+        new_features = self._abstract(xyz, new_xyz, features, sm_limit=self.sm_limit)
         return new_xyz, new_features, inds
 
 

@@ -55,3 +55,119 @@ class CapturedTrainStep:
         self.static_in.copy_(batch, non_blocking=non_blocking)
         self.graph.replay()
         return self.static_loss
+
+
+class PipelinedTrainStep:
+    """The captured step, software-pipelined across batches: while the GPU runs forward + backward
+    + optimizer of batch i, the geometry pre-pass of batch i+1 (FPS, centre gather and ball query
+    of sa1..sa4 -- they depend on xyz alone, never on weights) runs beside it on a side stream
+    inside the same CUDA graph.  FPS is a serial chain of 2047+1023+511+255 dependent iterations
+    that keeps few SMs busy for 2 ms; here it is off the critical path, on narrow clusters
+    (`fps_cluster` CTAs per scene) next to MLP kernels whose persistent grids leave those SMs free.
+
+        pipe = PipelinedTrainStep(net.backbone_net, step_fn, first_batch)
+        for nxt in loader:            # the data loader is one batch ahead, as any prefetcher is
+            loss_of_previous = pipe(nxt)
+
+    `step_fn(pointcloud, geometry) -> loss` runs forward (passing `geometry` down to
+    Pointnet2Backbone.forward), backward and the optimizer.  Every call does one geometry pre-pass
+    and one full step, so K calls cost K of each: nothing is skipped, only re-ordered.
+    `__call__(next_batch)` returns the loss of the batch submitted by the PREVIOUS call (or by
+    the constructor / `prime`).  BatchNorm momentum / learning-rate caveats as CapturedTrainStep.
+    """
+
+    GEO_KEYS = ("inds", "new_xyz", "idx")
+
+    def __init__(self, backbone, step_fn, first_batch, warmup=3, fps_cluster=4, sm_caps=None,
+                 after_warmup_step=None):
+        from . import fused_sa
+        self.backbone = backbone
+        self.step_fn = step_fn
+        self.after_warmup_step = after_warmup_step
+        self.fps_cluster = int(fps_cluster)
+        B = first_batch.shape[0]
+        if sm_caps is None:
+            # SA1's FPS holds B*fps_cluster SMs for the first ~2 ms of the step (the forward);
+            # the later levels hold B SMs (one CTA per scene) into the early backward.  The
+            # backward of sa1/sa2 -- the bulk of the step -- runs after the chain has drained.
+            wide = max(fused_sa.NUM_SMS - B * self.fps_cluster, 32)
+            narrow = max(fused_sa.NUM_SMS - B, 32)
+            sm_caps = [(wide, 0), (wide, 0), (wide, narrow), (wide, narrow)]
+        self.sm_caps = sm_caps
+        self.warmup = warmup
+        self.cur = first_batch.clone()
+        self.next = first_batch.clone()
+        self.side = torch.cuda.Stream(device=first_batch.device)
+        self.geo_cur = None
+        self.graph = None
+        self.static_loss = None
+        self.launches_per_step = None
+        self.prime(first_batch)
+        self.recapture()
+
+    def _xyz(self, pc):
+        return pc[..., 0:3].contiguous()
+
+    def _levels(self, tensors):
+        return [dict(t, event=None, sm_limit=cap) for t, cap in zip(tensors, self.sm_caps)]
+
+    def prime(self, batch):
+        """(Re)start the pipeline: `batch` becomes the current batch, its geometry is computed
+        now, eagerly."""
+        self.cur.copy_(batch)
+        xyz = self._xyz(self.cur)     # stays referenced until the side stream has been joined
+        levels = self.backbone.geometry_prepass(xyz, side=self.side)
+        torch.cuda.current_stream().wait_stream(self.side)
+        fresh = [{k: lv[k] for k in self.GEO_KEYS} for lv in levels]
+        if self.geo_cur is None:
+            self.geo_cur = [{k: v.clone() for k, v in lv.items()} for lv in fresh]
+        else:
+            for dst, src in zip(self.geo_cur, fresh):
+                for k in self.GEO_KEYS:
+                    dst[k].copy_(src[k])
+
+    def _pipelined(self):
+        """one pipelined step on the static buffers: geometry(next) beside step(cur), then rotate"""
+        main = torch.cuda.current_stream()
+        # xyz_next is allocated on the main stream and read by the side stream for the whole
+        # step: keep the reference until the join, or the allocator hands its memory to the
+        # step's own activations while FPS is still reading it
+        xyz_next = self._xyz(self.next)
+        nxt = self.backbone.geometry_prepass(xyz_next, fps_cluster=self.fps_cluster, sm_limit=0,
+                                             side=self.side)
+        loss = self.step_fn(self.cur, self._levels(self.geo_cur))
+        main.wait_stream(self.side)
+        del xyz_next
+        for dst, src in zip(self.geo_cur, nxt):
+            for k in self.GEO_KEYS:
+                dst[k].copy_(src[k])
+        self.cur.copy_(self.next)
+        return loss
+
+    def recapture(self):
+        from . import _ext
+        warm = torch.cuda.Stream()
+        warm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(warm):
+            for _ in range(self.warmup):
+                self._pipelined()
+                if self.after_warmup_step is not None:
+                    self.after_warmup_step()
+        torch.cuda.current_stream().wait_stream(warm)
+        torch.cuda.synchronize()
+        saved_ops = set(_ext.TIME_OPS)
+        _ext.TIME_OPS.clear()          # timing events cannot be recorded inside a capture
+        l0 = _ext.LAUNCHES
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                loss = self._pipelined()
+            self.graph, self.static_loss = g, loss
+            self.launches_per_step = _ext.LAUNCHES - l0
+        finally:
+            _ext.TIME_OPS.update(saved_ops)
+
+    def __call__(self, next_batch, non_blocking=True):
+        self.next.copy_(next_batch, non_blocking=non_blocking)
+        self.graph.replay()
+        return self.static_loss

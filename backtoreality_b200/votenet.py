@@ -150,7 +150,9 @@ class VoteNet(nn.Module):
                                    num_proposal, sampling)
 
     def forward(self, inputs):
-        end_points = self.backbone_net(inputs['point_clouds'], {})
+        # 'geometry' (optional, not in the reference): sa1..sa4 indices computed ahead of time
+        end_points = self.backbone_net(inputs['point_clouds'], {},
+                                       geometry=inputs.get('geometry'))
         xyz = end_points['fp2_xyz']
         features = end_points['fp2_features']
         end_points['seed_inds'] = end_points['fp2_inds']

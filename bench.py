@@ -60,6 +60,13 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every kernel from Python instead of replaying the captured step")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="geometry pre-pass of a batch inside its own step (not one step ahead)")
+    ap.add_argument("--fps-cluster", type=int, default=4,
+                    help="pipelined step: CTAs per scene of the next batch's FPS")
+    ap.add_argument("--sm-caps", default="",
+                    help="pipelined step: persistent-grid caps 'fwd:bwd' of sa1,sa2,sa3,sa4,vote-agg "
+                         "(comma separated, 0 = every SM); default: see PipelinedTrainStep")
     return ap.parse_args()
 
 
@@ -75,6 +82,11 @@ def workload_config(a, world):
         "l2": "256 MB buffer written between steps (flush) + 4 rotating input batches",
         "launch": ("whole step (fwd+bwd+Adam) captured in one CUDA graph, replayed per batch" if world == 1
                    else "fwd+bwd replayed from one CUDA graph; NCCL all-reduce + fused Adam eager"),
+        "pipeline": ("none: FPS / ball query of a batch run inside its own step" if a.no_pipeline or a.no_graph
+                     else "geometry pre-pass (FPS, centre gather, ball query of sa1..sa4) of batch i+1 runs "
+                          "beside the step of batch i in the same graph (%d-CTA FPS clusters); every timed "
+                          "step = one pre-pass + one fwd/bwd/Adam; e2e copies batch i+1 from pinned host "
+                          "memory and reads the loss of batch i" % a.fps_cluster),
         "mlp_math": "SA blocks: fused tcgen05, forward TF32 / backward BF16 operands, fp32 accumulate; "
                     "FP/vote heads: cuDNN with TF32 allowed (torch default, as the reference runs)",
     }
@@ -278,10 +290,10 @@ def run_b2r(a):
     resident = [h.to(dev) for h in host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def fwd_bwd(pc):
+    def fwd_bwd(pc, geometry=None):
         for p in params:          # autograd then ASSIGNS fresh gradients: no accumulate kernels,
             p.grad = None         # nothing to zero
-        ep = net({"point_clouds": pc})
+        ep = net({"point_clouds": pc, "geometry": geometry})
         loss = synthetic_loss(ep)
         loss.backward()
         live["grads"] = [p.grad for p in params]
@@ -292,8 +304,8 @@ def run_b2r(a):
             bucket.reduce_from(live["grads"])
         opt.step()
 
-    def step(pc):
-        loss = fwd_bwd(pc)
+    def step(pc, geometry=None):
+        loss = fwd_bwd(pc, geometry)
         finish()
         return loss
 
@@ -348,16 +360,35 @@ def run_b2r(a):
     # 3-kernel fused Adam stay eager so no collective is ever captured)
     graphed = None
     capture_all = world == 1
+    pipelined = not (a.no_graph or a.no_pipeline)
     if not a.no_graph:
         try:
-            from backtoreality_b200.train_step import CapturedTrainStep
+            from backtoreality_b200.train_step import CapturedTrainStep, PipelinedTrainStep
             stage("capturing the step into a CUDA graph")
-            graphed = CapturedTrainStep(step if capture_all else fwd_bwd, resident[0],
-                                        after_warmup_step=None if capture_all else finish)
+            if pipelined:
+                # the vote-aggregation block has no pre-pass level of its own: give its kernels the
+                # caps of the levels around it (forward: beside SA1's FPS; backward: it runs first)
+                from backtoreality_b200 import fused_sa
+                caps = None
+                net.pnet.vote_aggregation.sm_limit = (
+                    max(fused_sa.NUM_SMS - a.batch * a.fps_cluster, 32),
+                    max(fused_sa.NUM_SMS - a.batch, 32))
+                if a.sm_caps:
+                    caps = [tuple(int(v) for v in c.split(":")) for c in a.sm_caps.split(",")]
+                    net.pnet.vote_aggregation.sm_limit = caps[4]
+                    caps = caps[:4]
+                graphed = PipelinedTrainStep(net.backbone_net, step if capture_all else fwd_bwd,
+                                             resident[0], fps_cluster=a.fps_cluster, sm_caps=caps,
+                                             after_warmup_step=None if capture_all else finish)
+            else:
+                graphed = CapturedTrainStep(step if capture_all else fwd_bwd, resident[0],
+                                            after_warmup_step=None if capture_all else finish)
             stage("captured (%d libb2r launches per step)" % graphed.launches_per_step)
         except Exception as e:  # report, then measure the eager loop instead
             log("CUDA-graph capture failed (%s: %s); timing the eager step" % (type(e).__name__, e))
             graphed = None
+            pipelined = False
+            net.pnet.vote_aggregation.sm_limit = 0
 
     def run_step(pc):
         if graphed is None:
@@ -367,25 +398,35 @@ def run_b2r(a):
             finish()
         return loss
 
+    # pipelined: call i submits batch i+1 (whose geometry pre-pass runs in this call) and trains
+    # on batch i; resident[0] was submitted by the constructor
+    nxt = 1 if pipelined else 0
     for i in range(3):
-        run_step(resident[i % pool_n])
+        run_step(resident[(i + nxt) % pool_n])
+    if pipelined:
+        graphed.prime(resident[0])
     sampler = ClockSampler(dev) if rank == 0 else None
     time.sleep(0.3)
 
     # (1) inputs resident in HBM (graph mode: one device-to-device copy into the static input)
-    ms_dev, t0, t1 = timed_loop(lambda i: run_step(resident[i % pool_n]))
+    ms_dev, t0, t1 = timed_loop(lambda i: run_step(resident[(i + nxt) % pool_n]))
     launches = launches_per_step * a.steps
     clocks = sampler.window(t0, t1) if sampler else None
 
     # (2) end to end: pinned host input -> device each step, loss read back each step
     def e2e_step(i):
         if graphed is not None:
-            return float(run_step(host[i % pool_n]).item())  # H2D straight into the static input
+            # H2D straight into the static input (pipelined: the NEXT batch's buffer)
+            return float(run_step(host[(i + nxt) % pool_n]).item())
         pc = host[i % pool_n].to(dev, non_blocking=True)
         return float(step(pc).item())
 
+    if pipelined:
+        graphed.prime(resident[0])
     for i in range(2):
         e2e_step(i)
+    if pipelined:
+        graphed.prime(resident[0])
     ms_e2e, _, t1e = timed_loop(e2e_step)
     if sampler:
         # clocks over both timed regions (device-resident and end-to-end loops, back to back)

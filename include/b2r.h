@@ -62,6 +62,14 @@ B2R_API int b2r_ref_block_threads(int work_size);
  */
 B2R_API int b2r_fps(const float *xyz, int B, int N, int npoint, int *idx, void *stream);
 
+/* Same sampling, same indices, with the caller choosing how many SMs a scene may hold:
+ * cluster_hint = 0 picks the lowest-latency cluster (b2r_fps); 1..16 asks for that many CTAs per
+ * scene (raised only as far as the register-resident capacity needs).  A narrow cluster is for
+ * FPS that runs BESIDE other kernels -- the geometry pre-pass of the next batch on a side stream
+ * (backbone_module.Pointnet2Backbone.geometry_prepass) -- where it is off the critical path. */
+B2R_API int b2r_fps_ex(const float *xyz, int B, int N, int npoint, int *idx, int cluster_hint,
+                       void *stream);
+
 /* Launch geometry b2r_fps would use for (B,N): cluster size, threads per CTA, points per thread
  * and dynamic shared memory bytes.  Any out pointer may be NULL. */
 B2R_API int b2r_fps_plan(int B, int N, int *cluster_size, int *threads, int *points_per_thread,
@@ -266,6 +274,7 @@ typedef struct b2r_sa_layer_bwd_desc {
   float *g_feat_t;          /* mode 0: (B,N,Cin-3) point-major, ACCUMULATED; NULL = not needed */
   float *g_xyz;             /* mode 0: (B,N,3) ACCUMULATED; NULL = not needed */
   float *g_new_xyz;         /* mode 0: (B,NP,3) ACCUMULATED; NULL = not needed */
+  int sm_limit;             /* as b2r_sa_layer.sm_limit: 0 = every SM, else at most this many CTAs */
 } b2r_sa_layer_bwd_desc;
 
 B2R_API long long b2r_mlp_weight_bf16_image_bytes(int Cout, int Cin, int gather);

@@ -284,6 +284,57 @@ def test_captured_train_step_matches_eager(cuda):
     assert int(bn_e.num_batches_tracked) == 4 and int(bn_g.num_batches_tracked) == 7
 
 
+def test_pipelined_train_step_matches_sequential(cuda):
+    """train_step.PipelinedTrainStep (geometry pre-pass of batch i+1 beside the step of batch i,
+    narrow FPS clusters, capped MLP grids) must train on the same batches in the same order as
+    the plain step: with lr = 0 the loss returned by call i is the eager loss of batch i (up to
+    the summation order of the BatchNorm statistics under a different persistent grid), the
+    rotated geometry buffers hold exactly the indices a fresh pre-pass computes, and the
+    gradients agree within the atomics' run-to-run noise."""
+    from backtoreality_b200.train_step import PipelinedTrainStep
+    from backtoreality_b200.votenet import VoteNet
+
+    def make():
+        torch.manual_seed(5)
+        net = VoteNet(4, 1, 4, np.ones((4, 3), np.float32), input_feature_dim=1, num_proposal=64,
+                      vote_factor=1, sampling="vote_fps").to(cuda).train()
+        opt = torch.optim.SGD(net.parameters(), lr=0.0)
+
+        def step(pc, geometry=None):
+            for p in net.parameters():
+                p.grad = None
+            ep = net({"point_clouds": pc, "geometry": geometry})
+            loss = (ep["proposal_scores_raw"] ** 2).mean() + ((ep["vote_xyz"] - ep["seed_xyz"]) ** 2).mean()
+            loss.backward()
+            opt.step()
+            return loss.detach()
+        return net, step
+
+    batches = [torch.from_numpy(scenes.batch(300 + 2 * i, 2, 12000, C=1, kind="room", dup=0.2)).to(cuda)
+               for i in range(4)]
+    net_e, step_e = make()
+    eager = [float(step_e(b)) for b in batches]
+    net_p, step_p = make()
+    net_p.pnet.vote_aggregation.sm_limit = (100, 120)
+    pipe = PipelinedTrainStep(net_p.backbone_net, step_p, batches[0], warmup=2, fps_cluster=3)
+    assert pipe.launches_per_step > 50
+    got = [float(pipe(batches[(i + 1) % 4])) for i in range(4)]   # call i trains on batch i
+    assert len(set(got)) == 4
+    for g, e in zip(got, eager):
+        assert abs(g - e) <= 1e-5 * abs(e), (got, eager)
+    # after four calls the current batch is batches[0] again: its rotated geometry is the fresh one
+    torch.cuda.synchronize()
+    fresh = net_p.backbone_net.geometry_prepass(batches[0][..., :3].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(pipe.cur, batches[0])
+    for lv_p, lv_f in zip(pipe.geo_cur, fresh):
+        for k in PipelinedTrainStep.GEO_KEYS:
+            assert torch.equal(lv_p[k], lv_f[k]), k
+    for (n1, p1), (n2, p2) in zip(net_e.named_parameters(), net_p.named_parameters()):
+        assert torch.equal(p1, p2), n1        # lr = 0
+        assert rel_l2(p2.grad.cpu().numpy(), p1.grad.cpu().numpy()) < 3e-2, n1
+
+
 def test_geometry_stream_matches_serial_path(cuda):
     """Pointnet2Backbone with the geometry pre-pass on a side stream (FPS / centre gather / ball
     query of all levels ahead of the MLPs, MLP grids capped to leave SMs free) must compute what

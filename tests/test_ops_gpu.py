@@ -80,6 +80,20 @@ def test_fps_forced_cluster_sizes(cuda, cluster, monkeypatch):
     _fps_check(xyz, 300, cuda)
 
 
+@pytest.mark.parametrize("hint", [1, 3, 4, 5, 10, 16])
+def test_fps_cluster_hint_does_not_change_indices(cuda, hint):
+    """b2r_fps_ex: the caller-chosen cluster width (narrow clusters for FPS that runs beside
+    other kernels) changes the launch geometry only -- the indices stay the oracle's; a hint too
+    narrow for the register-resident capacity is widened, not refused."""
+    from backtoreality_b200 import _ext
+    xyz = scenes.batch(9, 2, 40000, C=0, kind="room", dup=0.2)[..., :3]
+    got = _ext.furthest_point_sampling(_t(xyz, cuda), 512, cluster=hint).cpu().numpy()
+    assert np.array_equal(got, cpu_ops.fps(xyz, 512))
+    small = scenes.batch(10, 2, 3000, C=0, kind="room", dup=0.2)[..., :3]  # one CTA regardless
+    got = _ext.furthest_point_sampling(_t(small, cuda), 256, cluster=hint).cpu().numpy()
+    assert np.array_equal(got, cpu_ops.fps(small, 256))
+
+
 def test_fps_npoint_zero_and_one(cuda):
     from backtoreality_b200 import _ext
     xyz = torch.rand(2, 100, 3, device=cuda)
