@@ -559,6 +559,8 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
     set_error("b2r_sa_layer_fwd: needs Cout <= 256 (got %d)", d->Cout);
     return B2R_ERR_UNSUPPORTED;
   }
+  // thin first layer (Cin <= 8): a streaming CUDA-core kernel, not a tensor-core tile pipeline
+  if (thin::fwd_applicable(d)) return thin::fwd_launch(d, stream);
   const int NT = fwd_pick_nt(a.Kp, a.Cout_pad, d->Cin, d->mode, d->epilogue, d->NS, M, per_scene,
                              &a.raw_stage);
   if (NT == 0) {

@@ -899,6 +899,8 @@ extern "C" int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *d, void *stream) {
   }
   B2R_REQUIRE(!(a.do_dgrad || a.top) || d->w_image_bf16 != nullptr,
               "b2r_sa_layer_bwd: null weight image");
+  // thin first layer without an input gradient (SA1: xyz / height are leaves): streaming kernel
+  if (thin::bwd_applicable(d)) return thin::bwd_launch(d, stream);
   const long long M = (long long)d->B * d->NP * d->NS;
   const long long per_scene = (long long)d->NP * d->NS;
   if (a.Cout_pad > 256 || (d->Cout % 8) != 0 || (d->mode == 1 && (d->Cin % 8) != 0)) {

@@ -216,4 +216,12 @@ inline int pow2_shift(int v) {   // log2(v) if v is a power of two (v >= 1), els
 }
 
 }  // namespace mlp
+
+// CUDA-core streaming variants of the thin first layer (Cin <= 8), mlp_thin.cu
+namespace thin {
+bool fwd_applicable(const b2r_sa_layer *d);
+int fwd_launch(const b2r_sa_layer *d, void *stream);
+bool bwd_applicable(const b2r_sa_layer_bwd_desc *d);
+int bwd_launch(const b2r_sa_layer_bwd_desc *d, void *stream);
+}  // namespace thin
 }  // namespace b2r

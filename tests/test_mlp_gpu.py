@@ -423,3 +423,86 @@ def test_center_refine_head_single_layer_block(cuda, training):
             assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < tol, n
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+# ------------------------------------------------ thin first layer (csrc/mlp_thin.cu) --------
+THIN_SHAPES = [(1, 64, 5000, 64, 64, True), (0, 64, 3000, 128, 32, True), (5, 128, 2000, 96, 16, False),
+               (2, 32, 1500, 33, 32, True), (1, 64, 40000, 2048, 64, True)]
+
+
+def _thin_inputs(cuda, C, Cout, N, NP, NS):
+    B = 2
+    g = torch.Generator(device="cpu").manual_seed(7 * C + Cout + N)
+    xyz = torch.rand(B, N, 3, generator=g).to(cuda)
+    new_xyz = torch.rand(B, NP, 3, generator=g).to(cuda)
+    feats = torch.randn(B, C, N, generator=g).to(cuda) if C else None
+    idx = torch.randint(0, N, (B, NP, NS), generator=g, dtype=torch.int32).to(cuda)
+    w = (torch.randn(Cout, 3 + C, 1, 1, generator=g) / (3 + C) ** 0.5).to(cuda)
+    return B, g, xyz, new_xyz, feats, idx, w
+
+
+@pytest.mark.parametrize("C,Cout,N,NP,NS,norm", THIN_SHAPES)
+def test_thin_first_layer_forward(cuda, C, Cout, N, NP, NS, norm, monkeypatch):
+    """Cin <= 8 gather layers run a streaming CUDA-core kernel instead of the tcgen05 pipeline:
+    same operand rounding (TF32), so z must agree with the tensor-core path to fp32 summation
+    order, with fp64 within the TF32 tolerance, and the BatchNorm sums must be the sums of z."""
+    from backtoreality_b200 import _ext, fused_sa
+    B, g, xyz, new_xyz, feats, idx, w = _thin_inputs(cuda, C, Cout, N, NP, NS)
+    r = 0.37
+    feat_t = fused_sa.to_point_major(feats) if C else None
+    image = fused_sa.pack_weight(w, gather=True)
+    M = B * NP * NS
+    out = {}
+    for path in ("thin", "tensor"):
+        monkeypatch.setenv("B2R_NO_THIN", "0" if path == "thin" else "1")
+        z = torch.full((M, Cout), float("nan"), device=cuda)
+        stats = torch.zeros(2, Cout, dtype=torch.float64, device=cuda)
+        kw = dict(B=B, N=N, NP=NP, NS=NS, Cin=3 + C, Cout=Cout, mode=0, epilogue=0, xyz=xyz,
+                  new_xyz=new_xyz, idx=idx, radius=r, normalize_xyz=int(norm), w_image=image, z=z,
+                  stats=stats)
+        if C:
+            kw["feat_t"] = feat_t
+        _run_layer(cuda, **kw)
+        out[path] = (z, stats)
+    z, stats = out["thin"]
+    grouped = _ext.query_group(xyz, new_xyz, feats, idx, r, norm)
+    x = grouped.permute(0, 2, 3, 1).reshape(M, 3 + C).double()
+    want = x @ w.double().reshape(Cout, 3 + C).t()
+    assert rel_l2(z.cpu().numpy(), want.cpu().numpy()) < TF32_TOL
+    assert rel_l2(z.cpu().numpy(), out["tensor"][0].cpu().numpy()) < 2e-6
+    np.testing.assert_allclose(stats[0].cpu().numpy(), z.double().sum(0).cpu().numpy(),
+                               rtol=1e-6, atol=1e-3)
+    np.testing.assert_allclose(stats[1].cpu().numpy(), (z.double() ** 2).sum(0).cpu().numpy(),
+                               rtol=1e-6, atol=1e-3)
+
+
+@pytest.mark.parametrize("C,Cout,N,NP,NS,norm", THIN_SHAPES)
+def test_thin_first_layer_backward(cuda, C, Cout, N, NP, NS, norm, monkeypatch):
+    """dW of a thin first layer whose inputs need no gradient: dz = a*gr + b*z + c streamed from
+    gr and z, dW = dz^T x in fp32 registers.  Against fp64 (fp32 tolerance) and against the
+    tcgen05 BF16 path (its tolerance); dW is ACCUMULATED into the caller's buffer."""
+    from backtoreality_b200 import _ext, fused_sa
+    B, g, xyz, new_xyz, feats, idx, w = _thin_inputs(cuda, C, Cout, N, NP, NS)
+    r = 0.37
+    M = B * NP * NS
+    gr = torch.randn(M, Cout, generator=g).to(cuda)
+    zz = torch.randn(M, Cout, generator=g).to(cuda)
+    ca, cb, cc = (torch.randn(Cout, generator=g).to(cuda) for _ in range(3))
+    feat_t = fused_sa.to_point_major(feats) if C else None
+    out = {}
+    for path in ("thin", "tensor"):
+        monkeypatch.setenv("B2R_NO_THIN", "0" if path == "thin" else "1")
+        dW = torch.ones(Cout, 3 + C, device=cuda)      # accumulated on top of what is there
+        kw = dict(B=B, N=N, NP=NP, NS=NS, Cin=3 + C, Cout=Cout, mode=0, xyz=xyz, new_xyz=new_xyz,
+                  idx=idx, radius=r, normalize_xyz=int(norm), gr=gr, z=zz, coef_a=ca, coef_b=cb,
+                  coef_c=cc, dW=dW)
+        if C:
+            kw["feat_t"] = feat_t
+        _run_bwd(**kw)
+        out[path] = dW - 1.0
+    grouped = _ext.query_group(xyz, new_xyz, feats, idx, r, norm)
+    x = grouped.permute(0, 2, 3, 1).reshape(M, 3 + C).double()
+    dz = ca.double() * gr.double() + cb.double() * zz.double() + cc.double()
+    want = dz.t() @ x
+    assert rel_l2(out["thin"].cpu().numpy(), want.cpu().numpy()) < 2e-5
+    assert rel_l2(out["tensor"].cpu().numpy(), want.cpu().numpy()) < BF16_TOL
