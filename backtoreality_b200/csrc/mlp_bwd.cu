@@ -166,15 +166,21 @@ __global__ void pack_weight_bf16_kernel(const float *__restrict__ w, int Cout, i
   }
 }
 
-template <int NT, int EW>
+// MODE (0 gather layer, 1 dense layer) and TOP (pooled top layer: z recomputed, DZ built by the
+// epilogue warps) are compile-time: every instantiation carries only its own producer /
+// epilogue code.  One runtime-branched kernel was 52,872 SASS instructions (846 KB) and spent
+// 25 % of its warp-stall samples waiting for instruction fetch (ncu, stall_no_inst).
+template <int NT, int EW, int MODE, int TOP>
 __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdArgs a) {
+  constexpr int kMode = MODE;
+  constexpr bool kTop = TOP != 0;
   constexpr int kEpiThreads = EW * 32, kProdThreads = (kBwdWarps - 1 - EW) * 32;
   auto bar_epi = [] { bar_named<kEpiThreads>(1); };
   auto bar_prod = [] { bar_named<kProdThreads>(2); };
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~(uintptr_t)1023);
-  const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, NT, a.top);
+  const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, NT, kTop);
   uint8_t *s_w = base + L.w_off;
   float *s_ca = reinterpret_cast<float *>(base + L.coef_off);
   float *s_cb = s_ca + a.Cout;
@@ -198,7 +204,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
   const int MTl = a.Cout_pad >> 7;        // 128-row M tiles over Cout (recompute, wgrad)
   constexpr int NCH = NT / 32;
   const bool has_coef = a.dz == nullptr;
-  const int w12 = ((a.top && MTl > (a.do_dgrad ? MTp : 0)) ? MTl : (a.do_dgrad ? MTp : 0)) * NT;
+  const int w12 = ((kTop && MTl > (a.do_dgrad ? MTp : 0)) ? MTl : (a.do_dgrad ? MTp : 0)) * NT;
   const uint32_t d3_col0 = 2u * (uint32_t)w12;
   constexpr uint32_t kTmemCols = 512;
   const long long per_scene = (long long)a.NP * a.NS;
@@ -214,7 +220,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
     for (uint32_t i = tid * 16; i < zb; i += kBwdThreads * 16)
       *reinterpret_cast<uint4 *>(base + L.x_off[0] + i) = make_uint4(0, 0, 0, 0);
   }
-  if (a.mode == 1)
+  if (kMode == 1)
     for (int i = tid; i < a.Cin; i += kBwdThreads) {
       s_scale[i] = a.scale_prev[i];
       s_shift[i] = a.shift_prev[i];
@@ -230,7 +236,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const bool need_w = a.top || a.do_dgrad;
+  const bool need_w = kTop || a.do_dgrad;
   if (tid == 0 && need_w) {
     mbar_expect_tx(bar(12), L.w_bytes);
     bulk_g2s(smem_u32(s_w), a.w_image, L.w_bytes, bar(12));
@@ -250,17 +256,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
       int *s_idx = s_idx4 + (k & 3) * NT;
       if (ptid == 0 && tile + 2 * grid < a.num_tiles) {   // pull tile k+2 into L2 meanwhile
         const size_t pn = (size_t)(pos0 + 2ll * grid * NT);
-        if (!a.top) {
+        if (!kTop) {
           if (!has_coef) prefetch_l2(a.dz + pn * a.Cout, (uint32_t)NT * a.Cout * 4u);
           else {
             prefetch_l2(a.gr + pn * a.Cout, (uint32_t)NT * a.Cout * 4u);
             prefetch_l2(a.z + pn * a.Cout, (uint32_t)NT * a.Cout * 4u);
           }
         }
-        if (a.mode == 1) prefetch_l2(a.z_prev + pn * a.Cin, (uint32_t)NT * a.Cin * 4u);
+        if (kMode == 1) prefetch_l2(a.z_prev + pn * a.Cin, (uint32_t)NT * a.Cin * 4u);
       }
       // ---- DZ tile from HBM (dense layers / direct dz); the top layer's DZ comes from D1 ------
-      if (!a.top) {
+      if (!kTop) {
         const int total = NT * CH8;
         const size_t o0 = (size_t)pos0 * a.Cout;
         for (int i0 = ptid; i0 < total; i0 += kProdThreads * 4) {
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
         }
       }
       // ---- X tile ---------------------------------------------------------------------------
-      if (a.mode == 0) {
+      if (kMode == 0) {
         // indices of this tile were requested one tile ago (nidx): no dependent global wait here
         if (ptid < NT) {
           s_idx[ptid] = (k == 0) ? a.idx[pos0 + ptid] : nidx;
@@ -427,7 +433,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
         mbar_wait(bar(0 + s), (uint32_t)(n & 1));           // X (and DZ) of tile k are in smem
         mbar_wait(bar(10 + s), (uint32_t)((n & 1) ^ 1));    // epilogue of tile k-2 left D1/D2[s]
         tc_fence_after();
-        if (a.top) {
+        if (kTop) {
           // D1[co, pos] = W (K-major) * X (K-major): the top layer's z, never stored by the forward
           for (int ml = 0; ml < MTl; ++ml)
             for (int ks = 0; ks < KS16; ++ks) {
@@ -514,8 +520,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
         const bool ok = co < a.Cout;
         const float ca = ok ? s_ca[co] : 0.f, cb = ok ? s_cb[co] : 0.f, cc = ok ? s_cc[co] : 0.f;
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          if (EW == 8 && (ch & 1) != h) continue;
+        for (int c0 = 0; c0 < NCH; c0 += (EW == 8 ? 2 : 1)) {
+          const int ch = c0 + (EW == 8 ? h : 0);   // 8 warps: the quadrant's two warps alternate
           uint32_t r[32];
           cuda::ptx::tcgen05_ld_32x32b(r, d12 + lane_addr + (uint32_t)(ml * NT + ch * 32));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -544,18 +550,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
       bar_epi();
       if (tid == 0) mbar_arrive(bar(6 + s));
     };
-    if (a.top && (int)blockIdx.x < a.num_tiles) produce_dz(0, blockIdx.x);
+    if (kTop && (int)blockIdx.x < a.num_tiles) produce_dz(0, blockIdx.x);
     for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k, ++ntiles) {
       const int s = k & 1, n = k >> 1;
       const long long pos0 = (long long)tile * NT;
       const uint32_t d12 = tmem_base + (uint32_t)(s * w12);
       const int *s_idx = s_idx4 + (k & 3) * NT;
-      if (a.top && tile + grid < a.num_tiles) produce_dz(k + 1, tile + grid);
+      if (kTop && tile + grid < a.num_tiles) produce_dz(k + 1, tile + grid);
       mbar_wait(bar(8 + s), (uint32_t)(n & 1));
       tc_fence_after();
       if (a.do_dgrad) {
         int tile_b = 0, in_scene0 = 0;
-        if (a.mode == 0) {
+        if (kMode == 0) {
           tile_b = (int)(pos0 / per_scene);
           in_scene0 = (int)(pos0 - (long long)tile_b * per_scene);
         }
@@ -563,14 +569,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
         for (int m = 0; m < 3; ++m) {
           if (m >= MTp) continue;
 #pragma unroll
-          for (int cc = 0; cc < NCH; ++cc) {
-            if (EW == 8 && (cc & 1) != h) continue;
+          for (int c0 = 0; c0 < NCH; c0 += (EW == 8 ? 2 : 1)) {
+            const int cc = c0 + (EW == 8 ? h : 0);
             uint32_t r[32];
             cuda::ptx::tcgen05_ld_32x32b(r, d12 + lane_addr + (uint32_t)(m * NT + cc * 32));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const int kp = m * 128 + q * 32 + lane;   // packed K row owned by this thread
             const long long p0 = pos0 + cc * 32;
-            if (a.mode == 1) {
+            if (kMode == 1) {
               if (kp < a.Cin) {
                 const float sc = s_scale[kp], sh = s_shift[kp];
                 const float *zp = a.z_prev + (size_t)p0 * a.Cin + kp;
@@ -619,7 +625,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
             }
           }
         }
-        if (a.mode == 1) {
+        if (kMode == 1) {
 #pragma unroll
           for (int m = 0; m < 3; ++m) {
             d1[m] += (double)s1[m];
@@ -634,7 +640,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
       if (tid == 0) mbar_arrive(bar(10 + s));
     }
 
-    if (a.do_dgrad && a.mode == 1 && a.stats_prev != nullptr) {
+    if (a.do_dgrad && kMode == 1 && a.stats_prev != nullptr) {
 #pragma unroll
       for (int m = 0; m < 3; ++m) {
         const int kp = m * 128 + q * 32 + lane;
@@ -665,7 +671,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
           __syncwarp();
           const int kp = at * 32 + lane;   // this lane's packed input channel
           int kk = -1;
-          if (a.mode == 0) {
+          if (kMode == 0) {
             if (kp < C) kk = 3 + kp;
             else if (kp >= Cf8 && kp < Cf8 + 3) kk = kp - Cf8;
           } else if (kp < a.Cin) {
@@ -920,18 +926,27 @@ extern "C" int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *d, void *stream) {
   if (d->sm_limit > 0 && d->sm_limit < kNumSMs) sms = d->sm_limit;
   const int grid = a.num_tiles < sms ? a.num_tiles : sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define B2R_LAUNCH_BWD(NTV, EWV)                                                                \
+#define B2R_LAUNCH_BWD1(NTV, EWV, MV, TV)                                                       \
   do {                                                                                          \
-    B2R_CUDA(cudaFuncSetAttribute(sa_layer_bwd_kernel<NTV, EWV>,                                \
+    B2R_CUDA(cudaFuncSetAttribute(sa_layer_bwd_kernel<NTV, EWV, MV, TV>,                        \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));  \
-    sa_layer_bwd_kernel<NTV, EWV><<<grid, kBwdThreads, L.total, st>>>(a);                       \
+    sa_layer_bwd_kernel<NTV, EWV, MV, TV><<<grid, kBwdThreads, L.total, st>>>(a);               \
   } while (0)
-  // the pooled top layer runs 8 epilogue warps (they also build DZ from the recomputed z)
-  const bool wide_epi = a.top && NT >= 64;
-  if (NT == 128) { if (wide_epi) B2R_LAUNCH_BWD(128, 8); else B2R_LAUNCH_BWD(128, 4); }
-  else if (NT == 64) { if (wide_epi) B2R_LAUNCH_BWD(64, 8); else B2R_LAUNCH_BWD(64, 4); }
+  // the pooled top layer runs 8 epilogue warps (they also build DZ from the recomputed z) on
+  // tiles of >= 64 positions
+#define B2R_LAUNCH_BWD(NTV, EWTOP)                                                              \
+  do {                                                                                          \
+    if (a.top) {                                                                                \
+      if (a.mode == 0) B2R_LAUNCH_BWD1(NTV, EWTOP, 0, 1); else B2R_LAUNCH_BWD1(NTV, EWTOP, 1, 1); \
+    } else {                                                                                    \
+      if (a.mode == 0) B2R_LAUNCH_BWD1(NTV, 4, 0, 0); else B2R_LAUNCH_BWD1(NTV, 4, 1, 0);       \
+    }                                                                                           \
+  } while (0)
+  if (NT == 128) B2R_LAUNCH_BWD(128, 8);
+  else if (NT == 64) B2R_LAUNCH_BWD(64, 8);
   else B2R_LAUNCH_BWD(32, 4);
 #undef B2R_LAUNCH_BWD
+#undef B2R_LAUNCH_BWD1
   B2R_CHECK_LAUNCH();
   return B2R_OK;
 }
