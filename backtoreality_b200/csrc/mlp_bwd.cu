@@ -489,28 +489,49 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
     // Top layer: D1 (recomputed z) -> dz = a*dy_routed + b*z + c -> DZ tile (BF16) of tile k.
     // Called one tile AHEAD of the D2 epilogue (software pipelining): while these warps turn
     // D1(k+1) into DZ(k+1), the tensor core runs dgrad/wgrad(k), so neither waits for the other.
+    // Routed gradient (dysel, asel) of every centre touching tile k (<= NT/16 centres), parked in
+    // smem stage k & 1.  Fetched with cp.async TWO tiles ahead (issued at the end of
+    // produce_dz(k-2)): a plain load here was an exposed HBM round trip per tile (13 % of this
+    // kernel's stall samples, ncu).  Every thread reads back only entries it copied itself (the
+    // two warps of a quadrant copy the same entries), so cp.async.wait_group is all the
+    // synchronisation needed.  One (possibly empty) group is committed per call.
+    auto fetch_route = [&](int k, int tile) {
+      if (tile < a.num_tiles) {
+        const int s = k & 1;
+        const long long pos0 = (long long)tile * NT;
+        const long long centre0 = pos0 >> a.ns_shift;
+        const int base_s = (int)(pos0 & (a.NS - 1));
+        const int ncen = ((base_s + NT - 1) >> a.ns_shift) + 1;
+        float *my_dy = s_dy + (size_t)s * (NT / 16) * a.Cout_pad;
+        int *my_as = s_as + (size_t)s * (NT / 16) * a.Cout_pad;
+        for (int ml = 0; ml < MTl; ++ml) {
+          const int co = ml * 128 + q * 32 + lane;
+          if (co < a.Cout)
+            for (int c = 0; c < ncen; ++c) {
+              const size_t o = (size_t)(centre0 + c) * a.Cout + co;
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                               smem_u32(my_dy + c * a.Cout_pad + co)),
+                           "l"(a.dysel + o)
+                           : "memory");
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                               smem_u32(my_as + c * a.Cout_pad + co)),
+                           "l"(a.asel + o)
+                           : "memory");
+            }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     auto produce_dz = [&](int k, int tile) {
       const int s = k & 1, n = k >> 1;
       const long long pos0 = (long long)tile * NT;
       const uint32_t d12 = tmem_base + (uint32_t)(s * w12);
       uint8_t *sdz = base + L.dz_off[s];
       const int ns_mask = a.NS - 1;                         // NS is a power of two >= 16 (host)
-      const long long centre0 = pos0 >> a.ns_shift;
       const int base_s = (int)(pos0 & ns_mask);
-      // routed gradient of every centre touching this tile (<= NT/16), fetched BEFORE the wait
-      // on the recomputed z and parked in smem; every thread reads back only its own entries
-      const int ncen = ((base_s + NT - 1) >> a.ns_shift) + 1;
-      float *my_dy = s_dy + (size_t)s * (NT / 16) * a.Cout_pad;
-      int *my_as = s_as + (size_t)s * (NT / 16) * a.Cout_pad;
-      for (int ml = 0; ml < MTl; ++ml) {
-        const int co = ml * 128 + q * 32 + lane;
-        if (co < a.Cout)
-          for (int c = 0; c < ncen; ++c) {
-            const size_t o = (size_t)(centre0 + c) * a.Cout + co;
-            my_dy[c * a.Cout_pad + co] = __ldg(a.dysel + o);
-            my_as[c * a.Cout_pad + co] = __ldg(a.asel + o);
-          }
-      }
+      const float *my_dy = s_dy + (size_t)s * (NT / 16) * a.Cout_pad;
+      const int *my_as = s_as + (size_t)s * (NT / 16) * a.Cout_pad;
+      asm volatile("cp.async.wait_group 1;" ::: "memory");   // tile k's routes have landed
       mbar_wait(bar(4 + s), (uint32_t)(n & 1));
       tc_fence_after();
 #pragma unroll
@@ -549,8 +570,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
       fence_async_smem();
       bar_epi();
       if (tid == 0) mbar_arrive(bar(6 + s));
+      fetch_route(k + 2, tile + 2 * grid);   // stage s is free again: this thread's reads are done
     };
-    if (kTop && (int)blockIdx.x < a.num_tiles) produce_dz(0, blockIdx.x);
+    if (kTop) {
+      fetch_route(0, blockIdx.x);
+      fetch_route(1, blockIdx.x + grid);
+      if ((int)blockIdx.x < a.num_tiles) produce_dz(0, blockIdx.x);
+    }
     for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k, ++ntiles) {
       const int s = k & 1, n = k >> 1;
       const long long pos0 = (long long)tile * NT;
