@@ -91,6 +91,9 @@ class Pointnet2Backbone(nn.Module):
         if not end_points:
             end_points = {}
         xyz, features = self._break_up_pc(pointcloud)
+        if xyz.is_cuda and fused_sa.ENABLED and not end_points.get('_prepacked'):
+            # weight images of the four SA blocks, packed on a side stream beside the first kernels
+            fused_sa.prepack([m.mlp_module for m in (self.sa1, self.sa2, self.sa3, self.sa4)])
         geo = [None] * 4
         if geometry is not None:
             geo = geometry
@@ -124,4 +127,6 @@ class Pointnet2Backbone(nn.Module):
         end_points['fp2_xyz'] = end_points['sa2_xyz']
         num_seed = end_points['fp2_xyz'].shape[1]
         end_points['fp2_inds'] = end_points['sa1_inds'][:, 0:num_seed]
+        if not end_points.pop('_prepacked', False):
+            fused_sa.prepack_join()
         return end_points

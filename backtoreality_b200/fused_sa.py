@@ -51,6 +51,72 @@ def pack_weight(weight, gather):
     return image
 
 
+# ---- weight images packed ahead of time, off the critical path -------------------------------
+# Every fused layer needs its weight as a swizzled operand image (TF32 forward, BF16 backward):
+# 29 tiny launches per VoteNet step, each sitting between two dependent kernels on the main
+# stream.  `prepack` issues them all on a side stream at the start of the step (they depend on
+# nothing but the weights); the layers then `_take` their image instead of packing inline.
+_PREPACKED = {}      # (id(weight), kind) -> (image, event, weight._version, weight)
+_PACK_STREAMS = {}   # device -> side stream
+_PACK_EVENTS = []    # events recorded by the last prepack (joined by prepack_join)
+
+
+def prepack(mlp_modules, backward=None):
+    """Pack the operand images of every conv of the given SharedMLP modules on a side stream.
+    Entries are consumed once (a second forward through the same module in the same step packs
+    inline again) and dropped by the next call; a weight modified in between is detected by its
+    version counter and re-packed."""
+    mlp_modules = [m for m in mlp_modules if m is not None and len(m) > 0]
+    _PREPACKED.clear()
+    del _PACK_EVENTS[:]
+    if not mlp_modules or not mlp_modules[0][0].conv.weight.is_cuda:
+        return
+    dev = mlp_modules[0][0].conv.weight.device
+    if backward is None:
+        backward = torch.is_grad_enabled()
+    main = torch.cuda.current_stream(dev)
+    side = _PACK_STREAMS.get(dev)
+    if side is None:
+        side = _PACK_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side), torch.no_grad():
+        for kind in (("tf32", "bf16") if backward else ("tf32",)):
+            for mlp in mlp_modules:
+                entries = []
+                for i, blk in enumerate(mlp):
+                    w = blk.conv.weight
+                    if kind == "bf16" and not w.requires_grad:
+                        continue
+                    image = (pack_weight if kind == "tf32" else pack_weight_bf16)(w, gather=(i == 0))
+                    entries.append(((id(w), kind), image, w._version, w))
+                ev = torch.cuda.Event()
+                ev.record(side)
+                _PACK_EVENTS.append(ev)
+                for key, image, version, w in entries:
+                    _PREPACKED[key] = (image, ev, version, w)
+
+
+def prepack_join():
+    """Make the current stream wait for everything the last `prepack` issued (also needed so that
+    a CUDA-graph capture never ends with the packing stream un-joined)."""
+    for ev in _PACK_EVENTS:
+        torch.cuda.current_stream().wait_event(ev)
+    del _PACK_EVENTS[:]
+
+
+def _take(weight, kind):
+    ent = _PREPACKED.pop((id(weight), kind), None)
+    # the entry holds the Parameter itself: same object (not a recycled id / address) and
+    # unmodified since it was packed
+    if ent is None or ent[3] is not weight or ent[2] != weight._version:
+        return None
+    image, ev = ent[0], ent[1]
+    main = torch.cuda.current_stream(weight.device)
+    main.wait_event(ev)
+    image.record_stream(main)
+    return image
+
+
 def supported(mlp_module, xyz, features, idx, pooling="max"):
     """True when the fused kernels cover this block, forward AND backward (otherwise callers use
     the unfused path).  The shape rules live in the library: b2r_sa_layer_fwd_supported /
@@ -136,7 +202,9 @@ def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
         conv, bn = blk.conv, blk.bn.bn
         Cin, Cout = conv.in_channels, conv.out_channels
         last = i == L - 1
-        image = pack_weight(conv.weight, gather=(i == 0))
+        image = _take(conv.weight, "tf32")
+        if image is None:
+            image = pack_weight(conv.weight, gather=(i == 0))
         images.append(image)
         stats = None
         if training:
@@ -213,7 +281,7 @@ def pack_weight_bf16(weight, gather):
 
 
 def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, weights, gammas,
-                    training, saved, need_feat, need_xyz, need_new_xyz, sm_limit=0):
+                    training, saved, need_feat, need_xyz, need_new_xyz, sm_limit=0, versioned=None):
     """Backward of sa_mlp_forward through csrc/mlp_bwd.cu.
 
     g_out_cm (B,Cl,NP) gradient of the pooled output.  Returns
@@ -293,7 +361,11 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
             gr_prev = torch.empty((M, Cin), **f32)
             stats_prev = stats_all[s_off[l - 1]:s_off[l]]
             b.gr_prev, b.stats_prev = _ptr(gr_prev), _ptr(stats_prev)
-        image = pack_weight_bf16(weights[l], gather=(l == 0)) if (need_dgrad or l == top) else None
+        image = None
+        if need_dgrad or l == top:
+            image = _take(versioned[l], "bf16") if versioned is not None else None
+            if image is None:
+                image = pack_weight_bf16(weights[l], gather=(l == 0))
         b.w_image_bf16 = _ptr(image)
         with _ext._timed("sa_layer_bwd", _bwd_bytes(B, N, NP, NS, Cin, Cout, l == 0, l == top,
                                                     need_dgrad)):
@@ -343,7 +415,7 @@ class _FusedSABlock(torch.autograd.Function):
         g_feat_t, g_xyz, g_new_xyz, dWs, dgs, dbs = sa_mlp_backward(
             g_out.contiguous(), xyz, new_xyz, feat_t, idx, radius, normalize_xyz, weights, gammas,
             training, save, need_feat=nig[2], need_xyz=nig[0], need_new_xyz=nig[1],
-            sm_limit=ctx.bwd_sm_limit)
+            sm_limit=ctx.bwd_sm_limit, versioned=[params[3 * i] for i in range(L)])
         g_features = g_feat_t.transpose(1, 2).contiguous() if g_feat_t is not None else None
         out = [g_xyz, g_new_xyz, g_features, None, None, None, None, None, None]
         for i in range(L):

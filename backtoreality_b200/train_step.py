@@ -171,3 +171,48 @@ class PipelinedTrainStep:
         self.next.copy_(next_batch, non_blocking=non_blocking)
         self.graph.replay()
         return self.static_loss
+
+
+class HostPrefetcher:
+    """Input staging: batches travel pinned host memory -> device on a COPY
+    stream, one step ahead of their use, so the upload of the next batch overlaps the running
+    step instead of preceding it on the compute stream (the reference uploads synchronously at
+    the top of every iteration, train_Votenet_FSB.py:217-218).
+
+        slot = pre.upload(host_batch)        # asynchronous, returns immediately
+        ...
+        batch = pre.get(slot)                # compute stream waits for that upload only
+        loss = step(batch)
+        pre.release(slot)                    # the slot may be overwritten once `step` has read it
+    """
+
+    def __init__(self, example, device, depth=2):
+        self.stream = torch.cuda.Stream(device=device)
+        self.bufs = [torch.empty(example.shape, dtype=example.dtype, device=device)
+                     for _ in range(depth)]
+        self.ready = [None] * depth
+        self.free = [None] * depth
+        self.i = 0
+        self.bytes_uploaded = 0
+
+    def upload(self, host_batch):
+        slot = self.i
+        self.i = (self.i + 1) % len(self.bufs)
+        if self.free[slot] is not None:
+            self.stream.wait_event(self.free[slot])
+        with torch.cuda.stream(self.stream):
+            self.bufs[slot].copy_(host_batch, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.ready[slot] = ev
+        self.bytes_uploaded += host_batch.numel() * host_batch.element_size()
+        return slot
+
+    def get(self, slot):
+        torch.cuda.current_stream().wait_event(self.ready[slot])
+        return self.bufs[slot]
+
+    def release(self, slot):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.free[slot] = ev

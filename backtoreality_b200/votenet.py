@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import pointnet2_utils
+from . import fused_sa, pointnet2_utils
 from .backbone_module import Pointnet2Backbone
 from .pointnet2_modules import PointnetSAModuleVotes
 
@@ -150,8 +150,15 @@ class VoteNet(nn.Module):
                                    num_proposal, sampling)
 
     def forward(self, inputs):
+        pc = inputs['point_clouds']
+        prepacked = pc.is_cuda and fused_sa.ENABLED
+        if prepacked:
+            # operand images of all five fused blocks, packed on a side stream (fused_sa.prepack)
+            bb = self.backbone_net
+            fused_sa.prepack([m.mlp_module for m in (bb.sa1, bb.sa2, bb.sa3, bb.sa4,
+                                                     self.pnet.vote_aggregation)])
         # 'geometry' (optional, not in the reference): sa1..sa4 indices computed ahead of time
-        end_points = self.backbone_net(inputs['point_clouds'], {},
+        end_points = self.backbone_net(pc, {'_prepacked': True} if prepacked else {},
                                        geometry=inputs.get('geometry'))
         xyz = end_points['fp2_xyz']
         features = end_points['fp2_features']
@@ -163,4 +170,7 @@ class VoteNet(nn.Module):
         features = features.div(features_norm.unsqueeze(1))
         end_points['vote_xyz'] = xyz
         end_points['vote_features'] = features
-        return self.pnet(xyz, features, end_points)
+        end_points = self.pnet(xyz, features, end_points)
+        if prepacked:
+            fused_sa.prepack_join()
+        return end_points

@@ -80,6 +80,7 @@ def workload_config(a, world):
         "loss": "synthetic scalar: mean(proposal_scores^2) + mean((vote_xyz-seed_xyz)^2)",
         "parallelism": "dp%d (scenes sharded, flat-gradient NCCL all-reduce)" % world,
         "l2": "256 MB buffer written between steps (flush) + 4 rotating input batches",
+        "e2e_input": "pinned host -> device on a copy stream, one step ahead (train_step.HostPrefetcher)",
         "launch": ("whole step (fwd+bwd+Adam) captured in one CUDA graph, replayed per batch" if world == 1
                    else "fwd+bwd replayed from one CUDA graph; NCCL all-reduce + fused Adam eager"),
         "pipeline": ("none: FPS / ball query of a batch run inside its own step" if a.no_pipeline or a.no_graph
@@ -413,11 +414,22 @@ def run_b2r(a):
     launches = launches_per_step * a.steps
     clocks = sampler.window(t0, t1) if sampler else None
 
-    # (2) end to end: pinned host input -> device each step, loss read back each step
+    # (2) end to end: pinned host input -> device each step, loss read back each step.  The
+    # upload runs on a copy stream one step ahead of its use (train_step.HostPrefetcher): every
+    # timed step uploads ONE batch from pinned host memory, trains on one batch and reads one loss
+    from backtoreality_b200.train_step import HostPrefetcher
+    pre = HostPrefetcher(host[0], dev) if graphed is not None else None
+    state = {"slot": None}
+
     def e2e_step(i):
-        if graphed is not None:
-            # H2D straight into the static input (pipelined: the NEXT batch's buffer)
-            return float(run_step(host[(i + nxt) % pool_n]).item())
+        if pre is not None:
+            if state["slot"] is None:
+                state["slot"] = pre.upload(host[(i + nxt) % pool_n])
+            nslot = pre.upload(host[(i + nxt + 1) % pool_n])      # overlaps this step
+            loss = run_step(pre.get(state["slot"]))               # device copy into the static input
+            pre.release(state["slot"])
+            state["slot"] = nslot
+            return float(loss.item())
         pc = host[i % pool_n].to(dev, non_blocking=True)
         return float(step(pc).item())
 
@@ -425,9 +437,9 @@ def run_b2r(a):
         graphed.prime(resident[0])
     for i in range(2):
         e2e_step(i)
-    if pipelined:
-        graphed.prime(resident[0])
-    ms_e2e, _, t1e = timed_loop(e2e_step)
+    up0 = pre.bytes_uploaded if pre is not None else 0
+    ms_e2e, _, t1e = timed_loop(lambda i: e2e_step(i + 2))
+    h2d_per_step = ((pre.bytes_uploaded - up0) // a.steps) if pre is not None else int(host[0].numel() * 4)
     if sampler:
         # clocks over both timed regions (device-resident and end-to-end loops, back to back)
         clocks = sampler.window(t0, t1e)
@@ -446,7 +458,7 @@ def run_b2r(a):
         "vs_baseline": None, "dtype": "tf32 fwd / bf16 bwd operands, f32 accumulate", "data": "synthetic",
         "config": workload_config(a, world),
         "e2e": {"value": scenes_total / (ms_e2e * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": int(host[0].numel() * 4), "d2h_bytes_per_step": 4,
+                "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": launches,
         "clocks": clocks,

@@ -367,3 +367,73 @@ def test_geometry_stream_matches_serial_path(cuda):
         assert rel_l2(ea[k].cpu().numpy(), eb[k].cpu().numpy()) < 1e-5, k
     for n in ga:
         assert rel_l2(ga[n].cpu().numpy(), gb[n].cpu().numpy()) < 3e-2, n
+
+
+def test_host_prefetcher_delivers_batches_in_order(cuda):
+    """train_step.HostPrefetcher: uploads run on a copy stream one step ahead; what the compute
+    stream reads from a slot is exactly the batch uploaded into it, also when the slot is reused
+    while earlier consumers are still queued."""
+    from backtoreality_b200.train_step import HostPrefetcher
+    host = [torch.full((4, 50000, 4), float(i)).pin_memory() for i in range(6)]
+    pre = HostPrefetcher(host[0], cuda)
+    sums = []
+    slot = pre.upload(host[0])
+    for i in range(6):
+        nslot = pre.upload(host[(i + 1) % 6])
+        b = pre.get(slot)
+        # slow consumer; min == max == i proves the slot holds ONE whole batch
+        sums.append(torch.stack([b.min(), b.max()]) + 0 * torch.randn(1 << 20, device=cuda).sum())
+        pre.release(slot)
+        slot = nslot
+    torch.cuda.synchronize()
+    assert [s.tolist() for s in sums] == [[float(i), float(i)] for i in range(6)]
+    assert pre.bytes_uploaded == 7 * host[0].numel() * 4
+
+
+def test_prepacked_weight_images_match_inline_packing(cuda):
+    """fused_sa.prepack (operand images packed on a side stream at the start of the step) must
+    hand the layers the same images inline packing produces, be consumed once, and notice a
+    weight that changed after packing."""
+    from backtoreality_b200 import fused_sa
+    from backtoreality_b200.pointnet2_modules import PointnetSAModuleVotes
+    torch.manual_seed(3)
+    sa = PointnetSAModuleVotes(npoint=128, radius=0.4, nsample=32, mlp=[16, 32, 32, 64],
+                               use_xyz=True, normalize_xyz=True).to(cuda).train()
+    fused_sa.prepack([sa.mlp_module])
+    fused_sa.prepack_join()
+    torch.cuda.synchronize()
+    assert len(fused_sa._PREPACKED) == 6
+    for i, blk in enumerate(sa.mlp_module):
+        w = blk.conv.weight
+        a = fused_sa._take(w, "tf32")
+        b = fused_sa._take(w, "bf16")
+        torch.cuda.synchronize()
+        assert torch.equal(a, fused_sa.pack_weight(w, gather=(i == 0)))
+        assert torch.equal(b.view(torch.int16), fused_sa.pack_weight_bf16(w, gather=(i == 0)).view(torch.int16))
+        assert fused_sa._take(w, "tf32") is None          # consumed
+    fused_sa.prepack([sa.mlp_module])
+    with torch.no_grad():
+        sa.mlp_module[0].conv.weight.mul_(2.0)            # stale image must not be used
+    assert fused_sa._take(sa.mlp_module[0].conv.weight, "tf32") is None
+    assert fused_sa._take(sa.mlp_module[1].conv.weight, "tf32") is not None
+    fused_sa.prepack_join()
+    # end to end: the block computes the same output with and without pre-packed images
+    xyz = torch.rand(2, 1000, 3, device=cuda)
+    feats = torch.randn(2, 16, 1000, device=cuda)
+    fused_sa.prepack([])
+    _, y0, _ = sa(xyz, feats)
+    fused_sa.prepack([sa.mlp_module])
+    feats.requires_grad_(True)
+    _, y1, _ = sa(xyz, feats)
+    assert sorted(k[1] for k in fused_sa._PREPACKED) == ["bf16"] * 3   # forward took the TF32 images
+    y1.square().mean().backward()
+    assert len(fused_sa._PREPACKED) == 0                               # backward took the BF16 ones
+    fused_sa.prepack_join()
+    assert torch.equal(y0, y1)
+    # a different module must never be served this module's images (entries are keyed by the
+    # Parameter object, not by its address)
+    fused_sa.prepack([sa.mlp_module])
+    other = PointnetSAModuleVotes(npoint=128, radius=0.4, nsample=32, mlp=[16, 32, 32, 64],
+                                  use_xyz=True, normalize_xyz=True).to(cuda).train()
+    assert fused_sa._take(other.mlp_module[0].conv.weight, "tf32") is None
+    fused_sa.prepack([])
