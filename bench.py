@@ -64,6 +64,9 @@ def parse():
                     help="geometry pre-pass of a batch inside its own step (not one step ahead)")
     ap.add_argument("--fps-cluster", type=int, default=4,
                     help="pipelined step: CTAs per scene of the next batch's FPS")
+    ap.add_argument("--trace", default="",
+                    help="after timing, trace 3 steps with torch.profiler (CUPTI) and write a per-kernel "
+                         "summary + stream-occupancy analysis of one step to this file")
     ap.add_argument("--sm-caps", default="",
                     help="pipelined step: persistent-grid caps 'fwd:bwd' of sa1,sa2,sa3,sa4,vote-agg "
                          "(comma separated, 0 = every SM); default: see PipelinedTrainStep")
@@ -249,6 +252,52 @@ class ClockSampler:
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
+
+
+def trace_steps(path, fn, steps=3):
+    """Kernel timeline of `steps` steps from CUPTI (torch.profiler): per-kernel totals and, for
+    the LAST step, how much of the step some kernel was running / only side-stream kernels were
+    running / nothing was running.  Evidence for where a graph-replayed step spends its time."""
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(steps):
+            fn(i)
+        torch.cuda.synchronize()
+    ev = [e for e in prof.events() if e.device_type is not None and "cuda" in str(e.device_type).lower()
+          and e.time_range is not None]
+    ev.sort(key=lambda e: e.time_range.start)
+    if not ev:
+        open(path, "w").write("no CUDA activity records\n")
+        return
+    t_begin, t_end = ev[0].time_range.start, max(e.time_range.end for e in ev)
+    span = (t_end - t_begin) / steps
+    last = [e for e in ev if e.time_range.start >= t_end - span]
+    agg = {}
+    for e in last:
+        k = e.name[:90]
+        c = agg.setdefault(k, [0, 0.0])
+        c[0] += 1
+        c[1] += e.time_range.end - e.time_range.start
+    # union of busy intervals
+    busy, cur_s, cur_e = 0.0, None, None
+    for e in last:
+        s_, e_ = e.time_range.start, e.time_range.end
+        if cur_e is None or s_ > cur_e:
+            if cur_e is not None:
+                busy += cur_e - cur_s
+            cur_s, cur_e = s_, e_
+        else:
+            cur_e = max(cur_e, e_)
+    busy += (cur_e - cur_s) if cur_e is not None else 0.0
+    with open(path, "w") as f:
+        f.write("CUPTI trace of %d steps; last step analysed: span %.1f us, %d kernels/memcpys, "
+                "some kernel running %.1f us (%.1f%%), nothing running %.1f us\n"
+                % (steps, span, len(last), busy, 100 * busy / span, span - busy))
+        tot = sum(v[1] for v in agg.values())
+        f.write("sum of kernel durations %.1f us (overlap across streams counted twice)\n" % tot)
+        for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
+            f.write("%4d %9.1f us %5.1f%%  %s\n" % (n, us, 100 * us / tot, k))
 
 
 # ------------------------------------------------------------------------- GPU arm ---------
@@ -445,6 +494,9 @@ def run_b2r(a):
         clocks = sampler.window(t0, t1e)
         sampler.stop()
 
+    if a.trace and rank == 0:
+        trace_steps(a.trace, lambda i: run_step(resident[(i + nxt) % pool_n]))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -488,12 +540,13 @@ def run_b2r(a):
         ach = tot_b / (tot_ms * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[
-                kern]["dram_bytes_per_launch"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            traffic = (tj.get(name) or tj[kern])["dram_bytes_per_launch"]
         except Exception:
             pass
-        out["roofline"] = {"kernel": "%s (fused tcgen05 SA layer, %d launches/step; tensor "
-                                     "work is <10%% of its time, it is HBM-bound)" % (kern, n // k_div),
+        out["roofline"] = {"kernel": "%s: all %d launches/step of b2r_%s (fused tcgen05 SA layers; SA1's thin "
+                                     "first layer runs mlp_thin.cu's streaming kernel; tensor work is <10%% "
+                                     "of the time, the class is HBM-bound)" % (kern, n // k_div, name),
                            "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                            "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                            "algorithmic_bytes_per_launch": tot_b / n,

@@ -1,5 +1,4 @@
-"""Summarise an ncu report (raw page CSV on stdin or a .ncu-rep path) into a small text table and
-profiles/roofline_traffic.json:
+"""Summarise ncu reports (.ncu-rep paths) into a small text table:
     python scripts/ncu_summary.py gpurun_out/prof_sa1.ncu-rep [more.ncu-rep ...] > profiles/r01/ncu_sa_layers.txt
 """
 import csv
@@ -52,7 +51,4 @@ for rep in sys.argv[1:]:
             g("lts__t_sector_hit_rate.pct")))
         key = re.sub(r"<.*", "", name)
         traffic.setdefault(key, []).append(rd + wr)
-out = {k: {"dram_bytes_per_launch": sum(v) / len(v), "launches": len(v),
-           "source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches (%s)" % ", ".join(os.path.basename(a) for a in sys.argv[1:])}
-       for k, v in traffic.items()}
-json.dump(out, open(os.path.join(ROOT, "profiles", "roofline_traffic.json"), "w"), indent=1)
+# profiles/roofline_traffic.json is written by scripts/ncu_layers_csv.py (all launches of one step)
