@@ -79,6 +79,17 @@ class Pointnet2Backbone(nn.Module):
                                "sm_limit": (fused_sa.NUM_SMS - GEOMETRY_SMS) if sm_limit is None
                                else sm_limit})
                 cur = new_xyz
+            # the FP modules' 3-NN indices and inverse-distance weights are geometry too:
+            # fp1 interpolates sa4 -> sa3, fp2 sa3 -> sa2 (stored with the last level, whose
+            # event covers them)
+            sa2x, sa3x, sa4x = levels[1]["new_xyz"], levels[2]["new_xyz"], levels[3]["new_xyz"]
+            i1, w1 = PointnetFPModule.interpolation_weights(sa3x, sa4x)
+            i2, w2 = PointnetFPModule.interpolation_weights(sa2x, sa3x)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            for t in (i1, w1, i2, w2):
+                t.record_stream(main)
+            levels[3].update(fp1_idx=i1, fp1_weight=w1, fp2_idx=i2, fp2_weight=w2, fp_event=ev)
         if sm_limit is None:
             levels[-1]["sm_limit"] = 0   # nothing runs beside sa4's MLP
         return levels
@@ -119,10 +130,16 @@ class Pointnet2Backbone(nn.Module):
         end_points['sa4_xyz'] = xyz
         end_points['sa4_features'] = features
 
+        interp1 = interp2 = None
+        if geo[3] is not None and "fp1_idx" in geo[3]:
+            if geo[3].get("fp_event") is not None:
+                torch.cuda.current_stream().wait_event(geo[3]["fp_event"])
+            interp1 = (geo[3]["fp1_idx"], geo[3]["fp1_weight"])
+            interp2 = (geo[3]["fp2_idx"], geo[3]["fp2_weight"])
         features = self.fp1(end_points['sa3_xyz'], end_points['sa4_xyz'],
-                            end_points['sa3_features'], end_points['sa4_features'])
+                            end_points['sa3_features'], end_points['sa4_features'], interp=interp1)
         features = self.fp2(end_points['sa2_xyz'], end_points['sa3_xyz'],
-                            end_points['sa2_features'], features)
+                            end_points['sa2_features'], features, interp=interp2)
         end_points['fp2_features'] = features
         end_points['fp2_xyz'] = end_points['sa2_xyz']
         num_seed = end_points['fp2_xyz'].shape[1]

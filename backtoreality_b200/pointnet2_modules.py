@@ -141,12 +141,19 @@ class PointnetFPModule(nn.Module):
         super().__init__()
         self.mlp = pt_utils.SharedMLP(mlp, bn=bn)
 
-    def forward(self, unknown, known, unknow_feats, known_feats):
+    @staticmethod
+    def interpolation_weights(unknown, known):
+        """three_nn + the reference's inverse-distance weights (:486-490): (idx, weight), both
+        (B,n,3).  They depend on coordinates only, so a geometry pre-pass may compute them ahead
+        of time and hand them to `forward(..., interp=)`."""
+        dist, idx = pointnet2_utils.three_nn(unknown, known)
+        dist_recip = 1.0 / (dist + 1e-8)
+        norm = torch.sum(dist_recip, dim=2, keepdim=True)
+        return idx, dist_recip / norm
+
+    def forward(self, unknown, known, unknow_feats, known_feats, interp=None):
         if known is not None:
-            dist, idx = pointnet2_utils.three_nn(unknown, known)
-            dist_recip = 1.0 / (dist + 1e-8)
-            norm = torch.sum(dist_recip, dim=2, keepdim=True)
-            weight = dist_recip / norm
+            idx, weight = interp if interp is not None else self.interpolation_weights(unknown, known)
             interpolated_feats = pointnet2_utils.three_interpolate(known_feats, idx, weight)
         else:
             interpolated_feats = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))

@@ -76,7 +76,12 @@ class PipelinedTrainStep:
     the constructor / `prime`).  BatchNorm momentum / learning-rate caveats as CapturedTrainStep.
     """
 
-    GEO_KEYS = ("inds", "new_xyz", "idx")
+    GEO_KEYS = ("inds", "new_xyz", "idx")                       # every level
+    FP_KEYS = ("fp1_idx", "fp1_weight", "fp2_idx", "fp2_weight")   # last level: FP interpolation
+
+    @classmethod
+    def _keys(cls, level):
+        return cls.GEO_KEYS + tuple(k for k in cls.FP_KEYS if k in level)
 
     def __init__(self, backbone, step_fn, first_batch, warmup=3, fps_cluster=4, sm_caps=None,
                  after_warmup_step=None):
@@ -109,7 +114,8 @@ class PipelinedTrainStep:
         return pc[..., 0:3].contiguous()
 
     def _levels(self, tensors):
-        return [dict(t, event=None, sm_limit=cap) for t, cap in zip(tensors, self.sm_caps)]
+        return [dict(t, event=None, fp_event=None, sm_limit=cap)
+                for t, cap in zip(tensors, self.sm_caps)]
 
     def prime(self, batch):
         """(Re)start the pipeline: `batch` becomes the current batch, its geometry is computed
@@ -118,12 +124,12 @@ class PipelinedTrainStep:
         xyz = self._xyz(self.cur)     # stays referenced until the side stream has been joined
         levels = self.backbone.geometry_prepass(xyz, side=self.side)
         torch.cuda.current_stream().wait_stream(self.side)
-        fresh = [{k: lv[k] for k in self.GEO_KEYS} for lv in levels]
+        fresh = [{k: lv[k] for k in self._keys(lv)} for lv in levels]
         if self.geo_cur is None:
             self.geo_cur = [{k: v.clone() for k, v in lv.items()} for lv in fresh]
         else:
             for dst, src in zip(self.geo_cur, fresh):
-                for k in self.GEO_KEYS:
+                for k in dst:
                     dst[k].copy_(src[k])
 
     def _pipelined(self):
@@ -139,7 +145,7 @@ class PipelinedTrainStep:
         main.wait_stream(self.side)
         del xyz_next
         for dst, src in zip(self.geo_cur, nxt):
-            for k in self.GEO_KEYS:
+            for k in dst:
                 dst[k].copy_(src[k])
         self.cur.copy_(self.next)
         return loss

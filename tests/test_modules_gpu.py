@@ -327,8 +327,9 @@ def test_pipelined_train_step_matches_sequential(cuda):
     fresh = net_p.backbone_net.geometry_prepass(batches[0][..., :3].contiguous())
     torch.cuda.synchronize()
     assert torch.equal(pipe.cur, batches[0])
+    assert set(pipe.geo_cur[3]) == set(PipelinedTrainStep.GEO_KEYS + PipelinedTrainStep.FP_KEYS)
     for lv_p, lv_f in zip(pipe.geo_cur, fresh):
-        for k in PipelinedTrainStep.GEO_KEYS:
+        for k in lv_p:
             assert torch.equal(lv_p[k], lv_f[k]), k
     for (n1, p1), (n2, p2) in zip(net_e.named_parameters(), net_p.named_parameters()):
         assert torch.equal(p1, p2), n1        # lr = 0
