@@ -438,3 +438,40 @@ def test_prepacked_weight_images_match_inline_packing(cuda):
                                   use_xyz=True, normalize_xyz=True).to(cuda).train()
     assert fused_sa._take(other.mlp_module[0].conv.weight, "tf32") is None
     fused_sa.prepack([])
+
+
+def test_two_forwards_one_backward_is_the_sum_of_two_steps(cuda):
+    """The BR training step (BASELINE.json configs[2], reference train_Votenet_BR.py:277-289) runs
+    TWO forwards (source and target batch) through the same network and ONE backward of the summed
+    loss.  Gradients are linear in the loss, and train-mode BatchNorm makes each forward
+    independent of the other, so grad(L_a + L_b) must equal grad(L_a) + grad(L_b) of two separate
+    steps (within the atomics' run-to-run noise); every BatchNorm sees two batches."""
+    from backtoreality_b200.votenet import VoteNet
+    torch.manual_seed(9)
+    net = VoteNet(4, 1, 4, np.ones((4, 3), np.float32), input_feature_dim=1, num_proposal=64,
+                  vote_factor=1, sampling="vote_fps").to(cuda).train()
+    pa, pb = (torch.from_numpy(scenes.batch(500 + 2 * i, 2, 9000, C=1, kind="room", dup=0.2)).to(cuda)
+              for i in range(2))
+
+    def loss_of(pc):
+        ep = net({"point_clouds": pc})
+        return (ep["proposal_scores_raw"] ** 2).mean() + ((ep["vote_xyz"] - ep["seed_xyz"]) ** 2).mean()
+
+    def grads():
+        g = {n: p.grad.clone() for n, p in net.named_parameters()}
+        for p in net.parameters():
+            p.grad = None
+        return g
+
+    bn = net.backbone_net.sa2.mlp_module.layer1.bn.bn
+    n0 = int(bn.num_batches_tracked)
+    (loss_of(pa) + loss_of(pb)).backward()          # the BR pattern
+    assert int(bn.num_batches_tracked) == n0 + 2
+    both = grads()
+    loss_of(pa).backward()
+    ga = grads()
+    loss_of(pb).backward()
+    gb = grads()
+    for n in both:
+        want = (ga[n] + gb[n]).cpu().numpy()
+        assert rel_l2(both[n].cpu().numpy(), want) < 3e-2, n
