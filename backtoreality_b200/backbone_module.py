@@ -112,19 +112,33 @@ class Pointnet2Backbone(nn.Module):
                 and all(m.fusable(xyz) for m in (self.sa1, self.sa2, self.sa3, self.sa4))):
             geo = self.geometry_prepass(xyz)
 
+        # consecutive fused blocks hand their activations (and, in backward, their gradients) to
+        # each other point-major: no layout-conversion kernels between sa1 -> sa2 -> sa3 -> sa4
+        chain = all(isinstance(g, dict) for g in geo)
+        if chain:
+            geo = [dict(g) for g in geo]            # never mutate the caller's dicts
+            for g in geo[:3]:
+                g["want_pm"] = True
+
         xyz, features, fps_inds = self.sa1(xyz, features, geometry=geo[0])
         end_points['sa1_inds'] = fps_inds
         end_points['sa1_xyz'] = xyz
         end_points['sa1_features'] = features
+        if chain:
+            geo[1]["features_pm"] = geo[0].pop("out_pm", None)
 
         xyz, features, fps_inds = self.sa2(xyz, features, geometry=geo[1])
         end_points['sa2_inds'] = fps_inds
         end_points['sa2_xyz'] = xyz
         end_points['sa2_features'] = features
+        if chain:
+            geo[2]["features_pm"] = geo[1].pop("out_pm", None)
 
         xyz, features, fps_inds = self.sa3(xyz, features, geometry=geo[2])
         end_points['sa3_xyz'] = xyz
         end_points['sa3_features'] = features
+        if chain:
+            geo[3]["features_pm"] = geo[2].pop("out_pm", None)
 
         xyz, features, fps_inds = self.sa4(xyz, features, geometry=geo[3])
         end_points['sa4_xyz'] = xyz

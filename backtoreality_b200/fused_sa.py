@@ -281,16 +281,19 @@ def pack_weight_bf16(weight, gather):
 
 
 def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, weights, gammas,
-                    training, saved, need_feat, need_xyz, need_new_xyz, sm_limit=0, versioned=None):
+                    training, saved, need_feat, need_xyz, need_new_xyz, sm_limit=0, versioned=None,
+                    g_out_pm=None):
     """Backward of sa_mlp_forward through csrc/mlp_bwd.cu.
 
-    g_out_cm (B,Cl,NP) gradient of the pooled output.  Returns
+    g_out_cm (B,Cl,NP) and/or g_out_pm (B,NP,Cl): gradient of the pooled output in either
+    layout (summed when both are given; one of them may be None).  Returns
     (g_feat_t (B,N,C) | None, g_xyz (B,N,3) | None, g_new_xyz (B,NP,3) | None,
      [dW_i (Cout,Cin)], [dgamma_i], [dbeta_i]).
     """
     lib = _lib.lib()
     st = _ext._stream()
     dev = xyz.device
+    assert g_out_cm is not None or g_out_pm is not None
     B, N = xyz.shape[0], xyz.shape[1]
     NP, NS = idx.shape[1], idx.shape[2]
     M = B * NP * NS
@@ -314,7 +317,7 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
     stats = stats_all[s_off[top]:s_off[top + 1]]
     dysel = torch.empty((B * NP, Ct), **f32)
     asel = torch.empty((B * NP, Ct), dtype=torch.int32, device=dev)
-    _lib.check(lib.b2r_pool_bwd_prep(_ptr(g_out_cm), None, _ptr(saved["zmax"]), _ptr(saved["zmin"]),
+    _lib.check(lib.b2r_pool_bwd_prep(_ptr(g_out_cm), _ptr(g_out_pm), _ptr(saved["zmax"]), _ptr(saved["zmin"]),
                                      _ptr(saved["amax"]), _ptr(saved["amin"]), _ptr(scale),
                                      _ptr(shift), B, NP, Ct, _ptr(dysel), _ptr(asel), _ptr(stats),
                                      st), "pool_bwd_prep")
@@ -385,55 +388,83 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
 
 
 class _FusedSABlock(torch.autograd.Function):
-    """autograd node of the fused block: QueryAndGroup tail + SharedMLP + max-pool in, one
-    (B,C,npoint) tensor out.  Parameters are passed flat as (W0, gamma0, beta0, W1, ...)."""
+    """autograd node of the fused block: QueryAndGroup tail + SharedMLP + max-pool in; out come the
+    (B,C,npoint) tensor of the reference and, on request, the same values POINT-major (B,npoint,C)
+    -- the layout the next block gathers from.  Consecutive SA blocks hand activations (forward)
+    and gradients (backward) to each other point-major, so neither a to_point_major launch nor a
+    transposing copy sits between them.  Parameters are passed flat as (W0, gamma0, beta0, ...)."""
 
     @staticmethod
-    def forward(ctx, xyz, new_xyz, features, idx, radius, normalize_xyz, mlp_module, training,
-                sm_limit, *params):
-        feat_t = to_point_major(features.contiguous()) if features is not None else None
+    def forward(ctx, xyz, new_xyz, features, features_pm, idx, radius, normalize_xyz, mlp_module,
+                training, sm_limit, want_pm, *params):
+        if features_pm is not None:
+            feat_t = features_pm                       # (B,N,C) from the previous block
+        elif features is None:
+            feat_t = None
+        elif features.shape[1] == 1:                   # (B,1,N) and (B,N,1) are the same bytes
+            feat_t = features.contiguous().reshape(features.shape[0], features.shape[2], 1)
+        else:
+            feat_t = to_point_major(features.contiguous())
         need = any(ctx.needs_input_grad)
         save = {} if need else None
         # sm_limit: one cap for both directions, or (forward cap, backward cap)
         fwd_limit, bwd_limit = sm_limit if isinstance(sm_limit, tuple) else (sm_limit, 0)
-        out_cm, _ = sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
-                                   training, want_point_major=False, save=save,
-                                   sm_limit=fwd_limit)
+        out_cm, out_pm = sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz,
+                                        mlp_module, training, want_point_major=bool(want_pm),
+                                        save=save, sm_limit=fwd_limit)
+        ctx.set_materialize_grads(False)
         if need:
             ctx.saved = (xyz, new_xyz, feat_t, idx, float(radius), bool(normalize_xyz),
                          bool(training), save, params)
             ctx.bwd_sm_limit = int(bwd_limit)
-        return out_cm
+            ctx.from_pm = features_pm is not None
+        if want_pm:
+            return out_cm, out_pm
+        return out_cm, None
 
     @staticmethod
-    def backward(ctx, g_out):
+    def backward(ctx, g_cm, g_pm):
         xyz, new_xyz, feat_t, idx, radius, normalize_xyz, training, save, params = ctx.saved
         L = len(params) // 3
+        n_in = 11
+        if g_cm is None and g_pm is None:
+            return (None,) * (n_in + 3 * L)
         weights = [params[3 * i].detach().reshape(params[3 * i].shape[0], -1) for i in range(L)]
         gammas = [params[3 * i + 1].detach() for i in range(L)]
         nig = ctx.needs_input_grad
         g_feat_t, g_xyz, g_new_xyz, dWs, dgs, dbs = sa_mlp_backward(
-            g_out.contiguous(), xyz, new_xyz, feat_t, idx, radius, normalize_xyz, weights, gammas,
-            training, save, need_feat=nig[2], need_xyz=nig[0], need_new_xyz=nig[1],
-            sm_limit=ctx.bwd_sm_limit, versioned=[params[3 * i] for i in range(L)])
-        g_features = g_feat_t.transpose(1, 2).contiguous() if g_feat_t is not None else None
-        out = [g_xyz, g_new_xyz, g_features, None, None, None, None, None, None]
+            g_cm.contiguous() if g_cm is not None else None, xyz, new_xyz, feat_t, idx, radius,
+            normalize_xyz, weights, gammas, training, save, need_feat=nig[2] or nig[3],
+            need_xyz=nig[0], need_new_xyz=nig[1], sm_limit=ctx.bwd_sm_limit,
+            versioned=[params[3 * i] for i in range(L)],
+            g_out_pm=g_pm.contiguous() if g_pm is not None else None)
+        g_features = g_features_pm = None
+        if g_feat_t is not None:
+            if ctx.from_pm:
+                g_features_pm = g_feat_t
+            elif g_feat_t.shape[2] == 1:
+                g_features = g_feat_t.reshape(g_feat_t.shape[0], 1, g_feat_t.shape[1])
+            else:
+                g_features = g_feat_t.transpose(1, 2).contiguous()
+        out = [g_xyz, g_new_xyz, g_features, g_features_pm] + [None] * (n_in - 4)
         for i in range(L):
             out += [dWs[i].view_as(params[3 * i]), dgs[i], dbs[i]]
         return tuple(out)
 
 
 def sa_block(xyz, new_xyz, features, idx, radius, normalize_xyz, mlp_module, training,
-             sm_limit=0):
-    """Differentiable fused SA block: returns new_features (B, mlp[-1], npoint).  sm_limit > 0
-    caps the forward kernels' persistent grid (SMs left to a concurrent geometry stream); a tuple
-    (forward cap, backward cap) also caps the backward kernels (the pipelined step, where the
-    NEXT batch's geometry runs beside this batch's whole forward and backward)."""
+             sm_limit=0, features_pm=None, want_pm=False):
+    """Differentiable fused SA block: returns (new_features (B, mlp[-1], npoint), the same
+    point-major (B, npoint, mlp[-1]) when `want_pm`, else None).  `features_pm` (B,N,C): the
+    input features point-major (a previous block's second output) -- used instead of `features`.
+    sm_limit > 0 caps the forward kernels' persistent grid (SMs left to a concurrent geometry
+    stream); a tuple (forward cap, backward cap) also caps the backward kernels (the pipelined
+    step, where the NEXT batch's geometry runs beside this batch's whole forward and backward)."""
     params = []
     for blk in mlp_module:
         params += [blk.conv.weight, blk.bn.bn.weight, blk.bn.bn.bias]
-    return _FusedSABlock.apply(xyz, new_xyz, features, idx, radius, normalize_xyz, mlp_module,
-                               training, sm_limit, *params)
+    return _FusedSABlock.apply(xyz, new_xyz, features, features_pm, idx, radius, normalize_xyz,
+                               mlp_module, training, sm_limit, bool(want_pm), *params)
 
 
 NUM_SMS = 148   # B200

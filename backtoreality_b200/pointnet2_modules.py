@@ -76,7 +76,10 @@ class _SAVotesBase(nn.Module):
                 and isinstance(g, pointnet2_utils.QueryAndGroup) and g.use_xyz
                 and not g.sample_uniformly and not g.ret_unique_cnt)
 
-    def _abstract(self, xyz, new_xyz, features, idx=None, sm_limit=0):
+    def _abstract(self, xyz, new_xyz, features, idx=None, sm_limit=0, features_pm=None,
+                  want_pm=False):
+        """-> (new_features (B,C,npoint), the same point-major or None).  features_pm / want_pm:
+        point-major hand-over between consecutive fused blocks (fused_sa.sa_block)."""
         if self.fusable(xyz):
             # fused path: ball query, then ONE tcgen05 block for group -> relative xyz -> MLP ->
             # BN/ReLU -> max-pool (csrc/mlp.cu, csrc/mlp_bwd.cu); no (B,C,npoint,nsample) tensor
@@ -85,10 +88,11 @@ class _SAVotesBase(nn.Module):
             if fused_sa.supported(self.mlp_module, xyz, features, idx, self.pooling):
                 return fused_sa.sa_block(xyz, new_xyz, features, idx, self.radius,
                                          self.normalize_xyz, self.mlp_module, self.training,
-                                         sm_limit=sm_limit)
+                                         sm_limit=sm_limit, features_pm=features_pm,
+                                         want_pm=want_pm)
         grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features)
         new_features = self.mlp_module(grouped_features)  # (B, mlp[-1], npoint, nsample)
-        return _pool(new_features, grouped_xyz, self.pooling, self.sigma, self.nsample)
+        return _pool(new_features, grouped_xyz, self.pooling, self.sigma, self.nsample), None
 
 
 class PointnetSAModuleVotes(_SAVotesBase):
@@ -105,8 +109,12 @@ class PointnetSAModuleVotes(_SAVotesBase):
             # (backbone_module.Pointnet2Backbone.geometry_prepass): wait for them, run the MLP
             if geometry.get("event") is not None:
                 torch.cuda.current_stream().wait_event(geometry["event"])
-            new_features = self._abstract(xyz, geometry["new_xyz"], features, idx=geometry["idx"],
-                                          sm_limit=geometry.get("sm_limit", 0))
+            new_features, out_pm = self._abstract(
+                xyz, geometry["new_xyz"], features, idx=geometry["idx"],
+                sm_limit=geometry.get("sm_limit", 0), features_pm=geometry.get("features_pm"),
+                want_pm=geometry.get("want_pm", False))
+            if out_pm is not None:
+                geometry["out_pm"] = out_pm      # for the next block (Pointnet2Backbone.forward)
             return geometry["new_xyz"], new_features, geometry["inds"]
         xyz_flipped = xyz.transpose(1, 2).contiguous()
         if inds is None:
@@ -116,7 +124,7 @@ class PointnetSAModuleVotes(_SAVotesBase):
         new_xyz = pointnet2_utils.gather_operation(
             xyz_flipped, inds
         ).transpose(1, 2).contiguous() if self.npoint is not None else None
-        new_features = self._abstract(xyz, new_xyz, features, sm_limit=self.sm_limit)
+        new_features, _ = self._abstract(xyz, new_xyz, features, sm_limit=self.sm_limit)
         return new_xyz, new_features, inds
 
 
@@ -127,7 +135,7 @@ class PointnetSAModuleCenters(_SAVotesBase):
     """
 
     def forward(self, xyz: torch.Tensor, features: torch.Tensor, centers: torch.Tensor):
-        return self._abstract(xyz, centers, features)
+        return self._abstract(xyz, centers, features)[0]
 
 
 class PointnetFPModule(nn.Module):
