@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from backtoreality_b200 import scenes  # noqa: E402
 from backtoreality_b200.backbone_module import Pointnet2Backbone  # noqa: E402
-from backtoreality_b200.train_step import CapturedTrainStep  # noqa: E402
+from backtoreality_b200.train_step import CapturedTrainStep, PipelinedTrainStep  # noqa: E402
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -18,10 +18,10 @@ opt = torch.optim.Adam(net.parameters(), lr=1e-3, fused=True, capturable=True)
 pcs = [torch.from_numpy(scenes.batch(500 + 4 * i, 4, 50000, C=0, kind="room", dup=0.2)).to(dev) for i in range(3)]
 
 
-def step(pc):
+def step(pc, geometry=None):
     for p in net.parameters():
         p.grad = None
-    ep = net(pc)
+    ep = net(pc, geometry=geometry)
     loss = ep["fp2_features"].square().mean()
     loss.backward()
     opt.step()
@@ -44,5 +44,8 @@ def time(fn, n=10):
 ms_e = time(step)
 cap = CapturedTrainStep(step, pcs[0])
 ms_g = time(lambda pc: cap(pc))
+pipe = PipelinedTrainStep(net, step, pcs[0], fps_cluster=5)   # 50000 points: 20 per thread on 5 CTAs
+ms_p = time(lambda pc: pipe(pc))
 print("GF3D backbone fwd+bwd+Adam, B=4 x 50000 points: eager %.2f ms/step (%.0f scenes/s), "
-      "graph %.2f ms/step (%.0f scenes/s), loss %.4f" % (ms_e, 4e3 / ms_e, ms_g, 4e3 / ms_g, float(cap(pcs[0]))))
+      "graph %.2f ms/step (%.0f scenes/s), pipelined graph %.2f ms/step (%.0f scenes/s), loss %.4f"
+      % (ms_e, 4e3 / ms_e, ms_g, 4e3 / ms_g, ms_p, 4e3 / ms_p, float(cap(pcs[0]))))
