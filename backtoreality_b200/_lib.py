@@ -19,6 +19,7 @@ SIGNATURES = {
     "b2r_version": [],
     "b2r_status_string": [_i],
     "b2r_last_error": [],
+    "b2r_struct_bytes": [_i],
     "b2r_ref_block_threads": [_i],
     "b2r_fps": [_vp, _i, _i, _i, _vp, _vp],
     "b2r_fps_ex": [_vp, _i, _i, _i, _vp, _i, _vp],

@@ -31,6 +31,12 @@ extern "C" const char *b2r_status_string(int status) {
 
 extern "C" const char *b2r_last_error(void) { return b2r::g_err; }
 
+extern "C" int b2r_struct_bytes(int which) {
+  if (which == 0) return (int)sizeof(b2r_sa_layer);
+  if (which == 1) return (int)sizeof(b2r_sa_layer_bwd_desc);
+  return -1;
+}
+
 // Reference include/cuda_utils.h:20-24 (opt_n_threads): 2^floor(log2(work)) capped to [1,512],
 // computed with the same double log()/log(2.0) quotient and int truncation so that the FPS tie
 // order (which depends on this value) matches on every N, including exact powers of two.

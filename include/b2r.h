@@ -46,6 +46,10 @@ typedef enum b2r_status {
 B2R_API int b2r_version(void);
 B2R_API const char *b2r_status_string(int status);
 B2R_API const char *b2r_last_error(void);
+/* sizeof() of the descriptor structs as THIS build of the library sees them (0: b2r_sa_layer,
+ * 1: b2r_sa_layer_bwd_desc; -1 otherwise): lets a binding in another language verify its mirror
+ * of the struct layout before the first launch (tests/test_capi_symbols.py does). */
+B2R_API int b2r_struct_bytes(int which);
 
 /* The reference's power-of-two thread-count rule (include/cuda_utils.h:20-24).  Exposed because
  * it fixes the FPS tie order (see b2r_fps) and callers/tests may want to inspect it. */

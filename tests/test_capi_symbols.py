@@ -44,6 +44,12 @@ def test_host_only_entry_points():
     assert c.value * t.value * p.value >= 40000 and 1 <= c.value <= 16  # any cluster size <= 16
     assert l.b2r_fps_plan(1, 10_000_000, c, t, p, s) == -3       # B2R_ERR_UNSUPPORTED
     assert b"capacity" in l.b2r_last_error()
+    # the ctypes mirrors of the descriptor structs have the library's layout
+    assert l.b2r_struct_bytes(0) == ctypes.sizeof(_lib.SaLayer)
+    assert l.b2r_struct_bytes(1) == ctypes.sizeof(_lib.SaLayerBwd)
+    assert l.b2r_struct_bytes(7) == -1
+    # the cluster hint of b2r_fps_ex is validated like every other argument
+    assert l.b2r_fps_ex(None, 1, 10, 4, None, 17, None) == -1
     # argument validation happens before any CUDA call
     assert l.b2r_fps(None, 1, 10, 4, None, None) == -1
     assert l.b2r_ball_query(None, None, -1, 1, 1, 0.1, 1, None, None) == -1
