@@ -1,0 +1,9 @@
+#!/bin/bash
+# 8-GPU bench (torchrun, as the driver launches it)
+mkdir -p gpurun_out
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 \
+  bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_8gpu.json 2> gpurun_out/bench_8gpu.err
+tail -2 gpurun_out/bench_8gpu.err
+python -c "
+import json
+d = json.load(open('gpurun_out/bench_8gpu.json')); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks'])"
