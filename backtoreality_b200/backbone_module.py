@@ -94,6 +94,13 @@ class Pointnet2Backbone(nn.Module):
             levels[-1]["sm_limit"] = 0   # nothing runs beside sa4's MLP
         return levels
 
+    @staticmethod
+    def _after_forward(level):
+        """hook of a pre-computed geometry level: called once its SA block has been issued
+        (train_step.PipelinedTrainStep starts the next batch's pre-pass from here)"""
+        if isinstance(level, dict) and level.get("after_forward") is not None:
+            level["after_forward"]()
+
     def forward(self, pointcloud: torch.Tensor, end_points=None, geometry=None):
         """pointcloud (B,N,3+input_feature_dim) -> end_points dict (sa{1..4}_xyz/features,
         sa1_inds, sa2_inds, fp2_features, fp2_xyz, fp2_inds).  `geometry` (not in the reference's
@@ -124,6 +131,7 @@ class Pointnet2Backbone(nn.Module):
         end_points['sa1_inds'] = fps_inds
         end_points['sa1_xyz'] = xyz
         end_points['sa1_features'] = features
+        self._after_forward(geo[0])
         if chain:
             geo[1]["features_pm"] = geo[0].pop("out_pm", None)
 
@@ -131,18 +139,21 @@ class Pointnet2Backbone(nn.Module):
         end_points['sa2_inds'] = fps_inds
         end_points['sa2_xyz'] = xyz
         end_points['sa2_features'] = features
+        self._after_forward(geo[1])
         if chain:
             geo[2]["features_pm"] = geo[1].pop("out_pm", None)
 
         xyz, features, fps_inds = self.sa3(xyz, features, geometry=geo[2])
         end_points['sa3_xyz'] = xyz
         end_points['sa3_features'] = features
+        self._after_forward(geo[2])
         if chain:
             geo[3]["features_pm"] = geo[2].pop("out_pm", None)
 
         xyz, features, fps_inds = self.sa4(xyz, features, geometry=geo[3])
         end_points['sa4_xyz'] = xyz
         end_points['sa4_features'] = features
+        self._after_forward(geo[3])
 
         interp1 = interp2 = None
         if geo[3] is not None and "fp1_idx" in geo[3]:

@@ -67,6 +67,9 @@ def parse():
     ap.add_argument("--trace", default="",
                     help="after timing, trace 3 steps with torch.profiler (CUPTI) and write a per-kernel "
                          "summary + stream-occupancy analysis of one step to this file")
+    ap.add_argument("--prepass-after", type=int, default=1,
+                    help="pipelined step: start the next batch's pre-pass after this SA level's forward "
+                         "(-1: with the step)")
     ap.add_argument("--sm-caps", default="",
                     help="pipelined step: persistent-grid caps 'fwd:bwd' of sa1,sa2,sa3,sa4,vote-agg "
                          "(comma separated, 0 = every SM); default: see PipelinedTrainStep")
@@ -88,7 +91,8 @@ def workload_config(a, world):
                    else "fwd+bwd replayed from one CUDA graph; NCCL all-reduce + fused Adam eager"),
         "pipeline": ("none: FPS / ball query of a batch run inside its own step" if a.no_pipeline or a.no_graph
                      else "geometry pre-pass (FPS, centre gather, ball query of sa1..sa4) of batch i+1 runs "
-                          "beside the step of batch i in the same graph (%d-CTA FPS clusters); every timed "
+                          "beside the step of batch i in the same graph (%d-CTA FPS clusters, started after "
+                          "SA2's forward so the wide first-level kernels keep every SM); every timed "
                           "step = one pre-pass + one fwd/bwd/Adam; e2e copies batch i+1 from pinned host "
                           "memory and reads the loss of batch i" % a.fps_cluster),
         "mlp_math": "SA blocks: fused tcgen05, forward TF32 / backward BF16 operands, fp32 accumulate; "
@@ -418,18 +422,16 @@ def run_b2r(a):
             if pipelined:
                 # the vote-aggregation block has no pre-pass level of its own: give its kernels the
                 # caps of the levels around it (forward: beside SA1's FPS; backward: it runs first)
-                from backtoreality_b200 import fused_sa
-                caps = None
-                net.pnet.vote_aggregation.sm_limit = (
-                    max(fused_sa.NUM_SMS - a.batch * a.fps_cluster, 32),
-                    max(fused_sa.NUM_SMS - a.batch, 32))
+                start = None if a.prepass_after < 0 else a.prepass_after
+                caps, head_cap = PipelinedTrainStep.default_caps(a.batch, a.fps_cluster, start)
                 if a.sm_caps:
                     caps = [tuple(int(v) for v in c.split(":")) for c in a.sm_caps.split(",")]
-                    net.pnet.vote_aggregation.sm_limit = caps[4]
-                    caps = caps[:4]
+                    caps, head_cap = caps[:4], caps[4]
+                net.pnet.vote_aggregation.sm_limit = head_cap
                 graphed = PipelinedTrainStep(net.backbone_net, step if capture_all else fwd_bwd,
                                              resident[0], fps_cluster=a.fps_cluster, sm_caps=caps,
-                                             after_warmup_step=None if capture_all else finish)
+                                             after_warmup_step=None if capture_all else finish,
+                                             start_after_level=start)
             else:
                 graphed = CapturedTrainStep(step if capture_all else fwd_bwd, resident[0],
                                             after_warmup_step=None if capture_all else finish)

@@ -284,9 +284,11 @@ def test_captured_train_step_matches_eager(cuda):
     assert int(bn_e.num_batches_tracked) == 4 and int(bn_g.num_batches_tracked) == 7
 
 
-def test_pipelined_train_step_matches_sequential(cuda):
+@pytest.mark.parametrize("start_after_level", [None, 1, 3])
+def test_pipelined_train_step_matches_sequential(cuda, start_after_level):
     """train_step.PipelinedTrainStep (geometry pre-pass of batch i+1 beside the step of batch i,
-    narrow FPS clusters, capped MLP grids) must train on the same batches in the same order as
+    started with the step or from the hook after an SA level's forward, narrow FPS clusters,
+    capped MLP grids) must train on the same batches in the same order as
     the plain step: with lr = 0 the loss returned by call i is the eager loss of batch i (up to
     the summation order of the BatchNorm statistics under a different persistent grid), the
     rotated geometry buffers hold exactly the indices a fresh pre-pass computes, and the
@@ -316,7 +318,8 @@ def test_pipelined_train_step_matches_sequential(cuda):
     eager = [float(step_e(b)) for b in batches]
     net_p, step_p = make()
     net_p.pnet.vote_aggregation.sm_limit = (100, 120)
-    pipe = PipelinedTrainStep(net_p.backbone_net, step_p, batches[0], warmup=2, fps_cluster=3)
+    pipe = PipelinedTrainStep(net_p.backbone_net, step_p, batches[0], warmup=2, fps_cluster=3,
+                              start_after_level=start_after_level)
     assert pipe.launches_per_step > 50
     got = [float(pipe(batches[(i + 1) % 4])) for i in range(4)]   # call i trains on batch i
     assert len(set(got)) == 4
