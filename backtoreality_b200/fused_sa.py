@@ -58,20 +58,29 @@ def pack_weight(weight, gather):
 # nothing but the weights); the layers then `_take` their image instead of packing inline.
 _PREPACKED = {}      # (id(weight), kind) -> (image, event, weight._version, weight)
 _PACK_STREAMS = {}   # device -> side stream
-_PACK_EVENTS = []    # events recorded by the last prepack (joined by prepack_join)
+_PACK_EVENTS = {}    # device -> events recorded by its last prepack (joined by prepack_join)
 
 
 def prepack(mlp_modules, backward=None):
     """Pack the operand images of every conv of the given SharedMLP modules on a side stream.
     Entries are consumed once (a second forward through the same module in the same step packs
-    inline again) and dropped by the next call; a weight modified in between is detected by its
-    version counter and re-packed."""
+    inline again) and dropped by the next call for the same device; a weight modified in between
+    is detected by its version counter and re-packed.  The registry is process-wide on purpose:
+    autograd runs the backward nodes -- which take the BF16 images -- on its own threads; entries
+    and events are kept per device so that nn.DataParallel replicas (one thread and one device
+    each, reference train_Votenet_FSB.py:164-168) do not drop each other's images."""
     mlp_modules = [m for m in mlp_modules if m is not None and len(m) > 0]
-    _PREPACKED.clear()
-    del _PACK_EVENTS[:]
+    if not mlp_modules or not mlp_modules[0][0].conv.weight.is_cuda:
+        if not torch.cuda.is_available():
+            return
+        dev = torch.device("cuda", torch.cuda.current_device())
+    else:
+        dev = mlp_modules[0][0].conv.weight.device
+    for key in [k for k, ent in list(_PREPACKED.items()) if ent[3].device == dev]:
+        _PREPACKED.pop(key, None)
+    _PACK_EVENTS[dev] = []
     if not mlp_modules or not mlp_modules[0][0].conv.weight.is_cuda:
         return
-    dev = mlp_modules[0][0].conv.weight.device
     if backward is None:
         backward = torch.is_grad_enabled()
     main = torch.cuda.current_stream(dev)
@@ -91,7 +100,7 @@ def prepack(mlp_modules, backward=None):
                     entries.append(((id(w), kind), image, w._version, w))
                 ev = torch.cuda.Event()
                 ev.record(side)
-                _PACK_EVENTS.append(ev)
+                _PACK_EVENTS[dev].append(ev)
                 for key, image, version, w in entries:
                     _PREPACKED[key] = (image, ev, version, w)
 
@@ -99,9 +108,11 @@ def prepack(mlp_modules, backward=None):
 def prepack_join():
     """Make the current stream wait for everything the last `prepack` issued (also needed so that
     a CUDA-graph capture never ends with the packing stream un-joined)."""
-    for ev in _PACK_EVENTS:
+    if not torch.cuda.is_available():
+        return
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for ev in _PACK_EVENTS.pop(dev, []):
         torch.cuda.current_stream().wait_event(ev)
-    del _PACK_EVENTS[:]
 
 
 def _take(weight, kind):
