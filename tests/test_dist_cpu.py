@@ -85,3 +85,17 @@ def test_shard_validation_and_bucket_views():
     bucket.allreduce_mean()      # no process group: no-op
     bucket.zero()
     assert float(bucket.flat.abs().sum()) == 0
+
+
+def test_pipelined_step_default_caps():
+    """PipelinedTrainStep.default_caps (host logic, no GPU): the persistent-grid caps that keep
+    the next batch's FPS clusters and the MLP kernels off each other's SMs."""
+    from backtoreality_b200.train_step import PipelinedTrainStep
+    caps, head = PipelinedTrainStep.default_caps(8, 4, None)      # pre-pass starts with the step
+    assert caps == [(116, 0), (116, 0), (116, 140), (116, 140)] and head == (116, 140)
+    caps, head = PipelinedTrainStep.default_caps(8, 4, 1)         # ... after SA2's forward
+    assert caps == [(0, 140), (0, 140), (116, 116), (116, 116)] and head == (116, 116)
+    caps, head = PipelinedTrainStep.default_caps(4, 5, 3)         # GroupFree3D: 4 scenes, 5-CTA FPS
+    assert caps == [(0, 144)] * 4 and head == (128, 128)
+    caps, _ = PipelinedTrainStep.default_caps(64, 4, 1)           # never below 32 CTAs
+    assert caps[2] == (32, 32) and caps[0] == (0, 84)
