@@ -506,3 +506,37 @@ def test_thin_first_layer_backward(cuda, C, Cout, N, NP, NS, norm, monkeypatch):
     want = dz.t() @ x
     assert rel_l2(out["thin"].cpu().numpy(), want.cpu().numpy()) < 2e-5
     assert rel_l2(out["tensor"].cpu().numpy(), want.cpu().numpy()) < BF16_TOL
+
+
+def test_fused_block_single_scene_batch(cuda):
+    """B = 1 -- BatchNorm batch statistics over ONE scene, one FPS
+    cluster, one tile stream.  Module forward + backward through the fused path against the
+    unfused libb2r + cuDNN path (fp32 convolutions) with the same weights."""
+    import copy
+    from backtoreality_b200 import fused_sa, scenes
+    from backtoreality_b200.pointnet2_modules import PointnetSAModuleVotes
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(13)
+        sa = PointnetSAModuleVotes(npoint=512, radius=0.3, nsample=32, mlp=[1, 64, 64, 128],
+                                   use_xyz=True, normalize_xyz=True).to(cuda).train()
+        ref = copy.deepcopy(sa)
+        pc = torch.from_numpy(scenes.batch(90, 1, 9000, C=1, kind="room", dup=0.2)).to(cuda)
+        xyz = pc[..., :3].contiguous()
+        feats = pc[..., 3:].transpose(1, 2).contiguous()
+        outs = []
+        for mod, fused in ((sa, True), (ref, False)):
+            fused_sa.ENABLED = fused
+            new_xyz, y, inds = mod(xyz, feats)
+            (y * torch.sin(torch.arange(y.numel(), device=cuda, dtype=torch.float32)).view_as(y)).sum().backward()
+            outs.append((new_xyz, y.detach(), inds, [p.grad.clone() for p in mod.parameters()]))
+        (xa, ya, ia, ga), (xb, yb, ib, gb) = outs
+        assert torch.equal(ia, ib) and torch.equal(xa, xb)
+        assert rel_l2(ya.cpu().numpy(), yb.cpu().numpy()) < 5e-3
+        for a, b in zip(ga, gb):
+            assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 8e-2
+        assert int(sa.mlp_module.layer0.bn.bn.num_batches_tracked) == 1
+    finally:
+        fused_sa.ENABLED = True
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
