@@ -54,6 +54,7 @@ class SaLayer(ctypes.Structure):
         ("w_image", _vp), ("z", _vp), ("stats", _vp),
         ("zmax", _vp), ("zmin", _vp), ("amax", _vp), ("amin", _vp),
         ("sm_limit", _i),
+        ("cidx", _vp), ("ccen", _vp), ("cmeta", _vp),
     ]
 
 
@@ -83,6 +84,7 @@ class SaLayerBwd(ctypes.Structure):
         ("dW", _vp), ("gr_prev", _vp), ("stats_prev", _vp),
         ("g_feat_t", _vp), ("g_xyz", _vp), ("g_new_xyz", _vp),
         ("sm_limit", _i),
+        ("cidx", _vp), ("ccen", _vp), ("cmeta", _vp),
     ]
 
 
@@ -96,6 +98,17 @@ SIGNATURES.update({
                             _vp, _vp, _vp, _vp],
 })
 _RESTYPES["b2r_mlp_weight_bf16_image_bytes"] = ctypes.c_longlong
+
+# pad-free position space of a fused SA block (csrc/compact.cu)
+SIGNATURES.update({
+    "b2r_compact_capacity": [_i, _i, _i],
+    "b2r_compact_workspace_bytes": [_i, _i],
+    "b2r_compact_plan": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "b2r_sa_layer_fwd_tile": [_i] * 8,
+    "b2r_sa_layer_bwd_tile": [_i] * 9,
+})
+_RESTYPES["b2r_compact_capacity"] = ctypes.c_longlong
+_RESTYPES["b2r_compact_workspace_bytes"] = ctypes.c_longlong
 
 _lib = None
 

@@ -71,13 +71,17 @@ class Pointnet2Backbone(nn.Module):
                 new_xyz = pointnet2_utils.gather_operation(
                     cur.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
                 idx = pointnet2_utils.ball_query(sa.radius, sa.nsample, cur, new_xyz)
+                # the block's pad-free position space (fused_sa.compact_plan) is geometry too
+                plan = {}
+                if fused_sa.ENABLED and fused_sa.compact_wanted(sa.nsample):
+                    plan = fused_sa.compact_plan(idx, cur.shape[1])
                 ev = torch.cuda.Event()
                 ev.record(side)
-                for t in (inds, new_xyz, idx):
+                for t in (inds, new_xyz, idx) + tuple(plan.values()):
                     t.record_stream(main)
-                levels.append({"inds": inds, "new_xyz": new_xyz, "idx": idx, "event": ev,
-                               "sm_limit": (fused_sa.NUM_SMS - GEOMETRY_SMS) if sm_limit is None
-                               else sm_limit})
+                levels.append(dict(plan, inds=inds, new_xyz=new_xyz, idx=idx, event=ev,
+                                   sm_limit=(fused_sa.NUM_SMS - GEOMETRY_SMS) if sm_limit is None
+                                   else sm_limit))
                 cur = new_xyz
             # the FP modules' 3-NN indices and inverse-distance weights are geometry too:
             # fp1 interpolates sa4 -> sa3, fp2 sa3 -> sa2 (stored with the last level, whose

@@ -73,6 +73,7 @@ struct LayerArgs {
   float *zmax, *zmin;
   int *amax, *amin;
   int Kp, Cout_pad, num_tiles, chf_shift, ns_shift, raw_stage;
+  const int *cidx, *ccen, *cmeta;   // compacted position space (csrc/compact.cu) or NULL
 };
 
 // Warp roles (12 warps = 3 per SM sub-partition -> 168 registers/thread):
@@ -86,12 +87,15 @@ constexpr int kFwdEpiThreads = 128, kFwdProdThreads = 224;
 constexpr int kFwdThreads = kFwdEpiThreads + 32 + kFwdProdThreads;   // 384
 
 struct FwdSmem {
-  uint32_t w_off, w_bytes, x_off[2], x_bytes, raw_off[2], raw_bytes, scale_off, idx_off, bar_off,
-      total;
+  uint32_t w_off, w_bytes, x_off[2], x_bytes, raw_off[2], raw_bytes, scale_off, idx_off, cen_off,
+      bar_off, total;
 };
 // raw_cin > 0 (dense layers): two raw staging buffers of NT x raw_cin fp32, filled by TMA bulk
 // copies two tiles ahead, so the producers never wait on a global load
-__host__ __device__ inline FwdSmem fwd_smem_layout(int Kp, int Cout_pad, int NT, int raw_cin) {
+// cmp: compacted position space -- per-row centre ids for the producers (NT ints), a two-stage
+// ring of them for the pooling epilogue (2 NT ints) and a copy of the plan's meta words (8 ints)
+__host__ __device__ inline FwdSmem fwd_smem_layout(int Kp, int Cout_pad, int NT, int raw_cin,
+                                                   int cmp = 0) {
   FwdSmem s;
   const uint32_t KA = (uint32_t)(Kp + 31) >> 5;
   s.w_off = 0;
@@ -104,7 +108,8 @@ __host__ __device__ inline FwdSmem fwd_smem_layout(int Kp, int Cout_pad, int NT,
   s.raw_off[1] = s.raw_off[0] + s.raw_bytes;
   s.scale_off = s.raw_off[1] + s.raw_bytes;
   s.idx_off = s.scale_off + 2u * Kp * 4u;
-  s.bar_off = (s.idx_off + (uint32_t)NT * 4u + 15u) & ~15u;
+  s.cen_off = s.idx_off + (uint32_t)NT * 4u;
+  s.bar_off = (s.cen_off + (cmp ? 3u * (uint32_t)NT * 4u + 32u : 0u) + 15u) & ~15u;
   s.total = s.bar_off + 11 * 8 + 16 + 1024;   // + alignment slack
   return s;
 }
@@ -119,16 +124,23 @@ __device__ __forceinline__ void mbar_arrive1(uint32_t bar) {
 }
 
 // NT = positions per tile (MMA N); MT = Cout_pad / 128 accumulator M tiles (1 or 2).
-template <int NT>
+// CMP: positions are those of a b2r_compact_plan (csrc/compact.cu): the tile count comes from
+// the plan's meta words on the device, gather rows from cidx / ccen, and the epilogue works on
+// 8-column sample groups whose class (8/16/32/64 samples per centre), liveness and first-sample
+// weight are per-TILE constants.
+template <int NT, bool CMP>
 __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const LayerArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~(uintptr_t)1023);
-  const FwdSmem L = fwd_smem_layout(a.Kp, a.Cout_pad, NT, a.raw_stage ? a.Cin : 0);
+  const FwdSmem L = fwd_smem_layout(a.Kp, a.Cout_pad, NT, a.raw_stage ? a.Cin : 0, CMP ? 1 : 0);
   uint8_t *s_w = base + L.w_off;
   float *s_scale = reinterpret_cast<float *>(base + L.scale_off);
   float *s_shift = s_scale + a.Kp;
   int *s_idx = reinterpret_cast<int *>(base + L.idx_off);
+  int *s_cenp = reinterpret_cast<int *>(base + L.cen_off);   // CMP: producers' centre per row
+  int *s_cene = s_cenp + NT;                                 // CMP: pooling epilogue's, 2 stages
+  int *s_meta = s_cene + 2 * NT;                             // CMP: plan meta words 0..7
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(base + L.bar_off);
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 11);
   // mbarriers: [0,1] full  [2,3] empty  [4,5] mma_done  [6,7] d_free  [8] weights  [9,10] raw
@@ -139,6 +151,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
   constexpr int NCH = NT / 32;
   constexpr uint32_t kTmemCols = 512;
   const int grid = (int)gridDim.x;
+  int num_tiles = a.num_tiles;
+  if constexpr (CMP) {
+    num_tiles = __ldg(a.cmeta + 8) / NT;
+    if (tid < 8) s_meta[tid] = __ldg(a.cmeta + tid);
+  }
 
   if (tid == 0) {
     for (int i = 0; i < 11; ++i) mbar_init(bar(i), 1);
@@ -174,25 +191,38 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
     if (a.raw_stage && ptid == 0) {   // prime the raw ring with this CTA's first two tiles
       for (int k = 0; k < 2; ++k) {
         const long long tile = (long long)blockIdx.x + (long long)k * grid;
-        if (tile < a.num_tiles) {
+        if (tile < num_tiles) {
           mbar_expect_tx(bar(9 + k), L.raw_bytes);
           bulk_g2s(smem_u32(base + L.raw_off[k]), a.z_prev + (size_t)(tile * NT) * a.Cin,
                    L.raw_bytes, bar(9 + k));
         }
       }
     }
-    int nidx = 0;   // prefetched ball-query index of the next tile (gather layers)
-    for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k) {
+    int nidx = 0, ncen = 0;   // prefetched ball-query index (centre) of the next tile
+    for (int k = 0, tile = blockIdx.x; tile < num_tiles; tile += grid, ++k) {
       const int s = k & 1, n = k >> 1;
       mbar_wait(bar(2 + s), (uint32_t)((n & 1) ^ 1));   // MMAs of tile k-2 are done with stage s
       const long long pos0 = (long long)tile * NT;
       uint8_t *sx = base + L.x_off[s];
-      if (a.mode == 0) {
+      if (CMP && a.mode == 0) {
+        if (ptid < NT) {
+          s_idx[ptid] = (k == 0) ? a.cidx[pos0 + ptid] : nidx;
+          s_cenp[ptid] = (k == 0) ? a.ccen[pos0 + ptid] : ncen;
+          if (tile + grid < num_tiles) {
+            nidx = __ldg(a.cidx + pos0 + (long long)grid * NT + ptid);
+            ncen = __ldg(a.ccen + pos0 + (long long)grid * NT + ptid);
+          }
+        }
+        fwd_bar_prod();
+        build_x_gather<NT, kFwdProdThreads>(gsrc, 0, 0, s_idx, sx, ptid,
+                                            [](int row, int ch) { return sw128_off(row, ch, NT); },
+                                            s_cenp);
+      } else if (a.mode == 0) {
         // ball-query indices of this tile were requested one tile ago (nidx): the gathers below
         // start without waiting on a dependent global load
         if (ptid < NT) {
           s_idx[ptid] = (k == 0) ? a.idx[pos0 + ptid] : nidx;
-          if (tile + grid < a.num_tiles) nidx = __ldg(a.idx + pos0 + (long long)grid * NT + ptid);
+          if (tile + grid < num_tiles) nidx = __ldg(a.idx + pos0 + (long long)grid * NT + ptid);
         }
         fwd_bar_prod();
         const int b = (int)(pos0 / per_scene);
@@ -223,7 +253,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
         // 8 independent 16-byte loads per thread in flight, tile k+2 prefetched into L2
         const int CH = a.Cin >> 2;
         const int total = NT * CH;
-        if (ptid == 0 && tile + 2 * grid < a.num_tiles)
+        if (ptid == 0 && tile + 2 * grid < num_tiles)
           prefetch_l2(a.z_prev + (size_t)(pos0 + 2ll * grid * NT) * a.Cin, (uint32_t)total * 16u);
         const float4 *src = reinterpret_cast<const float4 *>(a.z_prev + (size_t)pos0 * a.Cin);
         for (int i0 = ptid; i0 < total; i0 += kFwdProdThreads * 8) {
@@ -254,7 +284,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
       fwd_bar_prod();
       if (ptid == 0) {
         mbar_arrive1(bar(0 + s));
-        if (a.raw_stage && tile + 2 * grid < a.num_tiles) {   // refill raw[s] with tile k+2
+        if (a.raw_stage && tile + 2 * grid < num_tiles) {   // refill raw[s] with tile k+2
           mbar_expect_tx(bar(9 + s), L.raw_bytes);
           bulk_g2s(smem_u32(base + L.raw_off[s]),
                    a.z_prev + (size_t)(pos0 + 2ll * grid * NT) * a.Cin, L.raw_bytes, bar(9 + s));
@@ -268,7 +298,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
       const uint32_t wa = smem_u32(s_w);
       const int KS = (a.Kp + 7) >> 3;  // K = 8 slices actually issued
       const uint32_t idesc = idesc_tf32(NT);
-      for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k) {
+      for (int k = 0, tile = blockIdx.x; tile < num_tiles; tile += grid, ++k) {
         const int s = k & 1, n = k >> 1;
         const uint32_t xa = smem_u32(base + L.x_off[s]);
         mbar_wait(bar(0 + s), (uint32_t)(n & 1));          // X tile of tile k is in smem
@@ -294,9 +324,23 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     double acc_s[2] = {0.0, 0.0}, acc_ss[2] = {0.0, 0.0};
     const int ns_mask = a.NS - 1;
-    for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k) {
+    int ncen_e = -1;   // CMP pooling: centre of this thread's column in the NEXT tile
+    if constexpr (CMP) {
+      if (a.epilogue == 1) {
+        if (tid < NT)
+          s_cene[tid] = ((int)blockIdx.x < num_tiles) ? a.ccen[(long long)blockIdx.x * NT + tid] : -1;
+        fwd_bar_epi();
+      }
+    }
+    for (int k = 0, tile = blockIdx.x; tile < num_tiles; tile += grid, ++k) {
       const int s = k & 1, n = k >> 1;
       const long long pos0 = (long long)tile * NT;
+      TileClass tc{};
+      if constexpr (CMP) {
+        tc = tile_class(s_meta, pos0, a.NS);
+        if (a.epilogue == 1 && tid < NT && tile + grid < num_tiles)
+          ncen_e = __ldg(a.ccen + pos0 + (long long)grid * NT + tid);
+      }
       mbar_wait(bar(4 + s), (uint32_t)(n & 1));
       tc_fence_after();
 #pragma unroll
@@ -314,6 +358,57 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
               r, tmem_base + lane_addr + (uint32_t)((s * MT + m) * NT + ch * 32));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (!c_ok) continue;
+          if constexpr (CMP) {
+            // 8-column sample groups: wholly live or wholly dead, inside one centre; the centre's
+            // first sample stands for its NS - ns pad copies as well (weight 1 + wx)
+            const int nsm = tc.ns - 1;
+            const int p64 = (int)(pos0 & 63);
+#pragma unroll
+            for (int sg = 0; sg < 4; ++sg) {
+              const int col0 = ch * 32 + sg * 8;
+              if (col0 < tc.live) {
+                const int s0 = (p64 + col0) & nsm;
+                float t = 0.f, tt = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float x = __uint_as_float(r[sg * 8 + i]);
+                  t += x;
+                  tt = fmaf(x, x, tt);
+                }
+                if (s0 == 0) {
+                  const float x0 = __uint_as_float(r[sg * 8]);
+                  t = fmaf(tc.wx, x0, t);
+                  tt = fmaf(tc.wx * x0, x0, tt);
+                }
+                ts += t;
+                tss += tt;
+                if (a.epilogue == 1) {
+                  if (s0 == 0) {
+                    mx = -INFINITY; mn = INFINITY; ax = 0; an = 0;
+                  }
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float x = __uint_as_float(r[sg * 8 + i]);
+                    if (x > mx) { mx = x; ax = s0 + i; }
+                    if (x < mn) { mn = x; an = s0 + i; }
+                  }
+                  if (s0 + 8 == tc.ns) {
+                    const int centre = s_cene[(k & 1) * NT + col0];
+                    if (centre >= 0) {
+                      const size_t o = (size_t)centre * a.Cout + c;
+                      a.zmax[o] = mx; a.zmin[o] = mn; a.amax[o] = ax; a.amin[o] = an;
+                    }
+                  }
+                }
+              }
+            }
+            if (a.epilogue == 0) {   // dead rows are stored too: later layers must read finite z
+              float *zp = a.z + (size_t)(pos0 + ch * 32) * a.Cout + c;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) zp[(size_t)i * a.Cout] = __uint_as_float(r[i]);
+            }
+            continue;
+          }
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float x = __uint_as_float(r[i]);
@@ -352,6 +447,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
         }
         acc_s[m] += (double)ts;
         acc_ss[m] += (double)tss;
+      }
+      if constexpr (CMP) {
+        if (a.epilogue == 1 && tid < NT) s_cene[((k + 1) & 1) * NT + tid] = ncen_e;
       }
       tc_fence_before();
       fwd_bar_epi();   // every epilogue thread has read D[s]
@@ -485,15 +583,15 @@ namespace {
 // TMA-staged: the widest tile whose two smem stages + two TMEM stages fit; a gather tile must lie
 // inside one scene and a pooling tile must hold whole centres
 int fwd_pick_nt(int Kp, int Cout_pad, int Cin, int mode, int epilogue, int NS, long long M,
-                long long per_scene, int *raw_stage) {
+                long long per_scene, int *raw_stage, int cmp = 0) {
   const int MT = Cout_pad >> 7;
   for (int raw = (mode == 1 ? 1 : 0); raw >= 0; --raw)
     for (int nt : {128, 64, 32}) {
       if (M % nt) continue;
-      if (mode == 0 && per_scene % nt) continue;
+      if (!cmp && mode == 0 && per_scene % nt) continue;   // (a plan's tiles hold global rows)
       if (epilogue == 1 && (nt % NS) != 0) continue;
       if (raw && nt < 64) continue;   // prefer wider register-staged tiles over tiny TMA ones
-      const FwdSmem L = fwd_smem_layout(Kp, Cout_pad, nt, raw ? Cin : 0);
+      const FwdSmem L = fwd_smem_layout(Kp, Cout_pad, nt, raw ? Cin : 0, cmp);
       if (L.total <= 227u * 1024u && 2 * MT * nt <= 512) {
         *raw_stage = raw;
         return nt;
@@ -515,6 +613,16 @@ extern "C" int b2r_sa_layer_fwd_supported(int B, int NP, int NS, int Cin, int Co
                      pooled ? 1 : 0, NS, M, per_scene, &raw) > 0 ? 1 : 0;
 }
 
+extern "C" int b2r_sa_layer_fwd_tile(int B, int NP, int NS, int Cin, int Cout, int gather,
+                                     int pooled, int compact) {
+  if (B <= 0 || NP <= 0 || NS <= 0 || Cin <= 0 || Cout <= 0 || Cout > 256) return 0;
+  const long long per_scene = (long long)NP * NS;
+  const long long M = compact ? b2r_compact_capacity(B, NP, NS) : (long long)B * per_scene;
+  int raw = 0;
+  return fwd_pick_nt(packed_k(Cin, gather), (Cout + 127) & ~127, Cin, gather ? 0 : 1,
+                     pooled ? 1 : 0, NS, M, per_scene, &raw, compact ? 1 : 0);
+}
+
 extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
   B2R_REQUIRE(d != nullptr, "b2r_sa_layer_fwd: null descriptor");
   B2R_REQUIRE(d->B > 0 && d->NP > 0 && d->NS > 0 && d->Cin > 0 && d->Cout > 0,
@@ -534,10 +642,19 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
   a.Cout_pad = (d->Cout + 127) & ~127;
   a.chf_shift = pow2_shift(((d->Cin - 3 + 3) & ~3) >> 2);
   a.ns_shift = pow2_shift(d->NS);
-  const long long M = (long long)d->B * d->NP * d->NS;
+  a.cidx = d->cidx; a.ccen = d->ccen; a.cmeta = d->cmeta;
+  const int cmp = d->cmeta != nullptr ? 1 : 0;
+  B2R_REQUIRE(!cmp || (d->cidx && d->ccen), "b2r_sa_layer_fwd: a plan needs cidx, ccen and cmeta");
+  if (cmp && !(d->NS == 16 || d->NS == 32 || d->NS == 64)) {
+    set_error("b2r_sa_layer_fwd: a compacted plan needs nsample 16/32/64 (got %d)", d->NS);
+    return B2R_ERR_UNSUPPORTED;
+  }
+  // with a plan the launch is sized for the plan's CAPACITY; the live tile count is on the device
+  const long long M = cmp ? b2r_compact_capacity(d->B, d->NP, d->NS)
+                          : (long long)d->B * d->NP * d->NS;
   const long long per_scene = (long long)d->NP * d->NS;
   if (d->mode == 0) {
-    B2R_REQUIRE(d->Cin >= 3 && d->xyz && d->new_xyz && d->idx && (d->feat_t || d->Cin == 3),
+    B2R_REQUIRE(d->Cin >= 3 && d->xyz && d->new_xyz && (d->idx || cmp) && (d->feat_t || d->Cin == 3),
                 "b2r_sa_layer_fwd: gather mode needs xyz, new_xyz, idx (and feat_t when Cin > 3)");
     B2R_REQUIRE(d->Cin == 3 || ((reinterpret_cast<uintptr_t>(d->feat_t) & 15u) == 0),
                 "b2r_sa_layer_fwd: feat_t must be 16-byte aligned");
@@ -562,14 +679,14 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
   // thin first layer (Cin <= 8): a streaming CUDA-core kernel, not a tensor-core tile pipeline
   if (thin::fwd_applicable(d)) return thin::fwd_launch(d, stream);
   const int NT = fwd_pick_nt(a.Kp, a.Cout_pad, d->Cin, d->mode, d->epilogue, d->NS, M, per_scene,
-                             &a.raw_stage);
+                             &a.raw_stage, cmp);
   if (NT == 0) {
     set_error("b2r_sa_layer_fwd: layer Cin=%d Cout=%d M=%lld NP*NS=%lld does not fit (needs "
               "B*NP*NS %% 32 == 0, gather layers NP*NS %% 32 == 0, operands within 227 KB)",
               d->Cin, d->Cout, M, per_scene);
     return B2R_ERR_UNSUPPORTED;
   }
-  const FwdSmem L = fwd_smem_layout(a.Kp, a.Cout_pad, NT, a.raw_stage ? d->Cin : 0);
+  const FwdSmem L = fwd_smem_layout(a.Kp, a.Cout_pad, NT, a.raw_stage ? d->Cin : 0, cmp);
   a.num_tiles = (int)(M / NT);
   // persistent grid: one CTA per SM, or fewer when the caller keeps SMs free for kernels running
   // concurrently on another stream (the geometry pre-pass: FPS needs whole SMs to itself)
@@ -577,19 +694,22 @@ extern "C" int b2r_sa_layer_fwd(const b2r_sa_layer *d, void *stream) {
   if (d->sm_limit > 0 && d->sm_limit < kNumSMs) sms = d->sm_limit;
   const int grid = a.num_tiles < sms ? a.num_tiles : sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (NT == 128) {
-    B2R_CUDA(cudaFuncSetAttribute(sa_layer_fwd_kernel<128>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    sa_layer_fwd_kernel<128><<<grid, kFwdThreads, L.total, st>>>(a);
-  } else if (NT == 64) {
-    B2R_CUDA(cudaFuncSetAttribute(sa_layer_fwd_kernel<64>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    sa_layer_fwd_kernel<64><<<grid, kFwdThreads, L.total, st>>>(a);
+#define B2R_LAUNCH_FWD(NTV, CMPV)                                                               \
+  do {                                                                                          \
+    B2R_CUDA(cudaFuncSetAttribute(sa_layer_fwd_kernel<NTV, CMPV>,                               \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));  \
+    sa_layer_fwd_kernel<NTV, CMPV><<<grid, kFwdThreads, L.total, st>>>(a);                      \
+  } while (0)
+  if (cmp) {
+    if (NT == 128) B2R_LAUNCH_FWD(128, true);
+    else if (NT == 64) B2R_LAUNCH_FWD(64, true);
+    else B2R_LAUNCH_FWD(32, true);
   } else {
-    B2R_CUDA(cudaFuncSetAttribute(sa_layer_fwd_kernel<32>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    sa_layer_fwd_kernel<32><<<grid, kFwdThreads, L.total, st>>>(a);
+    if (NT == 128) B2R_LAUNCH_FWD(128, false);
+    else if (NT == 64) B2R_LAUNCH_FWD(64, false);
+    else B2R_LAUNCH_FWD(32, false);
   }
+#undef B2R_LAUNCH_FWD
   B2R_CHECK_LAUNCH();
   return B2R_OK;
 }

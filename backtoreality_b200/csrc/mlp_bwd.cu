@@ -70,6 +70,7 @@ struct BwdArgs {
   int Kp, KA, WA, Cout_pad, num_tiles;   // KA: 64-wide atoms of packed K; WA: atoms in the image
   int ch8_shift;                         // log2(feature 16-byte chunks per row) or -1
   int ns_shift;                          // log2(NS) or -1
+  const int *cidx, *ccen, *cmeta;        // compacted position space (csrc/compact.cu) or NULL
 };
 
 // packed K extent of a layer in THIS kernel's operand order: gather layers put the C feature
@@ -81,10 +82,12 @@ __host__ __device__ inline int packed_k16(int Cin, int gather) {
 
 struct BwdSmem {
   uint32_t w_off, w_bytes, x_off[2], dz_off[2], x_bytes, dz_bytes, coef_off, scale_off, idx_off,
-      route_off, flush_off, bar_off, total;
+      cen_off, meta_off, route_off, flush_off, bar_off, total;
 };
+// cmp: compacted position space -- a second 4-deep ring for the rows' centre ids, the plan's meta
+// words, and routed-gradient stages for NT/8 (instead of NT/16) centres per tile
 __host__ __device__ inline BwdSmem bwd_smem_layout(int Kp, int KA, int WA, int Cout, int Cout_pad,
-                                                   int NT, int top) {
+                                                   int NT, int top, int cmp = 0) {
   BwdSmem s;
   s.w_off = 0;
   s.w_bytes = (uint32_t)Cout_pad * WA * 128u;
@@ -100,9 +103,22 @@ __host__ __device__ inline BwdSmem bwd_smem_layout(int Kp, int KA, int WA, int C
   s.coef_off = o;
   s.scale_off = s.coef_off + 3u * Cout * 4u;
   s.idx_off = s.scale_off + 2u * Kp * 4u;
-  s.route_off = (s.idx_off + 4u * (uint32_t)NT * 4u + 15u) & ~15u;   // idx: 4 buffers (below)
-  s.flush_off = s.route_off + (top ? 4u * (uint32_t)(NT / 16) * Cout_pad * 4u : 0u);   // 2 stages
-  s.bar_off = s.flush_off + 8u * 32u * 33u * 4u;   // wgrad flush: a padded 32x32 tile per warp
+  s.cen_off = s.idx_off + 4u * (uint32_t)NT * 4u;                    // idx: 4 buffers (below)
+  s.meta_off = s.cen_off + (cmp ? 4u * (uint32_t)NT * 4u : 0u);
+  s.route_off = (s.meta_off + (cmp ? 32u : 0u) + 15u) & ~15u;
+  s.flush_off = s.route_off +
+                (top ? 4u * (uint32_t)(NT / (cmp ? 8 : 16)) * Cout_pad * 4u : 0u);   // 2 stages
+  // wgrad flush staging: a padded 32x32 tile per warp.  With a plan it reuses the operand stages
+  // when they are large enough (the flush runs after the CTA's last MMA has completed, when no
+  // producer or tensor-core access to them is outstanding): the wider routed-gradient stages
+  // would otherwise push the 128->256 top layer down to 32-position tiles.
+  const uint32_t flush_bytes = 8u * 32u * 33u * 4u;
+  if (cmp && 2u * (s.x_bytes + s.dz_bytes) >= flush_bytes) {
+    s.bar_off = s.flush_off;
+    s.flush_off = s.x_off[0];
+  } else {
+    s.bar_off = s.flush_off + flush_bytes;
+  }
   s.total = s.bar_off + 13 * 8 + 16 + 1024;                        // + alignment slack
   return s;
 }
@@ -170,17 +186,22 @@ __global__ void pack_weight_bf16_kernel(const float *__restrict__ w, int Cout, i
 // epilogue warps) are compile-time: every instantiation carries only its own producer /
 // epilogue code.  One runtime-branched kernel was 52,872 SASS instructions (846 KB) and spent
 // 25 % of its warp-stall samples waiting for instruction fetch (ncu, stall_no_inst).
-template <int NT, int EW, int MODE, int TOP>
+// CMP: positions are those of a b2r_compact_plan (csrc/compact.cu).  Incoming gradients (gr,
+// dysel) and everything derived from them carry the positions' multiplicities implicitly: only
+// the DENSE BatchNorm-backward term b*z + c, which every padded position receives once, is
+// scaled by the multiplicity (1 + NS - class size for a centre's first sample, 0 for dead rows).
+template <int NT, int EW, int MODE, int TOP, bool CMP>
 __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdArgs a) {
   constexpr int kMode = MODE;
   constexpr bool kTop = TOP != 0;
+  constexpr int kRC = CMP ? NT / 8 : NT / 16;   // centres per tile a routed-gradient stage holds
   constexpr int kEpiThreads = EW * 32, kProdThreads = (kBwdWarps - 1 - EW) * 32;
   auto bar_epi = [] { bar_named<kEpiThreads>(1); };
   auto bar_prod = [] { bar_named<kProdThreads>(2); };
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~(uintptr_t)1023);
-  const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, NT, kTop);
+  const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, NT, kTop, CMP ? 1 : 0);
   uint8_t *s_w = base + L.w_off;
   float *s_ca = reinterpret_cast<float *>(base + L.coef_off);
   float *s_cb = s_ca + a.Cout;
@@ -190,8 +211,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
   // ball-query indices per tile, 4-deep ring: the producers may write tile k while the scatter
   // epilogue still reads tile k-3 (MMA(k-2) only waits for the epilogue of tile k-4)
   int *s_idx4 = reinterpret_cast<int *>(base + L.idx_off);
+  int *s_cen4 = reinterpret_cast<int *>(base + L.cen_off);     // CMP: centre of every row, same ring
+  int *s_meta = reinterpret_cast<int *>(base + L.meta_off);    // CMP: plan meta words 0..7
   float *s_dy = reinterpret_cast<float *>(base + L.route_off);
-  int *s_as = reinterpret_cast<int *>(s_dy + 2 * (NT / 16) * a.Cout_pad);
+  int *s_as = reinterpret_cast<int *>(s_dy + 2 * kRC * a.Cout_pad);
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(base + L.bar_off);
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 13);
   // mbarriers: [0,1] full  [2,3] empty  [4,5] z_done  [6,7] dz_ready  [8,9] mma_done
@@ -209,6 +232,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
   constexpr uint32_t kTmemCols = 512;
   const long long per_scene = (long long)a.NP * a.NS;
   const int C = a.Cin - 3, Cf8 = (C + 7) & ~7;   // gather layers: feature channels
+  int num_tiles = a.num_tiles;
+  if constexpr (CMP) {
+    num_tiles = __ldg(a.cmeta + 8) / NT;
+    if (tid < 8) s_meta[tid] = __ldg(a.cmeta + tid);
+  }
 
   if (tid == 0) {
     for (int i = 0; i < 13; ++i) mbar_init(bar(i), 1);
@@ -247,14 +275,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
     // =============================== PRODUCERS (7 warps) ========================================
     const int ptid = tid - (kEpiThreads + 32);
     const int CH8 = a.Cout >> 3;     // 16-byte BF16 chunks per DZ row
-    int nidx = 0;   // prefetched ball-query index of the next tile (gather layers)
-    for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k) {
+    int nidx = 0, ncen = 0;   // prefetched ball-query index (centre) of the next tile
+    for (int k = 0, tile = blockIdx.x; tile < num_tiles; tile += grid, ++k) {
       const int s = k & 1, n = k >> 1;
       mbar_wait(bar(2 + s), (uint32_t)((n & 1) ^ 1));   // MMAs of tile k-2 are done with stage s
       const long long pos0 = (long long)tile * NT;
       uint8_t *sx = base + L.x_off[s], *sdz = base + L.dz_off[s];
       int *s_idx = s_idx4 + (k & 3) * NT;
-      if (ptid == 0 && tile + 2 * grid < a.num_tiles) {   // pull tile k+2 into L2 meanwhile
+      int *s_cen = s_cen4 + (k & 3) * NT;
+      TileClass tc{};
+      int p64 = 0;
+      if constexpr (CMP) {
+        tc = tile_class(s_meta, pos0, a.NS);
+        p64 = (int)(pos0 & 63);
+      }
+      if (ptid == 0 && tile + 2 * grid < num_tiles) {   // pull tile k+2 into L2 meanwhile
         const size_t pn = (size_t)(pos0 + 2ll * grid * NT);
         if (!kTop) {
           if (!has_coef) prefetch_l2(a.dz + pn * a.Cout, (uint32_t)NT * a.Cout * 4u);
@@ -303,8 +338,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
                 *reinterpret_cast<float4 *>(cb8 + 4) = *reinterpret_cast<const float4 *>(s_cb + ch * 8 + 4);
                 *reinterpret_cast<float4 *>(cc8) = *reinterpret_cast<const float4 *>(s_cc + ch * 8);
                 *reinterpret_cast<float4 *>(cc8 + 4) = *reinterpret_cast<const float4 *>(s_cc + ch * 8 + 4);
+                if constexpr (CMP) {
+                  const float wgt = row < tc.live
+                                        ? ((((p64 + row) & (tc.ns - 1)) == 0) ? 1.f + tc.wx : 1.f)
+                                        : 0.f;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaf(ca8[e], v[e], fmaf(cb8[e], zv[e], cc8[e]));
+                  for (int e = 0; e < 8; ++e)
+                    v[e] = fmaf(ca8[e], v[e], wgt * fmaf(cb8[e], zv[e], cc8[e]));
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = fmaf(ca8[e], v[e], fmaf(cb8[e], zv[e], cc8[e]));
+                }
               }
               *reinterpret_cast<uint4 *>(sdz + bf_off(row, ch, NT)) =
                   make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
@@ -317,16 +361,26 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
       if (kMode == 0) {
         // indices of this tile were requested one tile ago (nidx): no dependent global wait here
         if (ptid < NT) {
-          s_idx[ptid] = (k == 0) ? a.idx[pos0 + ptid] : nidx;
-          if (tile + grid < a.num_tiles) nidx = __ldg(a.idx + pos0 + (long long)grid * NT + ptid);
+          if constexpr (CMP) {
+            s_idx[ptid] = (k == 0) ? a.cidx[pos0 + ptid] : nidx;
+            s_cen[ptid] = (k == 0) ? a.ccen[pos0 + ptid] : ncen;
+            if (tile + grid < num_tiles) {
+              nidx = __ldg(a.cidx + pos0 + (long long)grid * NT + ptid);
+              ncen = __ldg(a.ccen + pos0 + (long long)grid * NT + ptid);
+            }
+          } else {
+            s_idx[ptid] = (k == 0) ? a.idx[pos0 + ptid] : nidx;
+            if (tile + grid < num_tiles) nidx = __ldg(a.idx + pos0 + (long long)grid * NT + ptid);
+          }
         }
         bar_prod();
-        const int b = (int)(pos0 / per_scene);
-        const int in_scene0 = (int)(pos0 - (long long)b * per_scene);
+        // CMP: s_idx holds global source rows and s_cen global centres: scene 0's base pointers
+        const int b = CMP ? 0 : (int)(pos0 / per_scene);
+        const int in_scene0 = CMP ? 0 : (int)(pos0 - (long long)b * per_scene);
         const int CH8f = Cf8 >> 3;
         for (int row = ptid; row < NT; row += kProdThreads) {   // relative xyz chunk
           const int p = s_idx[row];
-          const int j = (in_scene0 + row) / a.NS;
+          const int j = CMP ? max(s_cen[row], 0) : (in_scene0 + row) / a.NS;
           const float *pp = a.xyz + ((size_t)b * a.N + p) * 3;
           const float *qq = a.new_xyz + ((size_t)b * a.NP + j) * 3;
           const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
@@ -426,7 +480,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
       const uint32_t lbo_w = (uint32_t)(a.Cout_pad >> 3) * 1024u;   // 64-wide K atoms of the image
       const uint32_t lbo_t = (uint32_t)(NT >> 3) * 1024u;           // 64-wide atoms of the tiles
       const int KS16 = (a.Kp + 15) >> 4, KSl16 = (a.Cout + 15) >> 4;
-      for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k) {
+      for (int k = 0, tile = blockIdx.x; tile < num_tiles; tile += grid, ++k) {
         const int s = k & 1, n = k >> 1;
         const uint32_t xa = smem_u32(base + L.x_off[s]), dza = smem_u32(base + L.dz_off[s]);
         const uint32_t d12 = tmem_base + (uint32_t)(s * w12);
@@ -496,19 +550,35 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
     // two warps of a quadrant copy the same entries), so cp.async.wait_group is all the
     // synchronisation needed.  One (possibly empty) group is committed per call.
     auto fetch_route = [&](int k, int tile) {
-      if (tile < a.num_tiles) {
+      if (tile < num_tiles) {
         const int s = k & 1;
         const long long pos0 = (long long)tile * NT;
-        const long long centre0 = pos0 >> a.ns_shift;
-        const int base_s = (int)(pos0 & (a.NS - 1));
-        const int ncen = ((base_s + NT - 1) >> a.ns_shift) + 1;
-        float *my_dy = s_dy + (size_t)s * (NT / 16) * a.Cout_pad;
-        int *my_as = s_as + (size_t)s * (NT / 16) * a.Cout_pad;
+        int ns_t = a.NS, shift_t = a.ns_shift;
+        if constexpr (CMP) {
+          ns_t = tile_class(s_meta, pos0, a.NS).ns;
+          shift_t = 31 - __clz(ns_t);
+        }
+        const long long centre0 = pos0 >> shift_t;
+        const int base_s = (int)(pos0 & (ns_t - 1));
+        const int ncen = ((base_s + NT - 1) >> shift_t) + 1;
+        float *my_dy = s_dy + (size_t)s * kRC * a.Cout_pad;
+        int *my_as = s_as + (size_t)s * kRC * a.Cout_pad;
         for (int ml = 0; ml < MTl; ++ml) {
           const int co = ml * 128 + q * 32 + lane;
           if (co < a.Cout)
             for (int c = 0; c < ncen; ++c) {
-              const size_t o = (size_t)(centre0 + c) * a.Cout + co;
+              long long cg = centre0 + c;
+              if constexpr (CMP) {
+                // global centre of the tile's c-th centre (its first in-tile position); dead
+                // padding routes nothing
+                cg = __ldg(a.ccen + pos0 + (c == 0 ? 0 : c * ns_t - base_s));
+                if (cg < 0) {
+                  my_dy[c * a.Cout_pad + co] = 0.f;
+                  my_as[c * a.Cout_pad + co] = -1;
+                  continue;
+                }
+              }
+              const size_t o = (size_t)cg * a.Cout + co;
               asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
                                smem_u32(my_dy + c * a.Cout_pad + co)),
                            "l"(a.dysel + o)
@@ -527,10 +597,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
       const long long pos0 = (long long)tile * NT;
       const uint32_t d12 = tmem_base + (uint32_t)(s * w12);
       uint8_t *sdz = base + L.dz_off[s];
-      const int ns_mask = a.NS - 1;                         // NS is a power of two >= 16 (host)
+      TileClass tc{};
+      int ns_t = a.NS, shift_t = a.ns_shift;
+      if constexpr (CMP) {
+        tc = tile_class(s_meta, pos0, a.NS);
+        ns_t = tc.ns;
+        shift_t = 31 - __clz(ns_t);
+      }
+      const int ns_mask = ns_t - 1;                         // NS is a power of two >= 16 (host)
       const int base_s = (int)(pos0 & ns_mask);
-      const float *my_dy = s_dy + (size_t)s * (NT / 16) * a.Cout_pad;
-      const int *my_as = s_as + (size_t)s * (NT / 16) * a.Cout_pad;
+      const float *my_dy = s_dy + (size_t)s * kRC * a.Cout_pad;
+      const int *my_as = s_as + (size_t)s * kRC * a.Cout_pad;
       asm volatile("cp.async.wait_group 1;" ::: "memory");   // tile k's routes have landed
       mbar_wait(bar(4 + s), (uint32_t)(n & 1));
       tc_fence_after();
@@ -546,7 +623,27 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
           uint32_t r[32];
           cuda::ptx::tcgen05_ld_32x32b(r, d12 + lane_addr + (uint32_t)(ml * NT + ch * 32));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (ok) {
+          if (ok && CMP) {
+#pragma unroll
+            for (int sg = 0; sg < 4; ++sg) {   // 8 columns lie inside one centre, live or dead
+              const int colb = ch * 32 + sg * 8;
+              const int t0 = base_s + colb;
+              const int c = t0 >> shift_t;
+              const int s0 = t0 & ns_mask;
+              const float dyv = my_dy[c * a.Cout_pad + co];
+              const int as = my_as[c * a.Cout_pad + co] - s0;   // routed sample, relative
+              const float w0 = colb < tc.live ? 1.f : 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float dy = (i == as) ? dyv : 0.f;
+                const float wgt = (s0 + i == 0) ? w0 * (1.f + tc.wx) : w0;
+                const float v =
+                    fmaf(ca, dy, wgt * fmaf(cb, __uint_as_float(r[sg * 8 + i]), cc));
+                *reinterpret_cast<__nv_bfloat16 *>(
+                    sdz + bf_off(colb + i, co >> 3, NT) + (co & 7) * 2) = __float2bfloat16_rn(v);
+              }
+            }
+          } else if (ok) {
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {   // 16 columns = one centre (NS >= 16, aligned)
               const int t0 = base_s + ch * 32 + hf * 16;
@@ -575,21 +672,29 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
     if (kTop) {
       fetch_route(0, blockIdx.x);
       fetch_route(1, blockIdx.x + grid);
-      if ((int)blockIdx.x < a.num_tiles) produce_dz(0, blockIdx.x);
+      if ((int)blockIdx.x < num_tiles) produce_dz(0, blockIdx.x);
     }
-    for (int k = 0, tile = blockIdx.x; tile < a.num_tiles; tile += grid, ++k, ++ntiles) {
+    for (int k = 0, tile = blockIdx.x; tile < num_tiles; tile += grid, ++k, ++ntiles) {
       const int s = k & 1, n = k >> 1;
       const long long pos0 = (long long)tile * NT;
       const uint32_t d12 = tmem_base + (uint32_t)(s * w12);
       const int *s_idx = s_idx4 + (k & 3) * NT;
-      if (kTop && tile + grid < a.num_tiles) produce_dz(k + 1, tile + grid);
+      const int *s_cen = s_cen4 + (k & 3) * NT;
+      if (kTop && tile + grid < num_tiles) produce_dz(k + 1, tile + grid);
       mbar_wait(bar(8 + s), (uint32_t)(n & 1));
       tc_fence_after();
       if (a.do_dgrad) {
         int tile_b = 0, in_scene0 = 0;
-        if (kMode == 0) {
+        if (kMode == 0 && !CMP) {
           tile_b = (int)(pos0 / per_scene);
           in_scene0 = (int)(pos0 - (long long)tile_b * per_scene);
+        }
+        int ns_t = a.NS;   // CMP: class size of this tile's centres (s_idx / s_cen are global)
+        if constexpr (CMP) {
+          if (kMode == 0) {
+            ns_t = tile_class(s_meta, pos0, a.NS).ns;
+            in_scene0 = (int)(pos0 & 63);
+          }
         }
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
@@ -641,7 +746,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
                   if (a.normalize_xyz) v = __fdiv_rn(v, a.radius);
                   if (gx != nullptr) atomicAdd(gx + (size_t)s_idx[cc * 32 + i] * 3, v);
                   run += v;
-                  if (((ins + 1) % a.NS) == 0 || i == 31) {   // end of this centre's run
+                  if constexpr (CMP) {
+                    if (((ins + 1) & (ns_t - 1)) == 0 || i == 31) {   // end of this centre's run
+                      const int cg = s_cen[cc * 32 + i];
+                      if (a.g_new_xyz != nullptr && cg >= 0)
+                        atomicAdd(a.g_new_xyz + (size_t)cg * 3 + e, -run);
+                      run = 0.f;
+                    }
+                  } else if (((ins + 1) % a.NS) == 0 || i == 31) {   // end of this centre's run
                     if (a.g_new_xyz != nullptr)
                       atomicAdd(a.g_new_xyz + ((size_t)tile_b * a.NP + ins / a.NS) * 3 + e, -run);
                     run = 0.f;
@@ -842,14 +954,14 @@ namespace {
 // positions per tile for one backward launch: the widest tile whose two smem stages and two TMEM
 // stages fit; 0 = the layer does not fit at all
 int bwd_pick_nt(const Geometry &g, int Cout, int mode, int top, int do_dgrad, int NS, long long M,
-                long long per_scene) {
+                long long per_scene, int cmp = 0) {
   const int MTp = (g.KA + 1) >> 1, MTl = g.Cout_pad >> 7;
   if (MTp > 3) return 0;
   for (int nt : {128, 64, 32}) {
     if (M % nt) continue;
-    if (mode == 0 && per_scene % nt) continue;       // a tile must lie inside one scene
+    if (!cmp && mode == 0 && per_scene % nt) continue;   // a tile must lie inside one scene
     if (top && (nt % NS) != 0 && (NS % nt) != 0) continue;
-    const BwdSmem L = bwd_smem_layout(g.Kp, g.KA, g.WA, Cout, g.Cout_pad, nt, top);
+    const BwdSmem L = bwd_smem_layout(g.Kp, g.KA, g.WA, Cout, g.Cout_pad, nt, top, cmp);
     const int w12 = ((top && MTl > (do_dgrad ? MTp : 0)) ? MTl : (do_dgrad ? MTp : 0)) * nt;
     const int cols = 2 * w12 + MTl * g.KA * 64;
     if (L.total <= 227u * 1024u && cols <= 512) return nt;
@@ -867,6 +979,15 @@ extern "C" int b2r_sa_layer_bwd_supported(int B, int NP, int NS, int Cin, int Co
   const long long per_scene = (long long)NP * NS, M = (long long)B * per_scene;
   // worst case for the tile choice: every gradient requested (dgrad on)
   return bwd_pick_nt(g, Cout, gather ? 0 : 1, top, 1, NS, M, per_scene) > 0 ? 1 : 0;
+}
+
+extern "C" int b2r_sa_layer_bwd_tile(int B, int NP, int NS, int Cin, int Cout, int gather, int top,
+                                     int dgrad, int compact) {
+  if (B <= 0 || NP <= 0 || NS <= 0 || Cin <= 0 || Cout <= 0) return 0;
+  const Geometry g = bwd_geometry(Cout, Cin, gather);
+  const long long per_scene = (long long)NP * NS;
+  const long long M = compact ? b2r_compact_capacity(B, NP, NS) : (long long)B * per_scene;
+  return bwd_pick_nt(g, Cout, gather ? 0 : 1, top, dgrad, NS, M, per_scene, compact ? 1 : 0);
 }
 
 extern "C" long long b2r_mlp_weight_bf16_image_bytes(int Cout, int Cin, int gather) {
@@ -913,13 +1034,20 @@ extern "C" int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *d, void *stream) {
   a.Kp = g.Kp; a.KA = g.KA; a.WA = g.WA; a.Cout_pad = g.Cout_pad;
   a.ch8_shift = pow2_shift((((d->Cin - 3 + 7) & ~7) >> 3));
   a.ns_shift = pow2_shift(d->NS);
+  a.cidx = d->cidx; a.ccen = d->ccen; a.cmeta = d->cmeta;
+  const int cmp = d->cmeta != nullptr ? 1 : 0;
+  B2R_REQUIRE(!cmp || (d->cidx && d->ccen), "b2r_sa_layer_bwd: a plan needs cidx, ccen and cmeta");
+  if (cmp && !(d->NS == 16 || d->NS == 32 || d->NS == 64)) {
+    set_error("b2r_sa_layer_bwd: a compacted plan needs nsample 16/32/64 (got %d)", d->NS);
+    return B2R_ERR_UNSUPPORTED;
+  }
   if (a.top && a.ns_shift < 0) {
     set_error("b2r_sa_layer_bwd: the pooled top layer needs a power-of-two nsample (got %d)", d->NS);
     return B2R_ERR_UNSUPPORTED;
   }
   a.num_tiles = 0;
   if (d->mode == 0) {
-    B2R_REQUIRE(d->Cin >= 3 && d->xyz && d->new_xyz && d->idx && (d->feat_t || d->Cin == 3),
+    B2R_REQUIRE(d->Cin >= 3 && d->xyz && d->new_xyz && (d->idx || cmp) && (d->feat_t || d->Cin == 3),
                 "b2r_sa_layer_bwd: gather mode needs xyz, new_xyz, idx (and feat_t when Cin > 3)");
     a.do_dgrad = (d->g_feat_t != nullptr && d->Cin > 3) || d->g_xyz != nullptr ||
                  d->g_new_xyz != nullptr;
@@ -933,30 +1061,36 @@ extern "C" int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *d, void *stream) {
               "b2r_sa_layer_bwd: null weight image");
   // thin first layer without an input gradient (SA1: xyz / height are leaves): streaming kernel
   if (thin::bwd_applicable(d)) return thin::bwd_launch(d, stream);
-  const long long M = (long long)d->B * d->NP * d->NS;
+  // with a plan the launch is sized for the plan's CAPACITY; the live tile count is on the device
+  const long long M = cmp ? b2r_compact_capacity(d->B, d->NP, d->NS)
+                          : (long long)d->B * d->NP * d->NS;
   const long long per_scene = (long long)d->NP * d->NS;
   if (a.Cout_pad > 256 || (d->Cout % 8) != 0 || (d->mode == 1 && (d->Cin % 8) != 0)) {
     set_error("b2r_sa_layer_bwd: needs Cout %% 8 == 0, Cout <= 256, dense Cin %% 8 == 0 "
               "(Cin=%d Cout=%d)", d->Cin, d->Cout);
     return B2R_ERR_UNSUPPORTED;
   }
-  const int NT = bwd_pick_nt(g, d->Cout, d->mode, a.top, a.do_dgrad, d->NS, M, per_scene);
+  const int NT = bwd_pick_nt(g, d->Cout, d->mode, a.top, a.do_dgrad, d->NS, M, per_scene, cmp);
   if (NT == 0) {
     set_error("b2r_sa_layer_bwd: layer Cin=%d Cout=%d M=%lld does not fit shared memory / TMEM",
               d->Cin, d->Cout, M);
     return B2R_ERR_UNSUPPORTED;
   }
-  const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, NT, a.top);
+  const BwdSmem L = bwd_smem_layout(a.Kp, a.KA, a.WA, a.Cout, a.Cout_pad, NT, a.top, cmp);
   a.num_tiles = (int)(M / NT);
   int sms = kNumSMs;
   if (d->sm_limit > 0 && d->sm_limit < kNumSMs) sms = d->sm_limit;
   const int grid = a.num_tiles < sms ? a.num_tiles : sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define B2R_LAUNCH_BWD2(NTV, EWV, MV, TV, CV)                                                   \
+  do {                                                                                          \
+    B2R_CUDA(cudaFuncSetAttribute(sa_layer_bwd_kernel<NTV, EWV, MV, TV, CV>,                    \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));  \
+    sa_layer_bwd_kernel<NTV, EWV, MV, TV, CV><<<grid, kBwdThreads, L.total, st>>>(a);           \
+  } while (0)
 #define B2R_LAUNCH_BWD1(NTV, EWV, MV, TV)                                                       \
   do {                                                                                          \
-    B2R_CUDA(cudaFuncSetAttribute(sa_layer_bwd_kernel<NTV, EWV, MV, TV>,                        \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));  \
-    sa_layer_bwd_kernel<NTV, EWV, MV, TV><<<grid, kBwdThreads, L.total, st>>>(a);               \
+    if (cmp) B2R_LAUNCH_BWD2(NTV, EWV, MV, TV, true); else B2R_LAUNCH_BWD2(NTV, EWV, MV, TV, false); \
   } while (0)
   // the pooled top layer runs 8 epilogue warps (they also build DZ from the recomputed z) on
   // tiles of >= 64 positions
@@ -973,6 +1107,7 @@ extern "C" int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *d, void *stream) {
   else B2R_LAUNCH_BWD(32, 4);
 #undef B2R_LAUNCH_BWD
 #undef B2R_LAUNCH_BWD1
+#undef B2R_LAUNCH_BWD2
   B2R_CHECK_LAUNCH();
   return B2R_OK;
 }

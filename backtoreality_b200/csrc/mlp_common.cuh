@@ -145,15 +145,17 @@ struct GatherSrc {
   int normalize_xyz;
 };
 
+// s_cen != nullptr: compacted position space (csrc/compact.cu): s_idx holds GLOBAL source rows
+// and s_cen the global centre of every row (-1 = dead padding -> centre 0); pass b = 0.
 template <int NT, int NTHREADS, class OffFn>
 __device__ __forceinline__ void build_x_gather(const GatherSrc &g, int b, int in_scene0,
                                                const int *s_idx, uint8_t *s_x, int tid,
-                                               OffFn off) {
+                                               OffFn off, const int *s_cen = nullptr) {
   const int C = g.C, CHf = g.Cf4 >> 2;
   // relative xyz chunk: one thread per row, six independent loads
   for (int row = tid; row < NT; row += NTHREADS) {
     const int p = s_idx[row];
-    const int j = (in_scene0 + row) / g.NS;
+    const int j = s_cen != nullptr ? max(s_cen[row], 0) : (in_scene0 + row) / g.NS;
     const float *pp = g.xyz + ((size_t)b * g.N + p) * 3;
     const float *qq = g.new_xyz + ((size_t)b * g.NP + j) * 3;
     const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
@@ -206,6 +208,25 @@ __device__ __forceinline__ void build_x_gather(const GatherSrc &g, int b, int in
           make_uint4(to_tf32(f[0]), to_tf32(f[1]), to_tf32(f[2]), to_tf32(f[3]));
     }
   }
+}
+
+// ---------------------------------------------------------------- compacted position space --
+// Per-tile view of a b2r_compact_plan (csrc/compact.cu).  `m` = the plan's meta words 0..7 (class
+// ends, live ends), normally a shared-memory copy; pos0 = first position of the tile (a multiple
+// of 32 that never straddles a class).  Everything here is uniform across the CTA.
+struct TileClass {
+  int ns;      // class size of the tile's centres: 8, 16, 32 or 64 samples
+  int live;    // rows [0, live) of the tile are live (<= 0: all dead; may exceed the tile)
+  float wx;    // EXTRA weight of a centre's first sample in sums over positions: NS - ns
+};
+__device__ __forceinline__ TileClass tile_class(const int *m, long long pos0, int NS) {
+  const int p = (int)pos0;
+  const int c = (p >= m[0]) + (p >= m[1]) + (p >= m[2]);
+  TileClass t;
+  t.ns = 8 << c;
+  t.live = m[4 + c] - p;
+  t.wx = (float)(NS - t.ns);
+  return t;
 }
 
 inline int pow2_shift(int v) {   // log2(v) if v is a power of two (v >= 1), else -1

@@ -50,16 +50,25 @@ struct ThinArgs {
   // backward
   const float *gr, *zin, *coef_a, *coef_b, *coef_c;
   float *dW;
+  // compacted position space (csrc/compact.cu) or NULL; Mcap = its capacity (sizes the grid)
+  const int *cidx, *ccen, *cmeta;
 };
 
 // one lane = one position of the warp's 32-position chunk: its input row in the reference's
 // channel order [dx, dy, dz, f0 .. fC-1]
-template <int KM>
+template <int KM, bool CMP>
 __device__ __forceinline__ void gather_row(const ThinArgs &a, long long pos, float (&x)[KM]) {
-  const int b = (int)(pos / a.per_scene);
-  const long long centre = pos / a.NS;
-  const int p = __ldg(a.idx + pos);
-  const float *pp = a.xyz + ((size_t)b * a.N + p) * 3;
+  size_t prow;        // global source row
+  long long centre;   // global centre
+  if constexpr (CMP) {
+    prow = (size_t)__ldg(a.cidx + pos);
+    centre = max(__ldg(a.ccen + pos), 0);   // dead padding rows: any valid centre
+  } else {
+    const int b = (int)(pos / a.per_scene);
+    centre = pos / a.NS;
+    prow = (size_t)b * a.N + __ldg(a.idx + pos);
+  }
+  const float *pp = a.xyz + prow * 3;
   const float *qq = a.new_xyz + (size_t)centre * 3;
   float d0 = __fsub_rn(__ldg(pp), __ldg(qq));
   float d1 = __fsub_rn(__ldg(pp + 1), __ldg(qq + 1));
@@ -70,19 +79,26 @@ __device__ __forceinline__ void gather_row(const ThinArgs &a, long long pos, flo
     d2 = __fdiv_rn(d2, a.radius);
   }
   x[0] = d0; x[1] = d1; x[2] = d2;
-  const float *ff = a.feat_t + ((size_t)b * a.N + p) * a.C;
+  const float *ff = a.feat_t + prow * a.C;
 #pragma unroll
   for (int c = 0; c < KM - 3; ++c) x[3 + c] = c < a.C ? __ldg(ff + c) : 0.f;
 }
 
 // LP lanes per position (Cout = 4 * LP); PPW = 32 / LP positions per warp instruction;
 // KM = register-array extent of the input row (4 for Cin <= 4, else 8)
-template <int LP, int KM>
+template <int LP, int KM, bool CMP>
 __global__ void __launch_bounds__(kThreads, kCtasPerSM) thin_fwd_kernel(const ThinArgs a) {
   constexpr int PPW = 32 / LP, ITERS = 32 / PPW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LP, c4 = (lane % LP) * 4;   // position within the instruction, channel
   __shared__ double s_red[kWarps][2][LP * 4];
+  __shared__ int s_meta[8];
+  long long M = a.M;
+  if constexpr (CMP) {
+    M = __ldg(a.cmeta + 8);
+    if (threadIdx.x < 8) s_meta[threadIdx.x] = __ldg(a.cmeta + threadIdx.x);
+    __syncthreads();
+  }
 
   // this lane's 4 x K weights, from the TF32 image (packed K order: features, pad, dx dy dz)
   float w[4][KM];
@@ -99,16 +115,22 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) thin_fwd_kernel(const Th
     }
 
   double acc_s[4] = {0, 0, 0, 0}, acc_ss[4] = {0, 0, 0, 0};
-  const long long nchunks = a.M >> 5, cstride = (long long)gridDim.x * kWarps;
+  const long long nchunks = M >> 5, cstride = (long long)gridDim.x * kWarps;
   long long chunk = (long long)blockIdx.x * kWarps + warp;
   float xn[KM];   // the NEXT chunk's row: its dependent index -> point loads overlap this chunk
-  if (chunk < nchunks) gather_row(a, (chunk << 5) + lane, xn);
+  if (chunk < nchunks) gather_row<KM, CMP>(a, (chunk << 5) + lane, xn);
   for (; chunk < nchunks; chunk += cstride) {
     const long long pos0 = chunk << 5;
     float x[KM];
 #pragma unroll
     for (int k = 0; k < KM; ++k) x[k] = __uint_as_float(to_tf32(xn[k]));
-    if (chunk + cstride < nchunks) gather_row(a, ((chunk + cstride) << 5) + lane, xn);
+    if (chunk + cstride < nchunks) gather_row<KM, CMP>(a, ((chunk + cstride) << 5) + lane, xn);
+    mlp::TileClass tc{};
+    int p64 = 0;
+    if constexpr (CMP) {
+      tc = mlp::tile_class(s_meta, pos0, a.NS);
+      p64 = (int)(pos0 & 63);
+    }
     float ts[4] = {0, 0, 0, 0}, tss[4] = {0, 0, 0, 0};
     float *zrow = a.z + (size_t)pos0 * a.Cout + c4;
 #pragma unroll 4
@@ -118,6 +140,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) thin_fwd_kernel(const Th
 #pragma unroll
       for (int k = 0; k < KM; ++k) xr[k] = __shfl_sync(0xffffffffu, x[k], src);
       float zz[4];
+      float wgt = 1.f;   // CMP: multiplicity of this position in sums over the padded positions
+      if constexpr (CMP)
+        wgt = src < tc.live ? ((((p64 + src) & (tc.ns - 1)) == 0) ? 1.f + tc.wx : 1.f) : 0.f;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float s = 0.f;
@@ -125,8 +150,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) thin_fwd_kernel(const Th
         for (int k = 0; k < KM; ++k)
           if (k < a.K) s = fmaf(w[e][k], xr[k], s);
         zz[e] = s;
-        ts[e] += s;
-        tss[e] = fmaf(s, s, tss[e]);
+        if constexpr (CMP) {
+          ts[e] = fmaf(wgt, s, ts[e]);
+          tss[e] = fmaf(wgt * s, s, tss[e]);
+        } else {
+          ts[e] += s;
+          tss[e] = fmaf(s, s, tss[e]);
+        }
       }
       stg_stream_v4(reinterpret_cast<float4 *>(zrow + (size_t)src * a.Cout),
                     make_float4(zz[0], zz[1], zz[2], zz[3]));
@@ -162,12 +192,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) thin_fwd_kernel(const Th
   }
 }
 
-template <int LP, int KM>
+template <int LP, int KM, bool CMP>
 __global__ void __launch_bounds__(kThreads, kCtasPerSM) thin_bwd_kernel(const ThinArgs a) {
   constexpr int PPW = 32 / LP, ITERS = 32 / PPW, UN = 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LP, c4 = (lane % LP) * 4;
   __shared__ float s_red[kWarps][LP * 4][KM];
+  __shared__ int s_meta[8];
+  long long M = a.M;
+  if constexpr (CMP) {
+    M = __ldg(a.cmeta + 8);
+    if (threadIdx.x < 8) s_meta[threadIdx.x] = __ldg(a.cmeta + threadIdx.x);
+    __syncthreads();
+  }
 
   float ca[4], cb[4], cc[4];
 #pragma unroll
@@ -182,16 +219,22 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) thin_bwd_kernel(const Th
 #pragma unroll
     for (int k = 0; k < KM; ++k) acc[e][k] = 0.f;
 
-  const long long nchunks = a.M >> 5, cstride = (long long)gridDim.x * kWarps;
+  const long long nchunks = M >> 5, cstride = (long long)gridDim.x * kWarps;
   long long chunk = (long long)blockIdx.x * kWarps + warp;
   float xn[KM];
-  if (chunk < nchunks) gather_row(a, (chunk << 5) + lane, xn);
+  if (chunk < nchunks) gather_row<KM, CMP>(a, (chunk << 5) + lane, xn);
   for (; chunk < nchunks; chunk += cstride) {
     const long long pos0 = chunk << 5;
     float x[KM];
 #pragma unroll
     for (int k = 0; k < KM; ++k) x[k] = xn[k];
-    if (chunk + cstride < nchunks) gather_row(a, ((chunk + cstride) << 5) + lane, xn);
+    if (chunk + cstride < nchunks) gather_row<KM, CMP>(a, ((chunk + cstride) << 5) + lane, xn);
+    mlp::TileClass tc{};
+    int p64 = 0;
+    if constexpr (CMP) {
+      tc = mlp::tile_class(s_meta, pos0, a.NS);
+      p64 = (int)(pos0 & 63);
+    }
     const int4 *grow = reinterpret_cast<const int4 *>(a.gr + (size_t)pos0 * a.Cout + c4);
     const int4 *zrow = reinterpret_cast<const int4 *>(a.zin + (size_t)pos0 * a.Cout + c4);
     const size_t rstride = (size_t)a.Cout >> 2;   // row stride in int4
@@ -214,9 +257,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM) thin_bwd_kernel(const Th
                              __int_as_float(g[u].z), __int_as_float(g[u].w)};
         const float zv[4] = {__int_as_float(zz[u].x), __int_as_float(zz[u].y),
                              __int_as_float(zz[u].z), __int_as_float(zz[u].w)};
+        // CMP: gr carries the position's multiplicity already (it came through the weighted dz
+        // of the layers above); the dense BatchNorm-backward term is once per padded position
+        float wgt = 1.f;
+        if constexpr (CMP)
+          wgt = src < tc.live ? ((((p64 + src) & (tc.ns - 1)) == 0) ? 1.f + tc.wx : 1.f) : 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float dz = fmaf(ca[e], gv[e], fmaf(cb[e], zv[e], cc[e]));
+          const float dz = CMP ? fmaf(ca[e], gv[e], wgt * fmaf(cb[e], zv[e], cc[e]))
+                               : fmaf(ca[e], gv[e], fmaf(cb[e], zv[e], cc[e]));
 #pragma unroll
           for (int k = 0; k < KM; ++k)
             if (k < a.K) acc[e][k] = fmaf(dz, xr[k], acc[e][k]);
@@ -280,12 +329,19 @@ int fwd_launch(const b2r_sa_layer *d, void *stream) {
   a.Cout_pad = (d->Cout + 127) & ~127;
   a.Cf4 = (a.C + 3) & ~3;
   a.z = d->z; a.stats = d->stats;
-  const int grid = grid_for(a.M, d->sm_limit);
+  a.cidx = d->cidx; a.ccen = d->ccen; a.cmeta = d->cmeta;
+  const bool cmp = d->cmeta != nullptr;
+  const int grid = grid_for(cmp ? b2r_compact_capacity(d->B, d->NP, d->NS) : a.M, d->sm_limit);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define B2R_THIN(LPV)                                                        \
-  do {                                                                     \
-    if (a.K <= 4) thin_fwd_kernel<LPV, 4><<<grid, kThreads, 0, st>>>(a);   \
-    else thin_fwd_kernel<LPV, 8><<<grid, kThreads, 0, st>>>(a);            \
+#define B2R_THIN(LPV)                                                                  \
+  do {                                                                               \
+    if (cmp) {                                                                       \
+      if (a.K <= 4) thin_fwd_kernel<LPV, 4, true><<<grid, kThreads, 0, st>>>(a);     \
+      else thin_fwd_kernel<LPV, 8, true><<<grid, kThreads, 0, st>>>(a);              \
+    } else {                                                                         \
+      if (a.K <= 4) thin_fwd_kernel<LPV, 4, false><<<grid, kThreads, 0, st>>>(a);    \
+      else thin_fwd_kernel<LPV, 8, false><<<grid, kThreads, 0, st>>>(a);             \
+    }                                                                                \
   } while (0)
   switch (d->Cout) {
     case 32: B2R_THIN(8); break;
@@ -315,12 +371,19 @@ int bwd_launch(const b2r_sa_layer_bwd_desc *d, void *stream) {
   a.gr = d->gr; a.zin = d->z;
   a.coef_a = d->coef_a; a.coef_b = d->coef_b; a.coef_c = d->coef_c;
   a.dW = d->dW;
-  const int grid = grid_for(a.M, d->sm_limit);
+  a.cidx = d->cidx; a.ccen = d->ccen; a.cmeta = d->cmeta;
+  const bool cmp = d->cmeta != nullptr;
+  const int grid = grid_for(cmp ? b2r_compact_capacity(d->B, d->NP, d->NS) : a.M, d->sm_limit);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define B2R_THIN(LPV)                                                        \
-  do {                                                                     \
-    if (a.K <= 4) thin_bwd_kernel<LPV, 4><<<grid, kThreads, 0, st>>>(a);   \
-    else thin_bwd_kernel<LPV, 8><<<grid, kThreads, 0, st>>>(a);            \
+#define B2R_THIN(LPV)                                                                  \
+  do {                                                                               \
+    if (cmp) {                                                                       \
+      if (a.K <= 4) thin_bwd_kernel<LPV, 4, true><<<grid, kThreads, 0, st>>>(a);     \
+      else thin_bwd_kernel<LPV, 8, true><<<grid, kThreads, 0, st>>>(a);              \
+    } else {                                                                         \
+      if (a.K <= 4) thin_bwd_kernel<LPV, 4, false><<<grid, kThreads, 0, st>>>(a);    \
+      else thin_bwd_kernel<LPV, 8, false><<<grid, kThreads, 0, st>>>(a);             \
+    }                                                                                \
   } while (0)
   switch (d->Cout) {
     case 32: B2R_THIN(8); break;

@@ -17,6 +17,7 @@ Math: TF32 operands (round-to-nearest), FP32 accumulate -- the precision the ref
 runs at by default (cuDNN TF32 convolutions on sm_80+).
 """
 import ctypes
+import os
 
 import torch
 
@@ -128,6 +129,39 @@ def _take(weight, kind):
     return image
 
 
+# Pad-free position space (csrc/compact.cu): the ball query pads a centre's unused slots with
+# copies of its first hit; the fused block computes each centre on its first 8/16/32/64 >= cnt
+# samples only and weights sample 0 by the number of copies it stands for.  Same results up to
+# fp32 summation order; on ScanNet-shaped scenes SA1 keeps ~73 % and SA2 ~39 % of its positions.
+# Used for blocks with nsample >= COMPACT_MIN_NS (with 16 samples nearly every ball is full).
+COMPACT = os.environ.get("B2R_COMPACT", "1") not in ("0", "")
+COMPACT_MIN_NS = 32
+PLAN_KEYS = ("cidx", "ccen", "cmeta")
+
+
+def compact_wanted(nsample):
+    return COMPACT and nsample in (32, 64) and nsample >= COMPACT_MIN_NS
+
+
+def compact_plan(idx, N):
+    """idx (B,NP,NS) int32 ball-query output (or ANY index tensor: a centre's trailing run of
+    copies of its sample 0 is what gets dropped) over N source points per scene ->
+    {"cidx", "ccen" (capacity ints each), "cmeta" (16 ints)} for sa_block(..., plan=).  Three tiny
+    launches on the current stream; no host synchronisation (sizes stay on the device)."""
+    B, NP, NS = idx.shape
+    lib = _lib.lib()
+    cap = int(lib.b2r_compact_capacity(B, NP, NS))
+    dev = idx.device
+    cidx = torch.empty(cap, dtype=torch.int32, device=dev)
+    ccen = torch.empty(cap, dtype=torch.int32, device=dev)
+    cmeta = torch.empty(16, dtype=torch.int32, device=dev)
+    ws = torch.empty(int(lib.b2r_compact_workspace_bytes(B, NP)), dtype=torch.uint8, device=dev)
+    _lib.check(lib.b2r_compact_plan(_ptr(idx), B, int(N), NP, NS, _ptr(cidx), _ptr(ccen),
+                                    _ptr(cmeta), _ptr(ws), _ext._stream()), "compact_plan")
+    _ext.LAUNCHES += 3
+    return {"cidx": cidx, "ccen": ccen, "cmeta": cmeta}
+
+
 def supported(mlp_module, xyz, features, idx, pooling="max"):
     """True when the fused kernels cover this block, forward AND backward (otherwise callers use
     the unfused path).  The shape rules live in the library: b2r_sa_layer_fwd_supported /
@@ -185,19 +219,21 @@ def _bwd_bytes(B, N, NP, NS, Cin, Cout, gather, top, dgrad):
 
 
 def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module, training,
-                   want_point_major=True, save=None, sm_limit=0):
+                   want_point_major=True, save=None, sm_limit=0, plan=None):
     """Run the fused block.
 
     xyz (B,N,3), new_xyz (B,NP,3), feat_t (B,N,C) POINT-major features or None, idx (B,NP,NS).
     Returns (out_cm (B,Cl,NP), out_pm (B,NP,Cl) or None).  When `save` is a dict it receives what
     a backward pass needs (raw z per layer, BN mean/invstd/scale/shift, pooled max/min/arg).
+    `plan`: a compact_plan(idx, N) -- the block then runs in its pad-free position space.
     """
     lib = _lib.lib()
     st = _ext._stream()
     dev = xyz.device
     B, N = xyz.shape[0], xyz.shape[1]
     NP, NS = idx.shape[1], idx.shape[2]
-    M = B * NP * NS
+    M = B * NP * NS                  # positions of the padded computation (BatchNorm count)
+    rows = M if plan is None else int(plan["cidx"].shape[0])   # rows of the z buffers
     blocks = list(mlp_module)
     L = len(blocks)
     z_prev = scale = shift = None
@@ -232,6 +268,8 @@ def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
             d.z_prev, d.scale_prev, d.shift_prev = _ptr(z_prev), _ptr(scale), _ptr(shift)
         d.w_image = _ptr(image)
         d.sm_limit = int(sm_limit)
+        if plan is not None:
+            d.cidx, d.ccen, d.cmeta = _ptr(plan["cidx"]), _ptr(plan["ccen"]), _ptr(plan["cmeta"])
         z = None
         if last:
             zmax = torch.empty((B * NP, Cout), dtype=torch.float32, device=dev)
@@ -240,7 +278,7 @@ def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
             amin = torch.empty_like(amax)
             d.zmax, d.zmin, d.amax, d.amin = _ptr(zmax), _ptr(zmin), _ptr(amax), _ptr(amin)
         else:
-            z = torch.empty((M, Cout), dtype=torch.float32, device=dev)
+            z = torch.empty((rows, Cout), dtype=torch.float32, device=dev)
             d.z = _ptr(z)
         d.stats = _ptr(stats)
         with _ext._timed("sa_layer_fwd", _fwd_bytes(B, N, NP, NS, Cin, Cout, i == 0, last)):
@@ -273,7 +311,8 @@ def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
                                      _ptr(out_cm), _ptr(out_pm), st), "pool_finalize")
     _ext.LAUNCHES += 1
     if save is not None:
-        save.update(zs=zs, bn=bn_saved, zmax=zmax, zmin=zmin, amax=amax, amin=amin, images=images)
+        save.update(zs=zs, bn=bn_saved, zmax=zmax, zmin=zmin, amax=amax, amin=amin, images=images,
+                    plan=plan)
     return out_cm, out_pm
 
 
@@ -308,6 +347,8 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
     B, N = xyz.shape[0], xyz.shape[1]
     NP, NS = idx.shape[1], idx.shape[2]
     M = B * NP * NS
+    plan = saved.get("plan")
+    rows = M if plan is None else int(plan["cidx"].shape[0])
     L = len(weights)
     zs, bn, images = saved["zs"], saved["bn"], saved["images"]
     f32 = dict(dtype=torch.float32, device=dev)
@@ -348,6 +389,8 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
         b.B, b.N, b.NP, b.NS, b.Cin, b.Cout = B, N, NP, NS, Cin, Cout
         b.mode = 0 if l == 0 else 1
         b.sm_limit = int(sm_limit)
+        if plan is not None:
+            b.cidx, b.ccen, b.cmeta = _ptr(plan["cidx"]), _ptr(plan["ccen"]), _ptr(plan["cmeta"])
         if l == top:   # z is recomputed inside the kernel from the layer's input
             b.dysel, b.asel = _ptr(dysel), _ptr(asel)
         else:
@@ -372,7 +415,7 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
             need_dgrad = g_feat_t is not None or need_xyz or need_new_xyz
         else:
             b.z_prev, b.scale_prev, b.shift_prev = _ptr(zs[l - 1]), _ptr(bn[l - 1][2]), _ptr(bn[l - 1][3])
-            gr_prev = torch.empty((M, Cin), **f32)
+            gr_prev = torch.empty((rows, Cin), **f32)
             stats_prev = stats_all[s_off[l - 1]:s_off[l]]
             b.gr_prev, b.stats_prev = _ptr(gr_prev), _ptr(stats_prev)
         image = None
@@ -407,7 +450,7 @@ class _FusedSABlock(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xyz, new_xyz, features, features_pm, idx, radius, normalize_xyz, mlp_module,
-                training, sm_limit, want_pm, *params):
+                training, sm_limit, want_pm, plan, *params):
         if features_pm is not None:
             feat_t = features_pm                       # (B,N,C) from the previous block
         elif features is None:
@@ -422,7 +465,7 @@ class _FusedSABlock(torch.autograd.Function):
         fwd_limit, bwd_limit = sm_limit if isinstance(sm_limit, tuple) else (sm_limit, 0)
         out_cm, out_pm = sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz,
                                         mlp_module, training, want_point_major=bool(want_pm),
-                                        save=save, sm_limit=fwd_limit)
+                                        save=save, sm_limit=fwd_limit, plan=plan)
         ctx.set_materialize_grads(False)
         if need:
             ctx.saved = (xyz, new_xyz, feat_t, idx, float(radius), bool(normalize_xyz),
@@ -437,7 +480,7 @@ class _FusedSABlock(torch.autograd.Function):
     def backward(ctx, g_cm, g_pm):
         xyz, new_xyz, feat_t, idx, radius, normalize_xyz, training, save, params = ctx.saved
         L = len(params) // 3
-        n_in = 11
+        n_in = 12
         if g_cm is None and g_pm is None:
             return (None,) * (n_in + 3 * L)
         weights = [params[3 * i].detach().reshape(params[3 * i].shape[0], -1) for i in range(L)]
@@ -464,18 +507,22 @@ class _FusedSABlock(torch.autograd.Function):
 
 
 def sa_block(xyz, new_xyz, features, idx, radius, normalize_xyz, mlp_module, training,
-             sm_limit=0, features_pm=None, want_pm=False):
+             sm_limit=0, features_pm=None, want_pm=False, plan=None):
     """Differentiable fused SA block: returns (new_features (B, mlp[-1], npoint), the same
     point-major (B, npoint, mlp[-1]) when `want_pm`, else None).  `features_pm` (B,N,C): the
     input features point-major (a previous block's second output) -- used instead of `features`.
     sm_limit > 0 caps the forward kernels' persistent grid (SMs left to a concurrent geometry
     stream); a tuple (forward cap, backward cap) also caps the backward kernels (the pipelined
-    step, where the NEXT batch's geometry runs beside this batch's whole forward and backward)."""
+    step, where the NEXT batch's geometry runs beside this batch's whole forward and backward).
+    plan: compact_plan(idx, N) computed ahead of time (geometry pre-pass); by default one is built
+    here when the block qualifies (compact_wanted)."""
+    if plan is None and compact_wanted(idx.shape[2]):
+        plan = compact_plan(idx, xyz.shape[1])
     params = []
     for blk in mlp_module:
         params += [blk.conv.weight, blk.bn.bn.weight, blk.bn.bn.bias]
     return _FusedSABlock.apply(xyz, new_xyz, features, features_pm, idx, radius, normalize_xyz,
-                               mlp_module, training, sm_limit, bool(want_pm), *params)
+                               mlp_module, training, sm_limit, bool(want_pm), plan, *params)
 
 
 NUM_SMS = 148   # B200

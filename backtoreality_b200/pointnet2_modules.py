@@ -77,7 +77,7 @@ class _SAVotesBase(nn.Module):
                 and not g.sample_uniformly and not g.ret_unique_cnt)
 
     def _abstract(self, xyz, new_xyz, features, idx=None, sm_limit=0, features_pm=None,
-                  want_pm=False):
+                  want_pm=False, plan=None):
         """-> (new_features (B,C,npoint), the same point-major or None).  features_pm / want_pm:
         point-major hand-over between consecutive fused blocks (fused_sa.sa_block)."""
         if self.fusable(xyz):
@@ -89,7 +89,7 @@ class _SAVotesBase(nn.Module):
                 return fused_sa.sa_block(xyz, new_xyz, features, idx, self.radius,
                                          self.normalize_xyz, self.mlp_module, self.training,
                                          sm_limit=sm_limit, features_pm=features_pm,
-                                         want_pm=want_pm)
+                                         want_pm=want_pm, plan=plan)
         grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features)
         new_features = self.mlp_module(grouped_features)  # (B, mlp[-1], npoint, nsample)
         return _pool(new_features, grouped_xyz, self.pooling, self.sigma, self.nsample), None
@@ -109,10 +109,13 @@ class PointnetSAModuleVotes(_SAVotesBase):
             # (backbone_module.Pointnet2Backbone.geometry_prepass): wait for them, run the MLP
             if geometry.get("event") is not None:
                 torch.cuda.current_stream().wait_event(geometry["event"])
+            plan = None
+            if fused_sa.COMPACT and "cmeta" in geometry:   # pad-free position space, pre-built
+                plan = {k: geometry[k] for k in fused_sa.PLAN_KEYS}
             new_features, out_pm = self._abstract(
                 xyz, geometry["new_xyz"], features, idx=geometry["idx"],
                 sm_limit=geometry.get("sm_limit", 0), features_pm=geometry.get("features_pm"),
-                want_pm=geometry.get("want_pm", False))
+                want_pm=geometry.get("want_pm", False), plan=plan)
             if out_pm is not None:
                 geometry["out_pm"] = out_pm      # for the next block (Pointnet2Backbone.forward)
             return geometry["new_xyz"], new_features, geometry["inds"]

@@ -99,9 +99,11 @@ class PipelinedTrainStep:
         caps = [(0, narrow) if lv <= start_after_level else (wide, wide) for lv in range(4)]
         return caps, (wide, wide)
 
+    PLAN_KEYS = ("cidx", "ccen", "cmeta")    # levels computed pad-free (fused_sa.compact_plan)
+
     @classmethod
     def _keys(cls, level):
-        return cls.GEO_KEYS + tuple(k for k in cls.FP_KEYS if k in level)
+        return cls.GEO_KEYS + tuple(k for k in cls.PLAN_KEYS + cls.FP_KEYS if k in level)
 
     def __init__(self, backbone, step_fn, first_batch, warmup=3, fps_cluster=4, sm_caps=None,
                  after_warmup_step=None, start_after_level=1):

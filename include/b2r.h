@@ -207,6 +207,13 @@ typedef struct b2r_sa_layer {
   int *amax, *amin;         /* epilogue 1: (B*NP,Cout) sample index in [0,NS) */
   int sm_limit;             /* 0 = one CTA on every SM; else at most this many CTAs, leaving the
                                other SMs to kernels on concurrent streams (geometry pre-pass) */
+  /* Pad-free position space from b2r_compact_plan (all three, or all NULL).  When set, a
+   * "position" is an entry of the plan instead of (b, centre, sample): mode 0 gathers through
+   * cidx / ccen instead of idx, z / z_prev hold b2r_compact_capacity(B,NP,NS) rows, statistics
+   * weight every centre's first sample by 1 + (NS - class size) so they equal the padded sums,
+   * and the number of tiles is read from cmeta on the device.  amax / amin are then sample
+   * indices inside the centre's class-size run (consistent with b2r_sa_layer_bwd). */
+  const int *cidx, *ccen, *cmeta;
 } b2r_sa_layer;
 
 B2R_API long long b2r_mlp_weight_image_bytes(int Cout, int Cin, int gather);
@@ -217,6 +224,11 @@ B2R_API int b2r_sa_layer_fwd(const b2r_sa_layer *desc, void *stream);
 /* 1 when b2r_sa_layer_fwd covers a layer of this shape, 0 otherwise (same rules as the launch). */
 B2R_API int b2r_sa_layer_fwd_supported(int B, int NP, int NS, int Cin, int Cout, int gather,
                                        int pooled);
+
+/* Positions per tile the launch would use for a layer of this shape (0 = unsupported); compact:
+ * with a b2r_compact_plan.  Diagnostic (DESIGN.md tile table, tests). */
+B2R_API int b2r_sa_layer_fwd_tile(int B, int NP, int NS, int Cin, int Cout, int gather, int pooled,
+                                  int compact);
 
 /* BatchNorm bookkeeping from accumulated statistics (replaces the statistics half of
  * nn.BatchNorm2d in training mode, reference pytorch_utils.py:55-58): scale = gamma*invstd,
@@ -279,6 +291,9 @@ typedef struct b2r_sa_layer_bwd_desc {
   float *g_xyz;             /* mode 0: (B,N,3) ACCUMULATED; NULL = not needed */
   float *g_new_xyz;         /* mode 0: (B,NP,3) ACCUMULATED; NULL = not needed */
   int sm_limit;             /* as b2r_sa_layer.sm_limit: 0 = every SM, else at most this many CTAs */
+  const int *cidx, *ccen, *cmeta; /* as b2r_sa_layer: the forward's plan (gr, z, z_prev, gr_prev
+                               are then in its position space; gradients carry the positions'
+                               multiplicities, see csrc/compact.cu) */
 } b2r_sa_layer_bwd_desc;
 
 B2R_API long long b2r_mlp_weight_bf16_image_bytes(int Cout, int Cin, int gather);
@@ -289,6 +304,9 @@ B2R_API int b2r_sa_layer_bwd(const b2r_sa_layer_bwd_desc *desc, void *stream);
  * 0 otherwise: lets the host decide BEFORE the forward whether to take the fused path. */
 B2R_API int b2r_sa_layer_bwd_supported(int B, int NP, int NS, int Cin, int Cout, int gather,
                                        int top);
+
+B2R_API int b2r_sa_layer_bwd_tile(int B, int NP, int NS, int Cin, int Cout, int gather, int top,
+                                  int dgrad, int compact);
 
 /* dout_cm (B,C,NP) and/or dout_pm (B,NP,C) (summed; either may be NULL) -> dysel (B*NP,C),
  * asel (B*NP,C), stats (2,C) double ACCUMULATED: sum(dysel), sum(dysel * zsel). */
@@ -304,6 +322,26 @@ B2R_API int b2r_bn_bwd_finalize(const double *stats, int C, double count, const 
                                 const float *mean, const float *invstd, int training,
                                 float *coef_a, float *coef_b, float *coef_c, float *k1, float *k2,
                                 float *gs, float *dgamma, float *dbeta, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pad-free position space of a set-abstraction block (csrc/compact.cu).
+ *
+ * The reference's ball query pads a centre's unused slots with copies of its first hit
+ * (src/ball_query_gpu.cu:38-46) and QueryAndGroup + SharedMLP + max_pool2d
+ * (pointnet2_modules.py:245-267) then compute every copy.  A copy has the same activations as
+ * sample 0 in every layer, so the fused block may compute each centre on its first
+ * u = 8/16/32/64 >= cnt samples only (cnt = 1 + last s with idx[s] != idx[0]) and give sample 0
+ * the weight 1 + (NS - u) in every sum over positions: same results up to fp32 summation order.
+ * b2r_compact_plan orders the centres by (u, centre id) and writes, per position p of that
+ * space: cidx[p] = b*N + idx (global source row), ccen[p] = b*NP + j (global centre, -1 = dead
+ * padding); meta (16 ints): [0..3] cumulative end of the classes 8/16/32/64 (each padded to a
+ * multiple of 128 positions), [4..7] end of the live positions of each class, [8] total
+ * positions, [10..13] centres per class.  NS must be 16, 32 or 64.
+ * cidx / ccen hold b2r_compact_capacity(B,NP,NS) ints; workspace b2r_compact_workspace_bytes. */
+B2R_API long long b2r_compact_capacity(int B, int NP, int NS);
+B2R_API long long b2r_compact_workspace_bytes(int B, int NP);
+B2R_API int b2r_compact_plan(const int *idx, int B, int N, int NP, int NS, int *cidx, int *ccen,
+                             int *meta, void *workspace, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Loss-side nearest-neighbour matching: the two arg-min vectors of

@@ -131,9 +131,11 @@ def _unfused(sa, xyz, new_xyz, feats):
                                  dict(N=1024, C=256, npoint=256, radius=0.3, nsample=16, mlp=[256, 128, 128, 128]),
                                  dict(N=3000, C=0, npoint=256, radius=0.3, nsample=16, mlp=[0, 64, 64, 128])])
 @pytest.mark.parametrize("training", [False, True])
-def test_fused_block_vs_unfused_module(cuda, cfg, training):
+@pytest.mark.parametrize("compact", [False, True])
+def test_fused_block_vs_unfused_module(cuda, cfg, training, compact, monkeypatch):
     import copy
     from backtoreality_b200 import fused_sa, pointnet2_utils, scenes
+    monkeypatch.setattr(fused_sa, "COMPACT", compact)
     from backtoreality_b200.pointnet2_modules import PointnetSAModuleVotes
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
@@ -163,8 +165,10 @@ def test_fused_block_vs_unfused_module(cuda, cfg, training):
         with torch.no_grad():
             want = _unfused(ref, xyz, new_xyz, feats)
             feat_t = fused_sa.to_point_major(feats) if feats is not None else None
+            plan = (fused_sa.compact_plan(idx, cfg["N"])
+                    if fused_sa.compact_wanted(cfg["nsample"]) else None)
             got, got_pm = fused_sa.sa_mlp_forward(xyz, new_xyz, feat_t, idx, cfg["radius"], True,
-                                                  sa.mlp_module, training)
+                                                  sa.mlp_module, training, plan=plan)
         assert got.shape == want.shape
         assert rel_l2(got.cpu().numpy(), want.cpu().numpy()) < 5e-3
         assert torch.equal(got_pm, got.transpose(1, 2).contiguous())
@@ -317,11 +321,14 @@ def test_gather_layer_backward(cuda, C, Cout, N, NP, NS, norm, gx):
                                  dict(N=1024, C=256, npoint=256, radius=0.3, nsample=16, mlp=[256, 128, 128, 128]),
                                  dict(N=3000, C=0, npoint=256, radius=0.3, nsample=16, mlp=[0, 64, 64, 128])])
 @pytest.mark.parametrize("training", [False, True])
-def test_fused_block_backward_vs_unfused_module(cuda, cfg, training):
+@pytest.mark.parametrize("compact", [False, True])
+def test_fused_block_backward_vs_unfused_module(cuda, cfg, training, compact, monkeypatch):
     """PointnetSAModuleVotes fwd+bwd: fused tcgen05 path (TF32) against the unfused fp32 path
-    (QueryAndGroup kernel + cuDNN fp32 SharedMLP + max_pool2d) with identical parameters."""
+    (QueryAndGroup kernel + cuDNN fp32 SharedMLP + max_pool2d) with identical parameters, in the
+    padded and in the pad-free position space (csrc/compact.cu; blocks with nsample >= 32)."""
     import copy
     from backtoreality_b200 import fused_sa, scenes
+    monkeypatch.setattr(fused_sa, "COMPACT", compact)
     from backtoreality_b200.pointnet2_modules import PointnetSAModuleVotes
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
@@ -540,3 +547,198 @@ def test_fused_block_single_scene_batch(cuda):
     finally:
         fused_sa.ENABLED = True
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+# ------------------------------------------- pad-free position space (csrc/compact.cu) --------
+def _padded_idx(g, B, N, NP, NS, full_frac=0.2):
+    """Ball-query-shaped indices: `cnt` ascending distinct hits, then copies of the first one
+    (reference ball_query_gpu.cu:38-46).  A share of the centres is full, one per scene has a
+    single hit, one repeats sample 0 in the MIDDLE of its run (not a trailing copy: must stay)."""
+    idx = np.zeros((B, NP, NS), np.int32)
+    rng = np.random.Generator(np.random.PCG64(int(g)))
+    for b in range(B):
+        for j in range(NP):
+            cnt = NS if rng.random() < full_frac else int(rng.integers(1, NS + 1))
+            if j == 0:
+                cnt = 1
+            hits = np.sort(rng.choice(N, size=cnt, replace=False)).astype(np.int32)
+            idx[b, j, :cnt] = hits
+            idx[b, j, cnt:] = hits[0]
+            if j == 1 and cnt >= 3:
+                idx[b, j, 1] = hits[0]
+    return idx
+
+
+def _plan_model(idx, N):
+    """numpy statement of b2r_compact_plan: (cidx, ccen, meta)."""
+    B, NP, NS = idx.shape
+    flat = idx.reshape(B * NP, NS)
+    neq = flat != flat[:, :1]
+    cnt = np.where(neq.any(1), NS - np.argmax(neq[:, ::-1], 1), 1)
+    cls = np.select([cnt <= 8, cnt <= 16, cnt <= 32], [0, 1, 2], 3)
+    cap = ((B * NP * NS + 127) // 128) * 128 + 512
+    cidx = np.zeros(cap, np.int64)
+    ccen = np.full(cap, -1, np.int64)
+    meta = np.zeros(16, np.int64)
+    start = 0
+    for k in range(4):
+        members = np.nonzero(cls == k)[0]
+        ns = 8 << k
+        for r, gidx in enumerate(members):
+            p0 = start + r * ns
+            cidx[p0:p0 + ns] = (gidx // NP) * N + flat[gidx, :ns]
+            ccen[p0:p0 + ns] = gidx
+        live = start + len(members) * ns
+        end = (live + 127) // 128 * 128
+        meta[k], meta[4 + k], meta[10 + k] = end, live, len(members)
+        start = end
+    meta[8] = start
+    return cidx, ccen, meta, cnt
+
+
+@pytest.mark.parametrize("B,N,NP,NS", [(2, 500, 37, 64), (3, 2048, 1024, 32), (1, 300, 5, 16),
+                                       (8, 4000, 2048, 64)])
+def test_compact_plan_matches_model(cuda, B, N, NP, NS):
+    from backtoreality_b200 import fused_sa
+    idx = _padded_idx(B * 1000 + NP, B, N, NP, NS)
+    plan = fused_sa.compact_plan(torch.from_numpy(idx).to(cuda), N)
+    torch.cuda.synchronize()
+    cidx, ccen, meta, cnt = _plan_model(idx, N)
+    got_meta = plan["cmeta"].cpu().numpy()
+    np.testing.assert_array_equal(got_meta[:9], meta[:9])
+    np.testing.assert_array_equal(got_meta[10:14], meta[10:14])
+    total = int(meta[8])
+    np.testing.assert_array_equal(plan["ccen"].cpu().numpy()[:total], ccen[:total])
+    np.testing.assert_array_equal(plan["cidx"].cpu().numpy()[:total], cidx[:total])
+    assert total <= plan["cidx"].numel()
+    # the weighted position count equals the padded one: sum over centres of ns + (NS - ns)
+    assert int((ccen[:total] >= 0).sum() + ((NS - (8 << np.select(
+        [cnt <= 8, cnt <= 16, cnt <= 32], [0, 1, 2], 3)))).sum()) == B * NP * NS
+
+
+@pytest.mark.parametrize("C,mlp,N,NP,NS", [(1, [64, 64, 128], 3000, 256, 64),
+                                            (128, [128, 128, 256], 2048, 512, 32),
+                                            (0, [64, 64, 128], 1500, 128, 32)])
+@pytest.mark.parametrize("training", [True, False])
+def test_compact_block_equals_padded_block(cuda, C, mlp, N, NP, NS, training):
+    """The pad-free position space computes what the padded one computes: pooled outputs, BatchNorm
+    running statistics and every gradient agree up to fp32 summation order (and the few TF32 /
+    BF16 operand roundings that a 1e-7 difference in a BatchNorm scale flips)."""
+    from backtoreality_b200 import fused_sa
+    from backtoreality_b200.pytorch_utils import SharedMLP
+    B = 2
+    g = torch.Generator(device="cpu").manual_seed(NS * 13 + C)
+    xyz0 = torch.rand(B, N, 3, generator=g).to(cuda)
+    new0 = torch.rand(B, NP, 3, generator=g).to(cuda)
+    f0 = torch.randn(B, C, N, generator=g).to(cuda) if C else None
+    idx = torch.from_numpy(_padded_idx(NS + C, B, N, NP, NS)).to(cuda)
+    torch.manual_seed(3)
+    net = SharedMLP([3 + C] + mlp, bn=True).to(cuda).train(training)
+    for blk in net:
+        bn = blk.bn.bn
+        bn.weight.data = torch.randn_like(bn.weight) * 0.5 + 0.8
+        bn.bias.data = torch.randn_like(bn.bias) * 0.2
+        bn.running_var.data = torch.rand_like(bn.running_var) + 0.5
+    state0 = {k: v.clone() for k, v in net.state_dict().items()}
+    outs = []
+    for compact in (False, True):
+        net.load_state_dict(state0)
+        net.zero_grad()
+        xyz = xyz0.clone().requires_grad_(True)
+        new_xyz = new0.clone().requires_grad_(True)
+        feats = f0.clone().requires_grad_(True) if C else None
+        plan = fused_sa.compact_plan(idx, N) if compact else None
+        old = fused_sa.COMPACT
+        fused_sa.COMPACT = False          # sa_block must not build its own plan for the padded arm
+        try:
+            y, y_pm = fused_sa.sa_block(xyz, new_xyz, feats, idx, 0.37, True, net, training,
+                                        want_pm=True, plan=plan)
+        finally:
+            fused_sa.COMPACT = old
+        patt = torch.sin(torch.arange(y.numel(), device=cuda, dtype=torch.float64) * 12.9898)
+        (y * patt.float().view_as(y)).sum().backward()
+        outs.append(dict(y=y.detach(), y_pm=y_pm.detach(), gx=xyz.grad, gn=new_xyz.grad,
+                         gf=feats.grad if C else None,
+                         gp=[p.grad.clone() for p in net.parameters()],
+                         rs={k: v.clone() for k, v in net.state_dict().items() if "running" in k}))
+    a, b = outs
+    assert torch.equal(b["y_pm"], b["y"].transpose(1, 2).contiguous())
+    assert rel_l2(b["y"].cpu().numpy(), a["y"].cpu().numpy()) < 2e-4
+    for k in a["rs"]:
+        assert rel_l2(b["rs"][k].cpu().numpy(), a["rs"][k].cpu().numpy()) < 1e-5, k
+    for name in ("gx", "gn", "gf"):
+        if a[name] is not None:
+            assert rel_l2(b[name].cpu().numpy(), a[name].cpu().numpy()) < 2e-2, name
+    for (n, _), pa, pb in zip(net.named_parameters(), a["gp"], b["gp"]):
+        assert rel_l2(pb.cpu().numpy(), pa.cpu().numpy()) < 2e-2, n
+
+
+@pytest.mark.parametrize("Cin,Cout,NS,epi", [(64, 64, 64, 0), (64, 128, 64, 1), (128, 256, 32, 1),
+                                             (128, 128, 32, 0)])
+def test_compact_dense_layer_statistics_and_pool(cuda, Cin, Cout, NS, epi):
+    """One dense layer in a plan's position space: the weighted statistics equal the sums over
+    the PADDED positions (each centre's sample 0 repeated) of the kernel's own z, and the pooled
+    extrema / arg indices are those of every centre's live run."""
+    from backtoreality_b200 import fused_sa
+    B, N, NP = 2, 999, 96
+    idx_np = _padded_idx(Cin + NS, B, N, NP, NS)
+    idx = torch.from_numpy(idx_np).to(cuda)
+    plan = fused_sa.compact_plan(idx, N)
+    torch.cuda.synchronize()
+    meta = plan["cmeta"].cpu().numpy()
+    total, cap = int(meta[8]), plan["cidx"].numel()
+    ccen = plan["ccen"].cpu().numpy()[:total]
+    g = torch.Generator(device="cpu").manual_seed(Cin + Cout)
+    zp = torch.randn(cap, Cin, generator=g).to(cuda)
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5).to(cuda)
+    sc = (torch.rand(Cin, generator=g) + 0.5).to(cuda)
+    sh = (torch.randn(Cin, generator=g) * 0.3).to(cuda)
+    image = fused_sa.pack_weight(w, gather=False)
+    base = dict(B=B, N=N, NP=NP, NS=NS, Cin=Cin, Cout=Cout, mode=1, z_prev=zp, scale_prev=sc,
+                shift_prev=sh, w_image=image, cidx=plan["cidx"], ccen=plan["ccen"],
+                cmeta=plan["cmeta"])
+    z = torch.full((cap, Cout), float("nan"), device=cuda)
+    st0 = torch.zeros(2, Cout, dtype=torch.float64, device=cuda)
+    _run_layer(cuda, epilogue=0, z=z, stats=st0, **base)
+    assert bool(torch.isfinite(z[:total]).all())          # dead rows are written too
+    x = torch.relu(zp[:total].double() * sc.double() + sh.double())
+    want = x @ w.double().reshape(Cout, Cin).t()
+    assert rel_l2(z[:total].cpu().numpy(), want.cpu().numpy()) < TF32_TOL
+    # multiplicity of every position in the padded computation
+    ends, lives = meta[0:4], meta[4:8]
+    wgt = np.zeros(total)
+    start = 0
+    for k in range(4):
+        ns = 8 << k
+        wgt[start:lives[k]] = 1.0
+        wgt[start:lives[k]:ns] = 1.0 + (NS - ns)
+        start = ends[k]
+    assert wgt.sum() == B * NP * NS
+    wt = torch.from_numpy(wgt).to(cuda)[:, None]
+    zz = z[:total].double()
+    np.testing.assert_allclose(st0[0].cpu().numpy(), (wt * zz).sum(0).cpu().numpy(), rtol=1e-6, atol=1e-3)
+    np.testing.assert_allclose(st0[1].cpu().numpy(), (wt * zz * zz).sum(0).cpu().numpy(), rtol=1e-6, atol=1e-3)
+    if epi == 1:
+        G = B * NP
+        zmax = torch.full((G, Cout), float("nan"), device=cuda)
+        zmin = torch.full_like(zmax, float("nan"))
+        amax = torch.full((G, Cout), -7, dtype=torch.int32, device=cuda)
+        amin = torch.full_like(amax, -7)
+        st1 = torch.zeros(2, Cout, dtype=torch.float64, device=cuda)
+        _run_layer(cuda, epilogue=1, zmax=zmax, zmin=zmin, amax=amax, amin=amin, stats=st1, **base)
+        assert torch.allclose(st0, st1, rtol=1e-9, atol=1e-6)
+        zc = z[:total].cpu().numpy()
+        first = {}
+        for p in range(total):
+            if ccen[p] >= 0 and ccen[p] not in first:
+                first[int(ccen[p])] = p
+        assert len(first) == G
+        zmax_c, zmin_c, amax_c, amin_c = (t.cpu().numpy() for t in (zmax, zmin, amax, amin))
+        for gi in range(0, G, 7):
+            p0 = first[gi]
+            n = int((ccen == gi).sum())
+            run = zc[p0:p0 + n]
+            np.testing.assert_array_equal(zmax_c[gi], run.max(0))
+            np.testing.assert_array_equal(zmin_c[gi], run.min(0))
+            np.testing.assert_array_equal(amax_c[gi], run.argmax(0))
+            np.testing.assert_array_equal(amin_c[gi], run.argmin(0))
