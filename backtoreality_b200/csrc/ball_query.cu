@@ -141,7 +141,8 @@ extern "C" int b2r_ball_query(const float *new_xyz, const float *xyz, int B, int
 // (bitonic, in shared memory) and writes the head.  The distance test is the same instruction
 // sequence on the same operands, so the hit SET is identical; every point with d < radius lies in
 // one of the 27 cells because |dx| < radius < cell size (the 1e-3 margin dominates the rounding of
-// x * (1/cell) for |x| < 8000 cells).  Hash aliasing (64 x 64 x 32 cells, coordinates wrapped)
+// x * (1/cell) for |x| < 8000 cells; scenes with larger coordinates are detected by the bucketing
+// pass and scanned in index order instead, see kSafeCells).  Hash aliasing (64 x 64 x 32 cells, coordinates wrapped)
 // only adds candidates that the distance test rejects.
 namespace b2r {
 namespace {
@@ -151,20 +152,36 @@ constexpr int kGCells = kGx * kGy * kGz;             // 131072
 constexpr int kHitCap = 512;                         // per-warp candidate buffer
 constexpr int kGqWarps = 8;
 
+// Cell coordinate of x: floor(x / cell), clamped to +-2^30 before the int cast (a float outside
+// the int range, or NaN, is undefined behaviour in the cast; such points can never pass the
+// distance test, any cell will do for them).
+__device__ __forceinline__ int cell_coord(float x, float inv) {
+  return (int)fminf(fmaxf(floorf(x * inv), -1073741824.f), 1073741824.f);
+}
 __device__ __forceinline__ int grid_cell(float x, float y, float z, float inv) {
-  const int ix = (int)floorf(x * inv) & (kGx - 1);
-  const int iy = (int)floorf(y * inv) & (kGy - 1);
-  const int iz = (int)floorf(z * inv) & (kGz - 1);
+  const int ix = cell_coord(x, inv) & (kGx - 1);
+  const int iy = cell_coord(y, inv) & (kGy - 1);
+  const int iz = cell_coord(z, inv) & (kGz - 1);
   return (iz * kGy + iy) * kGx + ix;
+}
+// The 27-cell argument needs the fp32 rounding of x * (1/cell) to stay below the 1e-3 cell margin:
+// |x / cell| * 2^-24 < 1e-3 / 2, i.e. |x| < ~8000 cells.  A scene with a finite coordinate beyond
+// kSafeCells sets its flag and every centre of that scene takes the index-order scan instead.
+constexpr float kSafeCells = 7900.f;
+__device__ __forceinline__ bool beyond_safe(float x, float y, float z, float inv) {
+  const float m = fmaxf(fabsf(x * inv), fmaxf(fabsf(y * inv), fabsf(z * inv)));
+  return m > kSafeCells && m < INFINITY;   // NaN / inf points never hit: no need to fall back
 }
 
 // counts per cell; cell id of every point kept for the fill pass
 __global__ void grid_count_kernel(const float *__restrict__ xyz, int N, float inv,
-                                  int *__restrict__ count, int *__restrict__ cell_of) {
+                                  int *__restrict__ count, int *__restrict__ cell_of,
+                                  int *__restrict__ far_flag) {
   const int b = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= N) return;
   const float *p = xyz + ((size_t)b * N + k) * 3;
+  if (beyond_safe(p[0], p[1], p[2], inv)) far_flag[b] = 1;
   const int c = grid_cell(p[0], p[1], p[2], inv);
   cell_of[(size_t)b * N + k] = c;
   atomicAdd(count + (size_t)b * (kGCells + 1) + c, 1);
@@ -239,7 +256,7 @@ __global__ void __launch_bounds__(kGqWarps * 32)
     grid_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz,
                       const int *__restrict__ start, const int *__restrict__ pop,
                       const int *__restrict__ sorted, int N, int M, float radius, float inv,
-                      int nsample, int *__restrict__ idx) {
+                      int nsample, int *__restrict__ idx, const int *__restrict__ far_flag) {
   __shared__ int s_hits[kGqWarps][kHitCap];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
@@ -253,7 +270,30 @@ __global__ void __launch_bounds__(kGqWarps * 32)
   const float *q = new_xyz + ((size_t)b * M + j) * 3;
   const float cx = q[0], cy = q[1], cz = q[2];
   const float r2 = __fmul_rn(radius, radius);
-  const int ix = (int)floorf(cx * inv), iy = (int)floorf(cy * inv), iz = (int)floorf(cz * inv);
+  int *out = idx + ((size_t)b * M + j) * nsample;
+  if (far_flag[b] != 0 || beyond_safe(cx, cy, cz, inv)) {
+    // coordinates too large for the grid's rounding margin: the reference's scan in index order
+    // (ball_query_gpu.cu:31-47), 32 points per step
+    int cnt = 0, first = 0;
+    for (int k0 = 0; k0 < N && cnt < nsample; k0 += 32) {
+      const int k = k0 + lane;
+      bool hit = false;
+      if (k < N) {
+        const float *p = xyz + (size_t)k * 3;
+        hit = sumsq_ref(__fsub_rn(cx, p[0]), __fsub_rn(cy, p[1]), __fsub_rn(cz, p[2])) < r2;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) {
+        if (cnt == 0) first = k0 + __ffs(m) - 1;
+        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+        if (hit && pos < nsample) out[pos] = k;
+        cnt += __popc(m);
+      }
+    }
+    for (int l = min(cnt, nsample) + lane; l < nsample; l += 32) out[l] = cnt > 0 ? first : 0;
+    return;
+  }
+  const int ix = cell_coord(cx, inv), iy = cell_coord(cy, inv), iz = cell_coord(cz, inv);
   int n = 0;   // hits buffered (warp-uniform)
 
   // sort what is buffered and keep the `keep` smallest: they are the only ones that can matter
@@ -293,7 +333,6 @@ __global__ void __launch_bounds__(kGqWarps * 32)
           }
         }
       }
-  int *out = idx + ((size_t)b * M + j) * nsample;
   if (n == 0) {
     for (int l = lane; l < nsample; l += 32) out[l] = 0;
     return;
@@ -305,8 +344,9 @@ __global__ void __launch_bounds__(kGqWarps * 32)
 }
 
 inline size_t grid_ws_bytes(int B, int N) {
-  // per scene: count/start (kGCells + 1), cursor (kGCells), cell_of (N), sorted (N) ints
-  return (size_t)B * ((size_t)(kGCells + 1) + kGCells + 2 * (size_t)N) * sizeof(int);
+  // per scene: count/start (kGCells + 1), cursor (kGCells), cell_of (N), sorted (N) ints and
+  // one "coordinates beyond the grid's safe range" flag
+  return (size_t)B * ((size_t)(kGCells + 1) + kGCells + 2 * (size_t)N + 1) * sizeof(int);
 }
 
 }  // namespace
@@ -336,15 +376,18 @@ extern "C" int b2r_ball_query_grid(const float *new_xyz, const float *xyz, int B
   int *cursor = count + (size_t)B * (b2r::kGCells + 1);
   int *cell_of = cursor + (size_t)B * b2r::kGCells;
   int *sorted = cell_of + (size_t)B * N;
+  int *far_flag = sorted + (size_t)B * N;
   const float inv = 1.0f / (radius * 1.001f);
   B2R_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)B * (b2r::kGCells + 1), st));
+  B2R_CUDA(cudaMemsetAsync(far_flag, 0, sizeof(int) * (size_t)B, st));
   dim3 gp(b2r::ceil_div(N, 256), B, 1);
-  b2r::grid_count_kernel<<<gp, 256, 0, st>>>(xyz, N, inv, count, cell_of);
+  b2r::grid_count_kernel<<<gp, 256, 0, st>>>(xyz, N, inv, count, cell_of, far_flag);
   b2r::grid_scan_kernel<<<dim3(b2r::kScanChunks, B, 1), 1024, 0, st>>>(count, cursor);
   b2r::grid_fill_kernel<<<gp, 256, 0, st>>>(cell_of, count, cursor, N, sorted);
   dim3 gq(b2r::ceil_div(M, b2r::kGqWarps), B, 1);
   b2r::grid_query_kernel<<<gq, b2r::kGqWarps * 32, 0, st>>>(new_xyz, xyz, count, cursor, sorted, N,
-                                                            M, radius, inv, nsample, idx);
+                                                            M, radius, inv, nsample, idx,
+                                                            far_flag);
   B2R_CHECK_LAUNCH();
   return B2R_OK;
 }

@@ -276,14 +276,20 @@ template <int P, int NT>
 cudaError_t launch_inst(const FpsPlan &pl, const float *xyz, int B, int N, int npoint, int *idx,
                         cudaStream_t stream) {
   auto kern = fps_cluster_kernel<P, NT>;
-  static bool attr_done = false;  // idempotent; a benign race at worst repeats the calls
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         3 * P * NT * (int)sizeof(float));
+  // Function attributes are PER DEVICE: one process may drive several GPUs (nn.DataParallel
+  // replica threads, reference train_Votenet_FSB.py:164-168), so the "already set" flag is kept
+  // per device ordinal.  Idempotent; a benign race at worst repeats the calls.
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             3 * P * NT * (int)sizeof(float));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pl.csize, B, 1);

@@ -333,7 +333,11 @@ def test_pipelined_train_step_matches_sequential(cuda, start_after_level):
     assert set(pipe.geo_cur[3]) == set(PipelinedTrainStep.GEO_KEYS + PipelinedTrainStep.FP_KEYS)
     for lv_p, lv_f in zip(pipe.geo_cur, fresh):
         for k in lv_p:
-            assert torch.equal(lv_p[k], lv_f[k]), k
+            n = None
+            if k in ("cidx", "ccen"):      # a plan's buffers are only defined up to its total
+                n = int(lv_f["cmeta"][8])
+                assert n == int(lv_p["cmeta"][8])
+            assert torch.equal(lv_p[k][:n], lv_f[k][:n]), k
     for (n1, p1), (n2, p2) in zip(net_e.named_parameters(), net_p.named_parameters()):
         assert torch.equal(p1, p2), n1        # lr = 0
         assert rel_l2(p2.grad.cpu().numpy(), p1.grad.cpu().numpy()) < 3e-2, n1

@@ -129,7 +129,7 @@ def test_ball_query_dense_uniform_early_exit(cuda):
 
 
 @pytest.mark.parametrize("case", ["room", "negative", "cluster", "huge_radius", "far_aliasing",
-                                  "nan", "ragged"])
+                                  "nan", "ragged", "beyond_grid_range", "overflowing_coordinate"])
 def test_ball_query_grid_path_matches_oracle(cuda, case, monkeypatch):
     """The hashed-grid ball query (b2r_ball_query_grid, taken for N >= 8192; forced here from
     N >= 1024) must return exactly what the brute-force scan returns: against the C oracle, on
@@ -161,6 +161,17 @@ def test_ball_query_grid_path_matches_oracle(cuda, case, monkeypatch):
         xyz[:, 4000, 1] = np.inf
         new_xyz = xyz[:, :300].copy()
         r, ns = 0.25, 32
+    elif case == "beyond_grid_range":
+        # a scan georeferenced 3 km from the origin at r = 0.2: 15000 cells, past the ~8000 the
+        # grid's fp32 rounding margin covers -> the kernel falls back to the index-order scan
+        xyz = rng.random((2, 6000, 3), dtype=np.float32) * np.float32(2.0) + np.float32(3000.0)
+        xyz[1] -= np.float32(3000.0)            # scene 1 stays on the grid path
+        new_xyz, r, ns = xyz[:, :400].copy(), 0.2, 16
+    elif case == "overflowing_coordinate":
+        # one finite coordinate whose cell index does not fit an int32 (x / cell ~ 5e37)
+        xyz = rng.random((2, 3000, 3), dtype=np.float32)
+        xyz[0, 5, 0] = np.float32(1e37)
+        new_xyz, r, ns = xyz[:, 100:300].copy(), 0.25, 8
     else:
         xyz = rng.random((2, 1025, 3), dtype=np.float32)
         new_xyz, r, ns = rng.random((2, 9, 3), dtype=np.float32), 0.35, 5
