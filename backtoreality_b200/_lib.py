@@ -110,6 +110,43 @@ SIGNATURES.update({
 _RESTYPES["b2r_compact_capacity"] = ctypes.c_longlong
 _RESTYPES["b2r_compact_workspace_bytes"] = ctypes.c_longlong
 
+
+
+class DenseLayer(ctypes.Structure):
+    """struct b2r_dense_layer (include/b2r.h)."""
+    _fields_ = [
+        ("M", _i), ("Cin", _i), ("Cout", _i),
+        ("in_", _vp), ("ld_in", _i), ("sc_in", _vp), ("sh_in", _vp),
+        ("w_img", _vp), ("bias", _vp), ("z", _vp), ("ld_z", _i), ("stats", _vp),
+    ]
+
+
+class DenseLayerBwd(ctypes.Structure):
+    """struct b2r_dense_layer_bwd (include/b2r.h)."""
+    _fields_ = [
+        ("M", _i), ("Cin", _i), ("Cout", _i),
+        ("in_", _vp), ("ld_in", _i), ("sc_in", _vp), ("sh_in", _vp),
+        ("g", _vp), ("zz", _vp), ("ld_g", _i),
+        ("ca", _vp), ("cb", _vp), ("cc", _vp),
+        ("wt_img", _vp), ("gin", _vp), ("ld_gin", _i), ("stats_in", _vp), ("dW", _vp),
+    ]
+
+
+_ll = ctypes.c_longlong
+SIGNATURES.update({
+    "b2r_bn_bwd_finalize_ex": [_vp, _i, ctypes.c_double, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp,
+                               _vp, _vp, _vp, _vp, _vp],
+    "b2r_dense_image_bytes": [_i, _i],
+    "b2r_dense_pack": [_vp, _i, _i, _vp, _vp, _vp],
+    "b2r_dense_fwd": [ctypes.POINTER(DenseLayer), _vp],
+    "b2r_dense_bwd": [ctypes.POINTER(DenseLayerBwd), _vp],
+    "b2r_interp_cat_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "b2r_interp_cat_bwd": [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "b2r_vote_tail_fwd": [_vp, _i, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp],
+    "b2r_vote_tail_bwd": [_vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp],
+})
+_RESTYPES["b2r_dense_image_bytes"] = ctypes.c_longlong
+
 _lib = None
 
 

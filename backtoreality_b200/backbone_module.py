@@ -128,8 +128,9 @@ class Pointnet2Backbone(nn.Module):
         chain = all(isinstance(g, dict) for g in geo)
         if chain:
             geo = [dict(g) for g in geo]            # never mutate the caller's dicts
-            for g in geo[:3]:
+            for g in geo:
                 g["want_pm"] = True
+        pm = {}      # point-major copies of sa2..sa4's features, for the dense FP path
 
         xyz, features, fps_inds = self.sa1(xyz, features, geometry=geo[0])
         end_points['sa1_inds'] = fps_inds
@@ -145,19 +146,21 @@ class Pointnet2Backbone(nn.Module):
         end_points['sa2_features'] = features
         self._after_forward(geo[1])
         if chain:
-            geo[2]["features_pm"] = geo[1].pop("out_pm", None)
+            pm[2] = geo[2]["features_pm"] = geo[1].pop("out_pm", None)
 
         xyz, features, fps_inds = self.sa3(xyz, features, geometry=geo[2])
         end_points['sa3_xyz'] = xyz
         end_points['sa3_features'] = features
         self._after_forward(geo[2])
         if chain:
-            geo[3]["features_pm"] = geo[2].pop("out_pm", None)
+            pm[3] = geo[3]["features_pm"] = geo[2].pop("out_pm", None)
 
         xyz, features, fps_inds = self.sa4(xyz, features, geometry=geo[3])
         end_points['sa4_xyz'] = xyz
         end_points['sa4_features'] = features
         self._after_forward(geo[3])
+        if chain:
+            pm[4] = geo[3].pop("out_pm", None)
 
         interp1 = interp2 = None
         if geo[3] is not None and "fp1_idx" in geo[3]:
@@ -165,11 +168,24 @@ class Pointnet2Backbone(nn.Module):
                 torch.cuda.current_stream().wait_event(geo[3]["fp_event"])
             interp1 = (geo[3]["fp1_idx"], geo[3]["fp1_weight"])
             interp2 = (geo[3]["fp2_idx"], geo[3]["fp2_weight"])
-        features = self.fp1(end_points['sa3_xyz'], end_points['sa4_xyz'],
-                            end_points['sa3_features'], end_points['sa4_features'], interp=interp1)
-        features = self.fp2(end_points['sa2_xyz'], end_points['sa3_xyz'],
-                            end_points['sa2_features'], features, interp=interp2)
+        fp2_pm = None
+        if all(pm.get(k) is not None for k in (2, 3, 4)):
+            # dense tcgen05 FP path on the blocks' point-major outputs (no transposes in between)
+            r1 = self.fp1.forward_pm(end_points['sa3_xyz'], end_points['sa4_xyz'], pm[3], pm[4],
+                                     interp=interp1)
+            r2 = None if r1 is None else self.fp2.forward_pm(
+                end_points['sa2_xyz'], end_points['sa3_xyz'], pm[2], r1[1], interp=interp2)
+            if r2 is not None:
+                features, fp2_pm = r2
+        if fp2_pm is None:
+            features = self.fp1(end_points['sa3_xyz'], end_points['sa4_xyz'],
+                                end_points['sa3_features'], end_points['sa4_features'],
+                                interp=interp1)
+            features = self.fp2(end_points['sa2_xyz'], end_points['sa3_xyz'],
+                                end_points['sa2_features'], features, interp=interp2)
         end_points['fp2_features'] = features
+        if fp2_pm is not None:
+            end_points['fp2_features_pm'] = fp2_pm      # (B,1024,C): for the voting module
         end_points['fp2_xyz'] = end_points['sa2_xyz']
         num_seed = end_points['fp2_xyz'].shape[1]
         end_points['fp2_inds'] = end_points['sa1_inds'][:, 0:num_seed]

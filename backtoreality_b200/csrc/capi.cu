@@ -34,6 +34,8 @@ extern "C" const char *b2r_last_error(void) { return b2r::g_err; }
 extern "C" int b2r_struct_bytes(int which) {
   if (which == 0) return (int)sizeof(b2r_sa_layer);
   if (which == 1) return (int)sizeof(b2r_sa_layer_bwd_desc);
+  if (which == 2) return (int)sizeof(b2r_dense_layer);
+  if (which == 3) return (int)sizeof(b2r_dense_layer_bwd);
   return -1;
 }
 

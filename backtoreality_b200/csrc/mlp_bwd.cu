@@ -905,7 +905,8 @@ __global__ void bn_bwd_finalize_kernel(const double *__restrict__ stats, int Cch
                                        float *__restrict__ coef_a, float *__restrict__ coef_b,
                                        float *__restrict__ coef_c, float *__restrict__ k1_out,
                                        float *__restrict__ k2_out, float *__restrict__ gs_out,
-                                       float *__restrict__ dgamma, float *__restrict__ dbeta) {
+                                       float *__restrict__ dgamma, float *__restrict__ dbeta,
+                                       float *__restrict__ dbias_conv) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= Cch) return;
   const double S1 = stats[ch], S2 = stats[Cch + ch];
@@ -927,6 +928,10 @@ __global__ void bn_bwd_finalize_kernel(const double *__restrict__ stats, int Cch
   if (gs_out) gs_out[ch] = (float)gs;
   if (dgamma) dgamma[ch] = (float)sx;
   if (dbeta) dbeta[ch] = (float)S1;
+  // gradient of a bias added by the convolution BEFORE this BatchNorm: sum over positions of
+  // dz = a*gr + b*z + c, i.e. a*S1 + count*(b*mean + c) -- zero with batch statistics, gs*S1 with
+  // running statistics (nn.Conv1d(bias=True) -> BatchNorm1d in the voting / proposal heads)
+  if (dbias_conv) dbias_conv[ch] = (float)(gs * S1 + count * (b * mu + (-gs * k1 - b * mu)));
 }
 
 }  // namespace
@@ -1127,15 +1132,24 @@ extern "C" int b2r_pool_bwd_prep(const float *dout_cm, const float *dout_pm, con
   return B2R_OK;
 }
 
+extern "C" int b2r_bn_bwd_finalize_ex(const double *stats, int C, double count, const float *gamma,
+                                      const float *mean, const float *invstd, int training,
+                                      float *coef_a, float *coef_b, float *coef_c, float *k1,
+                                      float *k2, float *gs, float *dgamma, float *dbeta,
+                                      float *dbias_conv, void *stream) {
+  B2R_REQUIRE(stats && mean && invstd && C > 0 && count > 0, "b2r_bn_bwd_finalize: bad argument");
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats, C, count, gamma, mean, invstd, training, coef_a, coef_b, coef_c, k1, k2, gs, dgamma,
+      dbeta, dbias_conv);
+  B2R_CHECK_LAUNCH();
+  return B2R_OK;
+}
+
 extern "C" int b2r_bn_bwd_finalize(const double *stats, int C, double count, const float *gamma,
                                    const float *mean, const float *invstd, int training,
                                    float *coef_a, float *coef_b, float *coef_c, float *k1,
                                    float *k2, float *gs, float *dgamma, float *dbeta,
                                    void *stream) {
-  B2R_REQUIRE(stats && mean && invstd && C > 0 && count > 0, "b2r_bn_bwd_finalize: bad argument");
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      stats, C, count, gamma, mean, invstd, training, coef_a, coef_b, coef_c, k1, k2, gs, dgamma,
-      dbeta);
-  B2R_CHECK_LAUNCH();
-  return B2R_OK;
+  return b2r_bn_bwd_finalize_ex(stats, C, count, gamma, mean, invstd, training, coef_a, coef_b,
+                                coef_c, k1, k2, gs, dgamma, dbeta, nullptr, stream);
 }

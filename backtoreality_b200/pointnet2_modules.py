@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import fused_sa
+from . import dense_mlp, fused_sa
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
 
@@ -102,6 +102,21 @@ class PointnetSAModuleVotes(_SAVotesBase):
         -> new_xyz (B,npoint,3), new_features (B,mlp[-1],npoint), inds (B,npoint)
     """
 
+    def forward_pm(self, xyz, features=None, inds=None, features_pm=None):
+        """`forward` for callers that hand features over POINT-major: features_pm (B,N,C) is used
+        instead of `features` by the fused block, and the block's output comes back in both
+        layouts: -> (new_xyz, new_features (B,C,npoint), inds, new_features_pm (B,npoint,C) | None)
+        (None when the unfused path ran)."""
+        xyz_flipped = xyz.transpose(1, 2).contiguous()
+        if inds is None:
+            inds = pointnet2_utils.furthest_point_sample(xyz, self.npoint)
+        else:
+            assert (inds.shape[1] == self.npoint)
+        new_xyz = pointnet2_utils.gather_operation(xyz_flipped, inds).transpose(1, 2).contiguous()
+        new_features, out_pm = self._abstract(xyz, new_xyz, features, sm_limit=self.sm_limit,
+                                              features_pm=features_pm, want_pm=True)
+        return new_xyz, new_features, inds, out_pm
+
     def forward(self, xyz: torch.Tensor, features: torch.Tensor = None,
                 inds: torch.Tensor = None, geometry: dict = None):
         if geometry is not None:
@@ -162,7 +177,34 @@ class PointnetFPModule(nn.Module):
         norm = torch.sum(dist_recip, dim=2, keepdim=True)
         return idx, dist_recip / norm
 
+    def _specs(self):
+        return dense_mlp.layer_specs([blk.conv for blk in self.mlp], [blk.bn.bn if hasattr(blk, "bn")
+                                                                    else None for blk in self.mlp])
+
+    def forward_pm(self, unknown, known, unknow_feats_pm, known_feats_pm, interp=None):
+        """The module on POINT-major features: unknow_feats_pm (B,n,C1) | None, known_feats_pm
+        (B,m,C2) -> (new_features (B,mlp[-1],n), the same point-major (B,n,mlp[-1])), or None when
+        the dense tcgen05 path does not cover this module (callers then use `forward`).
+        Interpolation + concatenation run as one pass, the SharedMLP on csrc/dense.cu."""
+        specs = self._specs()
+        if known is None or not dense_mlp.supported(specs, known_feats_pm) or \
+                any(bn is None for _, bn in specs):
+            return None
+        idx, weight = interp if interp is not None else self.interpolation_weights(unknown, known)
+        x0 = dense_mlp.interp_cat(known_feats_pm, unknow_feats_pm, idx, weight)
+        B, n = idx.shape[0], idx.shape[1]
+        out_pm, out_cm = dense_mlp.dense_mlp(x0, specs, self.training, B, n)
+        return out_cm, out_pm
+
     def forward(self, unknown, known, unknow_feats, known_feats, interp=None):
+        if known is not None and known_feats.is_cuda and dense_mlp.enabled():
+            # fused path: same maths, point-major inside (two transposing copies at the boundary)
+            res = self.forward_pm(unknown, known,
+                                  unknow_feats.transpose(1, 2).contiguous()
+                                  if unknow_feats is not None else None,
+                                  known_feats.transpose(1, 2).contiguous(), interp=interp)
+            if res is not None:
+                return res[0]
         if known is not None:
             idx, weight = interp if interp is not None else self.interpolation_weights(unknown, known)
             interpolated_feats = pointnet2_utils.three_interpolate(known_feats, idx, weight)

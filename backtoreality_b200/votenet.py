@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import fused_sa, pointnet2_utils
+from . import dense_mlp, fused_sa, pointnet2_utils
 from .backbone_module import Pointnet2Backbone
 from .pointnet2_modules import PointnetSAModuleVotes
 
@@ -31,6 +31,23 @@ class VotingModule(nn.Module):
         self.conv3 = nn.Conv1d(self.in_dim, (3 + self.out_dim) * self.vote_factor, 1)
         self.bn1 = nn.BatchNorm1d(self.in_dim)
         self.bn2 = nn.BatchNorm1d(self.in_dim)
+
+    def forward_normalized(self, seed_xyz, seed_features, seed_features_pm=None):
+        """forward + VoteNet's L2 feature normalisation (votenet.py:93-94) on the dense tcgen05
+        path (csrc/dense.cu, csrc/heads.cu): -> (vote_xyz (B,n,3), vote_features (B,C,n) normalised,
+        the same point-major (B,n,C)), or None when that path does not cover this module.
+        seed_features_pm (B,n,C): the seed features point-major, when the caller has them."""
+        if self.vote_factor != 1 or not seed_xyz.is_cuda:
+            return None
+        specs = dense_mlp.layer_specs([self.conv1, self.conv2, self.conv3], [self.bn1, self.bn2, None])
+        if seed_features_pm is None:
+            seed_features_pm = seed_features.transpose(1, 2).contiguous()
+        if not dense_mlp.supported(specs, seed_features_pm):
+            return None
+        B, n, C = seed_features_pm.shape
+        net, _ = dense_mlp.dense_mlp(seed_features_pm.reshape(B * n, C), specs, self.training, B, n)
+        vote_xyz, vf_pm = dense_mlp.vote_tail(net, seed_xyz, seed_features_pm)
+        return vote_xyz, vf_pm.transpose(1, 2).contiguous(), vf_pm
 
     def forward(self, seed_xyz, seed_features):
         B, num_seed = seed_xyz.shape[0], seed_xyz.shape[1]
@@ -101,29 +118,45 @@ class ProposalModule(nn.Module):
         self.register_buffer("_mean_size", torch.from_numpy(
             np.asarray(mean_size_arr, np.float32)).clone(), persistent=False)
 
-    def forward(self, xyz, features, end_points):
+    def forward(self, xyz, features, end_points, features_pm=None):
+        """features_pm (not in the reference's signature): the vote features point-major
+        (B,num_vote,C), when the caller has them (VotingModule.forward_normalized)."""
         if self.sampling == 'vote_fps':
-            xyz, features, fps_inds = self.vote_aggregation(xyz, features)
-            sample_inds = fps_inds
+            sample_inds = None
         elif self.sampling == 'seed_fps':
             sample_inds = pointnet2_utils.furthest_point_sample(end_points['seed_xyz'],
                                                                 self.num_proposal)
-            xyz, features, _ = self.vote_aggregation(xyz, features, sample_inds)
         elif self.sampling == 'random':
             num_seed = end_points['seed_xyz'].shape[1]
             B = end_points['seed_xyz'].shape[0]
             sample_inds = torch.randint(0, num_seed, (B, self.num_proposal), dtype=torch.int,
                                         device=xyz.device)
-            xyz, features, _ = self.vote_aggregation(xyz, features, sample_inds)
         else:
             raise ValueError('Unknown sampling strategy: %s' % (self.sampling,))
+        xyz, features, fps_inds, agg_pm = self.vote_aggregation.forward_pm(xyz, features, sample_inds,
+                                                                          features_pm)
+        if sample_inds is None:
+            sample_inds = fps_inds
         end_points['aggregated_vote_xyz'] = xyz
         end_points['aggregated_vote_features'] = features
         end_points['aggregated_vote_inds'] = sample_inds
 
-        net = F.relu(self.bn1(self.conv1(features)))
-        net = F.relu(self.bn2(self.conv2(net)))
-        net = self.conv3(net)
+        net = None
+        if features.is_cuda and dense_mlp.enabled():
+            # proposal head on the dense tcgen05 path, point-major (csrc/dense.cu)
+            specs = dense_mlp.layer_specs([self.conv1, self.conv2, self.conv3],
+                                          [self.bn1, self.bn2, None])
+            if agg_pm is None:
+                agg_pm = features.transpose(1, 2).contiguous()
+            if dense_mlp.supported(specs, agg_pm):
+                B, P, C = agg_pm.shape
+                net_pm, _ = dense_mlp.dense_mlp(agg_pm.reshape(B * P, C), specs, self.training, B, P)
+                Cout = self.conv3.out_channels
+                net = net_pm[:, :Cout].reshape(B, P, Cout).transpose(1, 2)    # (B, Cout, P) view
+        if net is None:
+            net = F.relu(self.bn1(self.conv1(features)))
+            net = F.relu(self.bn2(self.conv2(net)))
+            net = self.conv3(net)
         end_points['proposal_scores_raw'] = net
         return decode_scores(net, end_points, self.num_class, self.num_heading_bin,
                              self.num_size_cluster, self._mean_size)
@@ -165,12 +198,20 @@ class VoteNet(nn.Module):
         end_points['seed_inds'] = end_points['fp2_inds']
         end_points['seed_xyz'] = xyz
         end_points['seed_features'] = features
-        xyz, features = self.vgen(xyz, features)
-        features_norm = torch.norm(features, p=2, dim=1)
-        features = features.div(features_norm.unsqueeze(1))
+        res = None
+        if dense_mlp.enabled() and xyz.is_cuda:
+            # voting MLP + offset / residual split + normalisation on the dense tcgen05 path
+            res = self.vgen.forward_normalized(xyz, features, end_points.get('fp2_features_pm'))
+        if res is not None:
+            xyz, features, features_pm = res
+        else:
+            xyz, features = self.vgen(xyz, features)
+            features_norm = torch.norm(features, p=2, dim=1)
+            features = features.div(features_norm.unsqueeze(1))
+            features_pm = None
         end_points['vote_xyz'] = xyz
         end_points['vote_features'] = features
-        end_points = self.pnet(xyz, features, end_points)
+        end_points = self.pnet(xyz, features, end_points, features_pm=features_pm)
         if prepacked:
             fused_sa.prepack_join()
         return end_points

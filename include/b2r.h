@@ -47,7 +47,7 @@ B2R_API int b2r_version(void);
 B2R_API const char *b2r_status_string(int status);
 B2R_API const char *b2r_last_error(void);
 /* sizeof() of the descriptor structs as THIS build of the library sees them (0: b2r_sa_layer,
- * 1: b2r_sa_layer_bwd_desc; -1 otherwise): lets a binding in another language verify its mirror
+ * 1: b2r_sa_layer_bwd_desc, 2: b2r_dense_layer, 3: b2r_dense_layer_bwd; -1 otherwise): lets a binding in another language verify its mirror
  * of the struct layout before the first launch (tests/test_capi_symbols.py does). */
 B2R_API int b2r_struct_bytes(int which);
 
@@ -322,6 +322,14 @@ B2R_API int b2r_bn_bwd_finalize(const double *stats, int C, double count, const 
                                 const float *mean, const float *invstd, int training,
                                 float *coef_a, float *coef_b, float *coef_c, float *k1, float *k2,
                                 float *gs, float *dgamma, float *dbeta, void *stream);
+/* The same with one more output: dbias_conv (C) = sum over positions of dz, the gradient of a bias
+ * the convolution added in front of this BatchNorm (nn.Conv1d(bias=True) -> BatchNorm1d in the
+ * voting / proposal heads).  NULL = not needed. */
+B2R_API int b2r_bn_bwd_finalize_ex(const double *stats, int C, double count, const float *gamma,
+                                   const float *mean, const float *invstd, int training,
+                                   float *coef_a, float *coef_b, float *coef_c, float *k1,
+                                   float *k2, float *gs, float *dgamma, float *dbeta,
+                                   float *dbias_conv, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pad-free position space of a set-abstraction block (csrc/compact.cu).
@@ -342,6 +350,88 @@ B2R_API long long b2r_compact_capacity(int B, int NP, int NS);
 B2R_API long long b2r_compact_workspace_bytes(int B, int NP);
 B2R_API int b2r_compact_plan(const int *idx, int B, int N, int NP, int NS, int *cidx, int *ccen,
                              int *meta, void *workspace, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Wide 1x1-conv layers on POINT-major tensors (csrc/dense.cu): the SharedMLP of
+ * PointnetFPModule (reference pointnet2_modules.py:505-514), VotingModule's conv1..3 + bn1..2
+ * (models/voting_module.py:38-65) and ProposalModule's conv1..3 + bn1..2
+ * (models/proposal_module.py:115-119), which the reference runs as cuDNN Conv1d/Conv2d +
+ * BatchNorm + ReLU on (B,C,n) tensors.  Here a layer is  z (M,Cout) = x (M,Cin) W^T (+ bias)
+ * with M = B*n positions, TF32 operands / FP32 accumulate on tcgen05, both operands streamed in
+ * 32-deep K chunks; BatchNorm statistics, the previous layer's BatchNorm+ReLU (applied while
+ * loading), the ReLU mask and the BatchNorm-backward sums are fused in.  Any Cin, Cout, M.
+ *
+ * b2r_dense_pack     W (Cout,Cin) row-major -> the swizzled TF32 images the kernels stage by TMA:
+ *                    w_img (forward) and / or wt_img (W^T, input gradient); sizes from
+ *                    b2r_dense_image_bytes(Cout,Cin) and b2r_dense_image_bytes(Cin,Cout).
+ * b2r_dense_fwd      x = in, or relu(in*sc_in + sh_in) when sc_in != NULL; z = x W^T + bias;
+ *                    stats (2,Cout) += sum z, sum z^2 (double; NULL = none).
+ * b2r_dense_bwd      dz = g (ca == NULL) or ca*g + cb*zz + cc (b2r_bn_bwd_finalize);
+ *                    gin (M,Cin) = (dz W) * [in*sc_in + sh_in > 0]  (no mask when sc_in == NULL),
+ *                    stats_in (2,Cin) += sum gin, sum gin*in; dW (Cout,Cin) += dz^T x.
+ *                    gin and dW are optional (NULL).  sc_in / sh_in / ca / cb / cc must be
+ *                    readable up to the next multiple of 4 elements and 16-byte aligned, like the
+ *                    rows of in / g / zz (ld % 4 == 0).
+ */
+typedef struct b2r_dense_layer {
+  int M, Cin, Cout;
+  const float *in;          /* (M, ld_in) */
+  int ld_in;
+  const float *sc_in, *sh_in; /* (Cin) or NULL */
+  const float *w_img;
+  const float *bias;        /* (Cout) or NULL */
+  float *z;                 /* (M, ld_z) */
+  int ld_z;
+  double *stats;            /* (2, Cout) ACCUMULATED, or NULL */
+} b2r_dense_layer;
+
+typedef struct b2r_dense_layer_bwd {
+  int M, Cin, Cout;
+  const float *in;          /* (M, ld_in): the layer's input (before its BatchNorm+ReLU prologue) */
+  int ld_in;
+  const float *sc_in, *sh_in;
+  const float *g, *zz;      /* (M, ld_g) */
+  int ld_g;
+  const float *ca, *cb, *cc; /* (Cout) or NULL */
+  const float *wt_img;
+  float *gin;               /* (M, ld_gin) or NULL */
+  int ld_gin;
+  double *stats_in;         /* (2, Cin) ACCUMULATED, or NULL */
+  float *dW;                /* (Cout, Cin) ACCUMULATED, or NULL */
+} b2r_dense_layer_bwd;
+
+B2R_API long long b2r_dense_image_bytes(int rows, int k);
+B2R_API int b2r_dense_pack(const float *w, int Cout, int Cin, float *w_img, float *wt_img,
+                           void *stream);
+B2R_API int b2r_dense_fwd(const b2r_dense_layer *desc, void *stream);
+B2R_API int b2r_dense_bwd(const b2r_dense_layer_bwd *desc, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Point-major glue around the dense layers (csrc/heads.cu).
+ *
+ * b2r_interp_cat_fwd / _bwd: PointnetFPModule's three_interpolate + torch.cat([interpolated,
+ *   skip], dim=1) (reference pointnet2_modules.py:492-504, kernels src/interpolate_gpu.cu:77-148)
+ *   in one pass: known (B,m,C2), skip (B,n,C1) or NULL, idx / weight (B,n,3) ->
+ *   out (B*n, C2+C1) = [fma(p3,w3, fma(p1,w1, p2*w2)), skip]; backward: g (B*n, ld_g) ->
+ *   g_known (B,m,C2) ACCUMULATED (caller zeroes) and g_skip (B*n,C1) written; either may be NULL.
+ * b2r_vote_tail_fwd / _bwd: VotingModule's offset / residual split + VoteNet's L2 feature
+ *   normalisation (models/voting_module.py:56-64, models/votenet.py:93-94): net (M, ld_net) =
+ *   [offset(3), residual(C), pad] -> vote_xyz (M,3) = seed_xyz + offset, out (M,C) = v / |v|_2
+ *   with v = seed_feat + residual, norm (M); backward: g_out (M,C) / g_vote_xyz (M,3) (either
+ *   may be NULL) -> g_net (M, ld_net) fully written, g_seed_feat (M,C) (may be NULL); the seed
+ *   xyz gradient is g_vote_xyz itself. */
+B2R_API int b2r_interp_cat_fwd(const float *known, const float *skip, const int *idx,
+                               const float *weight, int B, int n, int m, int C2, int C1,
+                               float *out, void *stream);
+B2R_API int b2r_interp_cat_bwd(const float *g, int ld_g, const int *idx, const float *weight, int B,
+                               int n, int m, int C2, int C1, float *g_known, float *g_skip,
+                               void *stream);
+B2R_API int b2r_vote_tail_fwd(const float *net, int ld_net, const float *seed_xyz,
+                              const float *seed_feat, long long M, int C, float *vote_xyz,
+                              float *out, float *norm, void *stream);
+B2R_API int b2r_vote_tail_bwd(const float *g_out, const float *g_vote_xyz, const float *out,
+                              const float *norm, long long M, int C, int ld_net, float *g_net,
+                              float *g_seed_feat, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Loss-side nearest-neighbour matching: the two arg-min vectors of

@@ -47,6 +47,8 @@ def test_host_only_entry_points():
     # the ctypes mirrors of the descriptor structs have the library's layout
     assert l.b2r_struct_bytes(0) == ctypes.sizeof(_lib.SaLayer)
     assert l.b2r_struct_bytes(1) == ctypes.sizeof(_lib.SaLayerBwd)
+    assert l.b2r_struct_bytes(2) == ctypes.sizeof(_lib.DenseLayer)
+    assert l.b2r_struct_bytes(3) == ctypes.sizeof(_lib.DenseLayerBwd)
     assert l.b2r_struct_bytes(7) == -1
     # the cluster hint of b2r_fps_ex is validated like every other argument
     assert l.b2r_fps_ex(None, 1, 10, 4, None, 17, None) == -1
