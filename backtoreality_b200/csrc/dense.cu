@@ -31,12 +31,31 @@ namespace {
 
 constexpr int kDT = 128;                       // tile: 128 A rows x 128 B rows
 constexpr int kDK = 32;                        // K chunk: one 128-byte swizzle atom of TF32
-constexpr int kDStages = 6;
 constexpr uint32_t kDOperand = kDT * kDK * 4;  // 16 KB per operand per stage
 // 12 warps: warp 4 issues the MMAs; the other 11 build operand tiles during the main loop
 // (global loads -> transform -> TF32 -> swizzled smem), warps 0-3 then run the epilogue
 constexpr int kDEpi = 128, kDProd = 352, kDThreads = 384;
 constexpr int kDSlots = 3;                     // ceil(1024 float4 items / 352 threads)
+// Per mode: operand stages S (swizzled TF32 tiles the tensor core reads), raw operands R per chunk
+// (fp32 rows as they lie in global memory: x | g, z | g, z, x) and the depth D of the raw ring.
+// Raw rows arrive by cp.async D-1 chunks ahead of their use, 16 bytes per thread into slots the
+// SAME thread reads back (no barrier, no registers held across the global-memory latency).
+// (The weight tile of a stage arrives by TMA once the stage is free, i.e. S chunks ahead: S also
+// sets how much of the TMA latency is hidden.)
+__host__ __device__ constexpr int dn_stages(int mode) { return mode == 0 ? 4 : mode == 1 ? 3 : 2; }
+__host__ __device__ constexpr int dn_raws(int mode) { return mode == 0 ? 1 : mode == 1 ? 2 : 3; }
+__host__ __device__ constexpr int dn_depth(int mode) { return mode == 0 ? 4 : 3; }
+constexpr uint32_t kDRawSlot = kDSlots * kDProd * 16;   // bytes of one raw operand of one chunk
+// per-channel coefficient vectors staged in shared memory (they are read once per item):
+// [0, kDCoefX) floats: scale | shift of the x prologue (up to 512 + pad channels each),
+// then ca | cb | cc of the dz prologue (up to 384 channels each)
+constexpr int kDMaxCin = 512, kDMaxCoutBn = 512;
+constexpr uint32_t kDCoefBytes = (2 * kDMaxCin + 3 * kDMaxCoutBn) * 4;
+__host__ __device__ constexpr uint32_t dn_smem(int mode) {
+  return (uint32_t)dn_stages(mode) * 2 * kDOperand +
+         (uint32_t)dn_depth(mode) * dn_raws(mode) * kDRawSlot + kDCoefBytes +
+         (2 * dn_stages(mode) + 1) * 8 + 16 + 1024;
+}
 
 struct DenseArgs {
   int M, Cin, Cout;
@@ -84,28 +103,26 @@ __device__ __forceinline__ void dn_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// ---- raw loads of one producer item (4 consecutive channels of one position); the transform is
-// ---- applied later, when the item is stored, so that the loads of chunk j+1 are in flight while
-// ---- chunk j is converted and stored
-__device__ __forceinline__ float4 ld4_guard(const float *base, int ld, int pos, int ch, int M, int C) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+// ---- raw load of one producer item (4 consecutive channels of one position): 16 bytes by
+// ---- cp.async, zero-filled outside the tensor (src-size operand)
+__device__ __forceinline__ void cp16_guard(uint32_t dst, const float *base, int ld, int pos, int ch,
+                                           int M, int C) {
+  const float *src = base;
+  uint32_t bytes = 0;
   if (pos < M && ch < C) {
-    const float *p = base + (size_t)pos * ld + ch;
-    if (ch + 3 < C) {
-      v = __ldg(reinterpret_cast<const float4 *>(p));
-    } else {
-      v.x = __ldg(p);
-      if (ch + 1 < C) v.y = __ldg(p + 1);
-      if (ch + 2 < C) v.z = __ldg(p + 2);
-    }
+    src = base + (size_t)pos * ld + ch;
+    bytes = (uint32_t)min(4, C - ch) * 4u;
   }
-  return v;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes)
+               : "memory");
 }
 // x = in, or relu(in * sc + sh); zeros outside the tensor (coefficient vectors are padded to 4)
-__device__ __forceinline__ uint4 make_x4(const DenseArgs &a, float4 v, int pos, int ch) {
+// (s_sc / s_sh: shared-memory copies of the coefficient vectors, indexed by ch - c0)
+__device__ __forceinline__ uint4 make_x4(const DenseArgs &a, float4 v, int pos, int ch,
+                                         const float *s_sc, const float *s_sh, int c0) {
   if (a.sc_in != nullptr && pos < a.M && ch < a.Cin) {
-    const float4 sc = *reinterpret_cast<const float4 *>(a.sc_in + ch);
-    const float4 sh = *reinterpret_cast<const float4 *>(a.sh_in + ch);
+    const float4 sc = *reinterpret_cast<const float4 *>(s_sc + (ch - c0));
+    const float4 sh = *reinterpret_cast<const float4 *>(s_sh + (ch - c0));
     v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
     v.y = ch + 1 < a.Cin ? fmaxf(fmaf(v.y, sc.y, sh.y), 0.f) : 0.f;
     v.z = ch + 2 < a.Cin ? fmaxf(fmaf(v.z, sc.z, sh.z), 0.f) : 0.f;
@@ -114,11 +131,13 @@ __device__ __forceinline__ uint4 make_x4(const DenseArgs &a, float4 v, int pos, 
   return make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
 }
 // dz = g, or ca*g + cb*z + cc; zeros outside the tensor
-__device__ __forceinline__ uint4 make_dz4(const DenseArgs &a, float4 g, float4 z, int pos, int co) {
+__device__ __forceinline__ uint4 make_dz4(const DenseArgs &a, float4 g, float4 z, int pos, int co,
+                                          const float *s_ca, const float *s_cb, const float *s_cc,
+                                          int c0) {
   if (a.ca != nullptr && pos < a.M && co < a.Cout) {
-    const float4 A = *reinterpret_cast<const float4 *>(a.ca + co);
-    const float4 B = *reinterpret_cast<const float4 *>(a.cb + co);
-    const float4 C = *reinterpret_cast<const float4 *>(a.cc + co);
+    const float4 A = *reinterpret_cast<const float4 *>(s_ca + (co - c0));
+    const float4 B = *reinterpret_cast<const float4 *>(s_cb + (co - c0));
+    const float4 C = *reinterpret_cast<const float4 *>(s_cc + (co - c0));
     g.x = fmaf(A.x, g.x, fmaf(B.x, z.x, C.x));
     g.y = co + 1 < a.Cout ? fmaf(A.y, g.y, fmaf(B.y, z.y, C.y)) : 0.f;
     g.z = co + 2 < a.Cout ? fmaf(A.z, g.z, fmaf(B.z, z.z, C.z)) : 0.f;
@@ -143,17 +162,20 @@ __device__ __forceinline__ uint64_t smem_desc_mn32(uint32_t saddr) {
   return d;
 }
 
-struct RawChunk {
-  float4 a[kDSlots], b[kDSlots], c[kDSlots];
-};
-
 // MODE 0 FWD, 1 DGRAD, 2 WGRAD
 template <int MODE>
 __global__ void __launch_bounds__(kDThreads, 1) dense_gemm_kernel(const DenseArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~(uintptr_t)1023);
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(base + kDStages * 2 * kDOperand);
+  constexpr int kDStages = dn_stages(MODE), kRaws = dn_raws(MODE), kDepth = dn_depth(MODE);
+  uint8_t *s_raw = base + kDStages * 2 * kDOperand;
+  float *s_sc = reinterpret_cast<float *>(s_raw + (size_t)kDepth * kRaws * kDRawSlot);
+  float *s_sh = s_sc + kDMaxCin;
+  float *s_ca = s_sh + kDMaxCin;
+  float *s_cb = s_ca + kDMaxCoutBn;
+  float *s_cc = s_cb + kDMaxCoutBn;
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_cc + kDMaxCoutBn);
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2 * kDStages + 1);
   // mbarriers: [0,S) full  [S,2S) empty  [2S] done
   auto bar = [&](int i) { return smem_u32(&s_bar[i]); };
@@ -177,6 +199,23 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_gemm_kernel(const DenseArg
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) tmem_alloc(smem_u32(s_tmem), 128);
+  // coefficient vectors -> shared memory: the x prologue's (FWD: every input channel; WGRAD: this
+  // CTA's 128-channel block) and the dz prologue's (DGRAD: every output channel; WGRAD: block)
+  const int xc0 = MODE == 2 ? bt * kDT : 0, xcn = MODE == 2 ? kDT : ((a.Cin + 3) & ~3);
+  const int zc0 = MODE == 2 ? rb * kDT : 0, zcn = MODE == 2 ? kDT : ((a.Cout + 3) & ~3);
+  if (MODE != 1 && a.sc_in != nullptr)
+    for (int i = tid; i < xcn; i += kDThreads) {
+      const bool in = xc0 + i < ((a.Cin + 3) & ~3);
+      s_sc[i] = in ? a.sc_in[xc0 + i] : 0.f;
+      s_sh[i] = in ? a.sh_in[xc0 + i] : 0.f;
+    }
+  if (MODE != 0 && a.ca != nullptr)
+    for (int i = tid; i < zcn; i += kDThreads) {
+      const bool in = zc0 + i < ((a.Cout + 3) & ~3);
+      s_ca[i] = in ? a.ca[zc0 + i] : 0.f;
+      s_cb[i] = in ? a.cb[zc0 + i] : 0.f;
+      s_cc[i] = in ? a.cc[zc0 + i] : 0.f;
+    }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -187,29 +226,39 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_gemm_kernel(const DenseArg
     const int ptid = tid < 128 ? tid : tid - 32;
     // item i (0..1023) of a chunk: FWD/DGRAD: position row i >> 3, channel group i & 7 of the
     // chunk's 32 channels; WGRAD: position i >> 5 of the chunk's 32, channel group i & 31 of 128
-    auto load_chunk = [&](int j, RawChunk &r) {
+    // this thread's 16-byte slot of raw operand `op` of chunk j, item u
+    auto raw_slot = [&](int j, int op, int u) {
+      return s_raw + (size_t)((j % kDepth) * kRaws + op) * kDRawSlot + (size_t)(u * kDProd + ptid) * 16;
+    };
+    auto issue_chunk = [&](int j) {   // one (possibly empty) cp.async group per call
+      if (j < nch) {
 #pragma unroll
-      for (int u = 0; u < kDSlots; ++u) {
-        const int i = ptid + u * kDProd;
-        if (i < kDT * 8) {
-          if (MODE == 0) {
-            r.a[u] = ld4_guard(a.in, a.ld_in, bt * kDT + (i >> 3), j * kDK + (i & 7) * 4, a.M, a.Cin);
-          } else if (MODE == 1) {
-            const int pos = bt * kDT + (i >> 3), co = j * kDK + (i & 7) * 4;
-            r.a[u] = ld4_guard(a.g, a.ld_g, pos, co, a.M, a.Cout);
-            if (a.ca != nullptr) r.b[u] = ld4_guard(a.zz, a.ld_g, pos, co, a.M, a.Cout);
-          } else {
-            const int pl = i >> 5;
-            const int pos = pl < k_len - j * kDK ? k_begin + j * kDK + pl : a.M;   // a.M: zeros
-            const int co = rb * kDT + (i & 31) * 4, ch = bt * kDT + (i & 31) * 4;
-            r.a[u] = ld4_guard(a.g, a.ld_g, pos, co, a.M, a.Cout);
-            if (a.ca != nullptr) r.b[u] = ld4_guard(a.zz, a.ld_g, pos, co, a.M, a.Cout);
-            r.c[u] = ld4_guard(a.in, a.ld_in, pos, ch, a.M, a.Cin);
+        for (int u = 0; u < kDSlots; ++u) {
+          const int i = ptid + u * kDProd;
+          if (i < kDT * 8) {
+            if (MODE == 0) {
+              cp16_guard(smem_u32(raw_slot(j, 0, u)), a.in, a.ld_in, bt * kDT + (i >> 3),
+                         j * kDK + (i & 7) * 4, a.M, a.Cin);
+            } else if (MODE == 1) {
+              const int pos = bt * kDT + (i >> 3), co = j * kDK + (i & 7) * 4;
+              cp16_guard(smem_u32(raw_slot(j, 0, u)), a.g, a.ld_g, pos, co, a.M, a.Cout);
+              if (a.ca != nullptr)
+                cp16_guard(smem_u32(raw_slot(j, 1, u)), a.zz, a.ld_g, pos, co, a.M, a.Cout);
+            } else {
+              const int pl = i >> 5;
+              const int pos = pl < k_len - j * kDK ? k_begin + j * kDK + pl : a.M;   // a.M: zeros
+              const int co = rb * kDT + (i & 31) * 4, ch = bt * kDT + (i & 31) * 4;
+              cp16_guard(smem_u32(raw_slot(j, 0, u)), a.g, a.ld_g, pos, co, a.M, a.Cout);
+              if (a.ca != nullptr)
+                cp16_guard(smem_u32(raw_slot(j, 1, u)), a.zz, a.ld_g, pos, co, a.M, a.Cout);
+              cp16_guard(smem_u32(raw_slot(j, 2, u)), a.in, a.ld_in, pos, ch, a.M, a.Cin);
+            }
           }
         }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto store_chunk = [&](int j, const RawChunk &r) {
+    auto store_chunk = [&](int j) {
       const int s = j % kDStages, n = j / kDStages;
       mbar_wait(bar(kDStages + s), (uint32_t)((n & 1) ^ 1));   // MMAs of chunk j - S left stage s
       uint8_t *sa = stage_a(s), *sb = stage_b(s);
@@ -222,19 +271,25 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_gemm_kernel(const DenseArg
       for (int u = 0; u < kDSlots; ++u) {
         const int i = ptid + u * kDProd;
         if (i < kDT * 8) {
+          const float4 r0 = *reinterpret_cast<const float4 *>(raw_slot(j, 0, u));
           if (MODE == 0) {
             *reinterpret_cast<uint4 *>(sb + sw128_off(i >> 3, i & 7, kDT)) =
-                make_x4(a, r.a[u], bt * kDT + (i >> 3), j * kDK + (i & 7) * 4);
+                make_x4(a, r0, bt * kDT + (i >> 3), j * kDK + (i & 7) * 4, s_sc, s_sh, 0);
           } else if (MODE == 1) {
+            float4 r1 = r0;
+            if (a.ca != nullptr) r1 = *reinterpret_cast<const float4 *>(raw_slot(j, 1, u));
             *reinterpret_cast<uint4 *>(sb + sw128_off(i >> 3, i & 7, kDT)) =
-                make_dz4(a, r.a[u], r.b[u], bt * kDT + (i >> 3), j * kDK + (i & 7) * 4);
+                make_dz4(a, r0, r1, bt * kDT + (i >> 3), j * kDK + (i & 7) * 4, s_ca, s_cb, s_cc, 0);
           } else {
             const int pl = i >> 5, c4 = i & 31;
             const int pos = pl < k_len - j * kDK ? k_begin + j * kDK + pl : a.M;
+            float4 r1 = r0;
+            if (a.ca != nullptr) r1 = *reinterpret_cast<const float4 *>(raw_slot(j, 1, u));
+            const float4 r2 = *reinterpret_cast<const float4 *>(raw_slot(j, 2, u));
             *reinterpret_cast<uint4 *>(sa + mn32_off(c4 * 4, pl)) =
-                make_dz4(a, r.a[u], r.b[u], pos, rb * kDT + c4 * 4);
+                make_dz4(a, r0, r1, pos, rb * kDT + c4 * 4, s_ca, s_cb, s_cc, zc0);
             *reinterpret_cast<uint4 *>(sb + mn32_off(c4 * 4, pl)) =
-                make_x4(a, r.c[u], pos, bt * kDT + c4 * 4);
+                make_x4(a, r2, pos, bt * kDT + c4 * 4, s_sc, s_sh, xc0);
           }
         }
       }
@@ -242,16 +297,13 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_gemm_kernel(const DenseArg
       dn_bar_prod();
       if (ptid == 0) dn_arrive(bar(s));
     };
-    RawChunk r0, r1;
-    if (nch > 0) load_chunk(0, r0);
-    for (int j = 0; j < nch; j += 2) {
-      if (j + 1 < nch) load_chunk(j + 1, r1);
-      store_chunk(j, r0);
-      if (j + 1 < nch) {
-        if (j + 2 < nch) load_chunk(j + 2, r0);
-        store_chunk(j + 1, r1);
-      }
+    for (int j = 0; j < kDepth - 1; ++j) issue_chunk(j);
+    for (int j = 0; j < nch; ++j) {
+      issue_chunk(j + kDepth - 1);
+      asm volatile("cp.async.wait_group %0;" ::"n"(kDepth - 1) : "memory");   // chunk j has landed
+      store_chunk(j);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else {
     // =============================== MMA ISSUE ==================================================
     if (lane == 0) {
@@ -277,9 +329,11 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_gemm_kernel(const DenseArg
     __syncwarp();
   }
 
-  if (warp < 4) {
-    // =============================== EPILOGUE ===================================================
-    const int q = warp;
+  if (warp < 4 || warp >= 8) {
+    // =============================== EPILOGUE (8 warps) =========================================
+    // two warps per TMEM lane quadrant (warp & 3), each takes two of the four 32-column chunks
+    const int half = warp >> 3;
+    const int q = warp & 3;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int arow = rb * kDT + q * 32 + lane;   // this thread's channel
     if (nch > 0) {
@@ -291,7 +345,7 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_gemm_kernel(const DenseArg
       const float bias = (ok && a.bias != nullptr) ? a.bias[arow] : 0.f;
       double acc_s = 0.0, acc_ss = 0.0;
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = half * 2; ch < half * 2 + 2; ++ch) {
         uint32_t r[32];
         cuda::ptx::tcgen05_ld_32x32b(r, tmem_base + lane_addr + (uint32_t)(ch * 32));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -322,7 +376,7 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_gemm_kernel(const DenseArg
       const float sc = (ok && masked) ? a.sc_in[arow] : 0.f, sh = (ok && masked) ? a.sh_in[arow] : 0.f;
       double d1 = 0.0, d2 = 0.0;
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = half * 2; ch < half * 2 + 2; ++ch) {
         uint32_t r[32];
         cuda::ptx::tcgen05_ld_32x32b(r, tmem_base + lane_addr + (uint32_t)(ch * 32));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -360,10 +414,10 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_gemm_kernel(const DenseArg
     } else {
       // partial dW tile -> dW (Cout, Cin): transposed through smem (stage 0 is free: every MMA has
       // completed) so that one atomic instruction covers 32 consecutive input channels of a row
-      float *stg = reinterpret_cast<float *>(base) + warp * (32 * 33);
+      float *stg = reinterpret_cast<float *>(base) + (half * 4 + q) * (32 * 33);
       const int co0 = rb * kDT + q * 32;
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = half * 2; ch < half * 2 + 2; ++ch) {
         uint32_t r[32];
         cuda::ptx::tcgen05_ld_32x32b(r, tmem_base + lane_addr + (uint32_t)(ch * 32));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -386,13 +440,12 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_gemm_kernel(const DenseArg
   if (warp == 4) tmem_dealloc(tmem_base, 128);
 }
 
-constexpr uint32_t kDSmem = kDStages * 2 * kDOperand + (2 * kDStages + 1) * 8 + 16 + 1024;
 
 template <int MODE>
 int launch_dense(const DenseArgs &a, dim3 grid, cudaStream_t st) {
   B2R_CUDA(cudaFuncSetAttribute(dense_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)kDSmem));
-  dense_gemm_kernel<MODE><<<grid, kDThreads, kDSmem, st>>>(a);
+                                (int)dn_smem(MODE)));
+  dense_gemm_kernel<MODE><<<grid, kDThreads, dn_smem(MODE), st>>>(a);
   B2R_CHECK_LAUNCH();
   return B2R_OK;
 }
@@ -435,6 +488,10 @@ extern "C" int b2r_dense_fwd(const b2r_dense_layer *d, void *stream) {
   B2R_REQUIRE((d->sc_in == nullptr) == (d->sh_in == nullptr), "b2r_dense_fwd: scale and shift go together");
   B2R_REQUIRE((d->ld_in % 4) == 0 && aligned16(d->in) && aligned16(d->sc_in) && aligned16(d->sh_in),
               "b2r_dense_fwd: input rows / coefficient vectors must be 16-byte aligned");
+  if (d->sc_in != nullptr && d->Cin > kDMaxCin) {
+    set_error("b2r_dense_fwd: a BatchNorm+ReLU prologue supports Cin <= %d (got %d)", kDMaxCin, d->Cin);
+    return B2R_ERR_UNSUPPORTED;
+  }
   DenseArgs a = {};
   a.M = d->M; a.Cin = d->Cin; a.Cout = d->Cout;
   a.in = d->in; a.ld_in = d->ld_in; a.sc_in = d->sc_in; a.sh_in = d->sh_in;
@@ -453,6 +510,11 @@ extern "C" int b2r_dense_bwd(const b2r_dense_layer_bwd *d, void *stream) {
                   aligned16(d->cb) && aligned16(d->cc),
               "b2r_dense_bwd: gradient rows / coefficient vectors must be 16-byte aligned");
   B2R_REQUIRE((d->sc_in == nullptr) == (d->sh_in == nullptr), "b2r_dense_bwd: scale and shift go together");
+  if (d->ca != nullptr && d->Cout > kDMaxCoutBn) {
+    set_error("b2r_dense_bwd: the BatchNorm-backward form supports Cout <= %d (got %d)", kDMaxCoutBn,
+              d->Cout);
+    return B2R_ERR_UNSUPPORTED;
+  }
   DenseArgs a = {};
   a.M = d->M; a.Cin = d->Cin; a.Cout = d->Cout;
   a.in = d->in; a.ld_in = d->ld_in; a.sc_in = d->sc_in; a.sh_in = d->sh_in;

@@ -74,6 +74,86 @@ def supported(specs, x):
     return specs[0][0].in_channels % 4 == 0
 
 
+# ---- weight images packed ahead of time, off the critical path -------------------------------
+# Every layer needs its weight as a swizzled TF32 operand image (W for forward, W^T for the input
+# gradient).  `prepack` issues all of them on a side stream at the start of the step (they depend
+# on nothing but the weights); `_DenseMLP` then takes its images instead of packing inline.
+_PREPACKED = {}      # id(weight) -> (w_img, wt_img, event, weight._version, weight)
+_SIDE = {}           # device -> (pack stream, weight-gradient stream)
+_PACK_EVENTS = {}    # device -> event of the last prepack
+
+
+def _streams(dev):
+    st = _SIDE.get(dev)
+    if st is None:
+        st = _SIDE[dev] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+    return st
+
+
+def _pack(w2, Cout, Cin, need_wt):
+    lib = _lib.lib()
+    dev = w2.device
+    w_img = torch.empty(int(lib.b2r_dense_image_bytes(Cout, Cin)) // 4, dtype=torch.float32, device=dev)
+    wt_img = None
+    if need_wt:
+        wt_img = torch.empty(int(lib.b2r_dense_image_bytes(Cin, Cout)) // 4, dtype=torch.float32,
+                             device=dev)
+    _lib.check(lib.b2r_dense_pack(_ptr(w2), Cout, Cin, _ptr(w_img), _ptr(wt_img), _ext._stream()),
+               "dense_pack")
+    _ext.LAUNCHES += 1 if wt_img is None else 2
+    return w_img, wt_img
+
+
+def prepack(convs):
+    """Pack the operand images of the given 1x1 convolutions on a side stream (consumed once by
+    the next forward through each; a weight modified in between is re-packed inline)."""
+    convs = [c for c in convs if c is not None and c.weight.is_cuda]
+    if not convs or not enabled():
+        return
+    dev = convs[0].weight.device
+    for key in [k for k, ent in list(_PREPACKED.items()) if ent[4].device == dev]:
+        _PREPACKED.pop(key, None)
+    main = torch.cuda.current_stream(dev)
+    side = _streams(dev)[0]
+    side.wait_stream(main)
+    want_wt = torch.is_grad_enabled()
+    with torch.cuda.stream(side), torch.no_grad():
+        ents = []
+        for c in convs:
+            w = c.weight
+            w_img, wt_img = _pack(w.detach().reshape(c.out_channels, c.in_channels), c.out_channels,
+                                  c.in_channels, want_wt)
+            ents.append((w, w_img, wt_img))
+        ev = torch.cuda.Event()
+        ev.record(side)
+    for w, w_img, wt_img in ents:
+        _PREPACKED[id(w)] = (w_img, wt_img, ev, w._version, w)
+    _PACK_EVENTS[dev] = ev
+
+
+def prepack_join():
+    """Make the current stream wait for the last `prepack` (a CUDA-graph capture must not end
+    with the packing stream un-joined)."""
+    if not torch.cuda.is_available():
+        return
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ev = _PACK_EVENTS.pop(dev, None)
+    if ev is not None:
+        torch.cuda.current_stream().wait_event(ev)
+
+
+def _take(weight):
+    ent = _PREPACKED.pop(id(weight), None)
+    if ent is None or ent[4] is not weight or ent[3] != weight._version:
+        return None
+    main = torch.cuda.current_stream(weight.device)
+    main.wait_event(ent[2])
+    for t in ent[:2]:
+        if t is not None:
+            t.record_stream(main)
+    return ent[0], ent[1]
+
+
 class _DenseMLP(torch.autograd.Function):
     """x (M, Cin) point-major -> chain of [conv1x1 (+bias) -> BatchNorm -> ReLU], the last layer
     optionally a plain biased conv.  Returns (out_pm, out_cm):
@@ -92,24 +172,25 @@ class _DenseMLP(torch.autograd.Function):
         need = any(ctx.needs_input_grad)
         cur, ld_cur, sc, sh = x, x.shape[1], None, None
         zs, bn_saved, images = [], [], []
+        # batch statistics of every layer: ONE zero-filled buffer
+        stats_all, s_off = None, 0
+        if training:
+            stats_all = torch.zeros(sum(2 * c.out_channels for c, b in specs if b is not None),
+                                    dtype=torch.float64, device=dev)
         for l, (conv, bn) in enumerate(specs):
             w, bias = params[4 * l], params[4 * l + 1]
             Cout, Cin = conv.out_channels, conv.in_channels
-            w2 = w.detach().reshape(Cout, Cin)
-            w_img = torch.empty(int(lib.b2r_dense_image_bytes(Cout, Cin)) // 4,
-                                dtype=torch.float32, device=dev)
-            wt_img = None
-            if need and (l > 0 or ctx.needs_input_grad[0]):
-                wt_img = torch.empty(int(lib.b2r_dense_image_bytes(Cin, Cout)) // 4,
-                                     dtype=torch.float32, device=dev)
-            _lib.check(lib.b2r_dense_pack(_ptr(w2), Cout, Cin, _ptr(w_img), _ptr(wt_img), st),
-                       "dense_pack")
-            _ext.LAUNCHES += 1 if wt_img is None else 2
+            need_wt = need and (l > 0 or ctx.needs_input_grad[0])
+            taken = _take(w)
+            if taken is None or (need_wt and taken[1] is None):
+                taken = _pack(w.detach().reshape(Cout, Cin), Cout, Cin, need_wt)
+            w_img, wt_img = taken
             ld_z = _ceil4(Cout)
             z = torch.empty((M, ld_z), dtype=torch.float32, device=dev)
             stats = None
             if bn is not None and training:
-                stats = torch.zeros(2 * Cout, dtype=torch.float64, device=dev)
+                stats = stats_all[s_off:s_off + 2 * Cout]
+                s_off += 2 * Cout
             d = _lib.DenseLayer()
             d.M, d.Cin, d.Cout = M, Cin, Cout
             d.in_, d.ld_in, d.sc_in, d.sh_in = _ptr(cur), ld_cur, _ptr(sc), _ptr(sh)
@@ -178,6 +259,19 @@ class _DenseMLP(torch.autograd.Function):
         top = L - 1
         Ct = specs[top][0].out_channels
         coef = None
+        # every accumulated output from two zero-filled buffers
+        dW_all = torch.zeros(sum(c.out_channels * c.in_channels for c, _ in specs), **f32)
+        st_all = torch.zeros(sum(2 * c.out_channels for c, b in specs if b is not None),
+                             dtype=torch.float64, device=dev)
+        w_off, s_off = [0], [0]
+        for c, b_ in specs:
+            w_off.append(w_off[-1] + c.out_channels * c.in_channels)
+            s_off.append(s_off[-1] + (2 * c.out_channels if b_ is not None else 0))
+        # the weight gradients are off the dependency chain (layer l's input gradient only needs
+        # dz and W): they run on a side stream beside the chain and are joined at the end
+        main = torch.cuda.current_stream(dev)
+        wside = _streams(dev)[1]
+        keep = []     # buffers the side stream reads: alive until the join below
         if specs[top][1] is not None:
             # relu / BatchNorm backward of the output layer: mask the incoming gradient with
             # [relu(bn(z)) > 0] and take its two BatchNorm-backward sums (the pooled-output helper
@@ -186,7 +280,7 @@ class _DenseMLP(torch.autograd.Function):
             z = zs[top]
             gr = torch.empty((M, Ct), **f32)
             scratch = torch.empty((M, Ct), dtype=torch.int32, device=dev)
-            stats = torch.zeros(2 * Ct, dtype=torch.float64, device=dev)
+            stats = st_all[s_off[top]:s_off[top + 1]]
             _lib.check(lib.b2r_pool_bwd_prep(
                 _ptr(g_cm.contiguous() if g_cm is not None else None),
                 _ptr(g_pm.contiguous() if g_pm is not None else None), _ptr(z), _ptr(z),
@@ -218,6 +312,14 @@ class _DenseMLP(torch.autograd.Function):
                 b.ca, b.cb, b.cc = _ptr(coef[0]), _ptr(coef[1]), _ptr(coef[2])
             gin = stats_in = None
             want_gin = l > 0 or ctx.needs_input_grad[0]
+            # weight gradient: same descriptor, on the side stream (dz's inputs are ready now)
+            dW = dW_all[w_off[l]:w_off[l + 1]].view(Cout, Cin)
+            b.dW = _ptr(dW)
+            keep += [gr, coef]
+            wside.wait_stream(main)
+            with _ext._timed("dense_bwd"):
+                _lib.check(lib.b2r_dense_bwd(ctypes.byref(b), _vp(wside.cuda_stream)), "dense_bwd")
+            b.dW = None
             if want_gin:
                 ld_gin = zs[l - 1].shape[1] if l > 0 else x.shape[1]
                 gin = torch.empty((M, ld_gin), **f32)
@@ -225,13 +327,10 @@ class _DenseMLP(torch.autograd.Function):
                     gin[:, Cin:].zero_()
                 b.wt_img, b.gin, b.ld_gin = _ptr(images[l]), _ptr(gin), ld_gin
                 if l > 0:
-                    stats_in = torch.zeros(2 * Cin, dtype=torch.float64, device=dev)
+                    stats_in = st_all[s_off[l - 1]:s_off[l]]
                     b.stats_in = _ptr(stats_in)
-            dW = torch.zeros((Cout, Cin), **f32)
-            b.dW = _ptr(dW)
-            with _ext._timed("dense_bwd"):
                 _lib.check(lib.b2r_dense_bwd(ctypes.byref(b), st), "dense_bwd")
-            _ext.LAUNCHES += 1 if want_gin else 0
+                _ext.LAUNCHES += 1
             grads[4 * l] = dW.view_as(params[4 * l])
             if l > 0:
                 mean, invstd, _, _ = bn_saved[l - 1]
@@ -240,6 +339,7 @@ class _DenseMLP(torch.autograd.Function):
                 gr, ld_g = gin, gin.shape[1]
             else:
                 g_x = gin
+        main.wait_stream(wside)      # join: the weight gradients are complete for what follows
         return (g_x, None, None, None, None) + tuple(grads)
 
     @staticmethod

@@ -190,6 +190,10 @@ class VoteNet(nn.Module):
             bb = self.backbone_net
             fused_sa.prepack([m.mlp_module for m in (bb.sa1, bb.sa2, bb.sa3, bb.sa4,
                                                      self.pnet.vote_aggregation)])
+            # ... and of the dense FP / voting / proposal layers (dense_mlp.prepack)
+            dense_mlp.prepack([blk.conv for blk in list(bb.fp1.mlp) + list(bb.fp2.mlp)] +
+                              [self.vgen.conv1, self.vgen.conv2, self.vgen.conv3,
+                               self.pnet.conv1, self.pnet.conv2, self.pnet.conv3])
         # 'geometry' (optional, not in the reference): sa1..sa4 indices computed ahead of time
         end_points = self.backbone_net(pc, {'_prepacked': True} if prepacked else {},
                                        geometry=inputs.get('geometry'))
@@ -214,4 +218,5 @@ class VoteNet(nn.Module):
         end_points = self.pnet(xyz, features, end_points, features_pm=features_pm)
         if prepacked:
             fused_sa.prepack_join()
+            dense_mlp.prepack_join()
         return end_points

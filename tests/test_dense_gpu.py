@@ -304,7 +304,13 @@ def test_vote_heads_dense_vs_torch(cuda, training, monkeypatch):
         names = [k for k, _ in vgen.named_parameters()] + [k for k, _ in pnet.named_parameters()]
         for name, ga, gb in zip(names, a[5], b[5]):
             assert (ga is None) == (gb is None), name
-            if ga is not None and float(gb.abs().max()) > 1e-6:
-                assert rel_l2(ga.cpu().numpy(), gb.cpu().numpy()) < tol, name
+            if ga is None:
+                continue
+            if training and name in ("conv1.bias", "conv2.bias"):
+                # a bias in front of a training-mode BatchNorm has a zero gradient analytically:
+                # both arms only hold rounding noise there
+                assert float(ga.abs().max()) < 1e-3 and float(gb.abs().max()) < 1e-3, name
+                continue
+            assert rel_l2(ga.cpu().numpy(), gb.cpu().numpy()) < 2 * tol, name
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
