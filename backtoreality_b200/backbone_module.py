@@ -48,7 +48,8 @@ class Pointnet2Backbone(nn.Module):
         features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
         return xyz, features
 
-    def geometry_prepass(self, xyz, fps_cluster=0, sm_limit=None, side=None):
+    def geometry_prepass(self, xyz, fps_cluster=0, sm_limit=None, side=None, first=0, last=3,
+                         prev=None):
         """inds / new_xyz / ball-query idx of sa1..sa4 for xyz (B,N,3), issued as one chain on a
         side stream with one event per level.  Returns the list of four per-level dicts that
         `forward(..., geometry=)` and `PointnetSAModuleVotes.forward(..., geometry=)` take.
@@ -57,16 +58,23 @@ class Pointnet2Backbone(nn.Module):
         the pre-pass belongs to the NEXT batch and runs beside this batch's step,
         train_step.PipelinedTrainStep).  sm_limit: cap of the MLP kernels that will consume each
         level (int, or (forward, backward) tuple); default leaves GEOMETRY_SMS free while a later
-        level's FPS may still be running."""
+        level's FPS may still be running.
+        first / last: compute only levels first..last (0-based; default all four).  With first > 0
+        `xyz` is the new_xyz of level first-1 and `prev` the list of the earlier levels' dicts
+        (returned in front of the new ones); the FP modules' interpolation weights are computed
+        with level 3.  Lets a caller run SA1's geometry -- 2047 dependent FPS iterations over the
+        whole scene -- and the later levels' as two independent chains
+        (train_step.PipelinedTrainStep with depth 2)."""
         main = torch.cuda.current_stream()
         if side is None:
             side = _GEO_STREAMS.get(xyz.device)
             if side is None:
                 side = _GEO_STREAMS[xyz.device] = torch.cuda.Stream(device=xyz.device)
         side.wait_stream(main)
-        levels, cur = [], xyz
+        levels, cur = list(prev) if prev is not None else [], xyz
+        assert len(levels) == first
         with torch.cuda.stream(side), torch.no_grad():
-            for sa in (self.sa1, self.sa2, self.sa3, self.sa4):
+            for sa in (self.sa1, self.sa2, self.sa3, self.sa4)[first:last + 1]:
                 inds = _ext.furthest_point_sampling(cur, sa.npoint, cluster=fps_cluster)
                 new_xyz = pointnet2_utils.gather_operation(
                     cur.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
@@ -83,6 +91,8 @@ class Pointnet2Backbone(nn.Module):
                                    sm_limit=(fused_sa.NUM_SMS - GEOMETRY_SMS) if sm_limit is None
                                    else sm_limit))
                 cur = new_xyz
+            if last < 3:
+                return levels
             # the FP modules' 3-NN indices and inverse-distance weights are geometry too:
             # fp1 interpolates sa4 -> sa3, fp2 sa3 -> sa2 (stored with the last level, whose
             # event covers them)

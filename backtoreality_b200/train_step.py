@@ -176,10 +176,13 @@ class PipelinedTrainStep:
         nxt = box["nxt"]
         main.wait_stream(self.side)
         del xyz_next
+        # rotate: ONE multi-tensor copy launch for all geometry tensors of all levels
+        dsts, srcs = [], []
         for dst, src in zip(self.geo_cur, nxt):
             for k in dst:
-                dst[k].copy_(src[k])
-        self.cur.copy_(self.next)
+                dsts.append(dst[k])
+                srcs.append(src[k])
+        torch._foreach_copy_(dsts + [self.cur], srcs + [self.next])
         return loss
 
     def recapture(self):
@@ -207,6 +210,110 @@ class PipelinedTrainStep:
 
     def __call__(self, next_batch, non_blocking=True):
         self.next.copy_(next_batch, non_blocking=non_blocking)
+        self.graph.replay()
+        return self.static_loss
+
+
+class PipelinedTrainStep2(PipelinedTrainStep):
+    """The pipelined step, two batches deep.  SA1's geometry (FPS of the whole 40k-point scene:
+    2047 dependent iterations, ~2 ms on narrow clusters) and the later levels' (FPS 2048 -> 1024
+    -> 512 -> 256, ball queries, 3-NN weights: ~1 ms) are independent chains once SA1's centres
+    exist, so they run side by side, for DIFFERENT batches: the graph of step i holds
+
+        side stream A   SA1 geometry of batch i+2
+        side stream B   SA2..SA4 + FP geometry of batch i+1 (from its SA1 centres, computed by
+                        stream A during step i-1)
+        main stream     forward + backward + optimizer of batch i
+
+    and then rotates the static buffers.  The longest geometry chain beside a step is ~2 ms
+    instead of ~3 ms, which takes the pre-pass off the critical path of a ~3.5 ms step.  Every
+    call still does one complete geometry pre-pass (two halves, of two batches) and one complete
+    step; the data loader is two batches ahead:
+
+        pipe = PipelinedTrainStep2(net.backbone_net, step_fn, batch0, batch1)
+        for b in loader_from_batch2:          # call i submits batch i+2, trains on batch i
+            loss_of_batch_i = pipe(b)
+    """
+
+    def __init__(self, backbone, step_fn, first_batch, second_batch, warmup=3, fps_cluster=4,
+                 sm_caps=None, after_warmup_step=None, start_after_level=1):
+        self.backbone = backbone
+        self.step_fn = step_fn
+        self.after_warmup_step = after_warmup_step
+        self.fps_cluster = int(fps_cluster)
+        if sm_caps is None:
+            sm_caps, _ = self.default_caps(first_batch.shape[0], self.fps_cluster, start_after_level)
+        self.sm_caps = sm_caps
+        self.start_after_level = start_after_level
+        self.warmup = warmup
+        self.cur = first_batch.clone()
+        self.next = second_batch.clone()
+        self.next2 = second_batch.clone()
+        self.side = torch.cuda.Stream(device=first_batch.device)     # A: SA1 geometry
+        self.side_b = torch.cuda.Stream(device=first_batch.device)   # B: SA2..SA4 + FP geometry
+        self.geo_cur = None
+        self.geo_a_next = None      # SA1 geometry of `next`
+        self.graph = None
+        self.static_loss = None
+        self.launches_per_step = None
+        self.prime(first_batch, second_batch)
+        self.recapture()
+
+    def prime(self, batch, batch_after=None):
+        """(Re)start the pipeline: `batch` becomes the current batch and `batch_after` the one
+        after it; the geometry of the first and SA1's geometry of the second are computed now."""
+        if batch_after is None:
+            batch_after = batch
+        super().prime(batch)
+        self.next.copy_(batch_after)
+        xyz = self._xyz(self.next)
+        lv = self.backbone.geometry_prepass(xyz, side=self.side, first=0, last=0)
+        torch.cuda.current_stream().wait_stream(self.side)
+        fresh = {k: lv[0][k] for k in self._keys(lv[0])}
+        if self.geo_a_next is None:
+            self.geo_a_next = {k: v.clone() for k, v in fresh.items()}
+        else:
+            for k in self.geo_a_next:
+                self.geo_a_next[k].copy_(fresh[k])
+
+    def _pipelined(self):
+        main = torch.cuda.current_stream()
+        xyz_next2 = self._xyz(self.next2)     # referenced until the side streams are joined
+        box = {}
+
+        def launch_a():
+            box["a"] = self.backbone.geometry_prepass(xyz_next2, fps_cluster=self.fps_cluster,
+                                                      sm_limit=0, side=self.side, first=0, last=0)
+
+        # B from the start of the step: one-CTA-per-scene FPS launches, 8 SMs
+        lvl0 = dict(self.geo_a_next, event=None, sm_limit=0)
+        geo_b = self.backbone.geometry_prepass(self.geo_a_next["new_xyz"], sm_limit=0,
+                                               side=self.side_b, first=1, last=3, prev=[lvl0])
+        levels = self._levels(self.geo_cur)
+        if self.start_after_level is None:
+            launch_a()
+        else:
+            levels[self.start_after_level]["after_forward"] = launch_a
+        loss = self.step_fn(self.cur, levels)
+        if "a" not in box:
+            launch_a()
+        main.wait_stream(self.side)
+        main.wait_stream(self.side_b)
+        del xyz_next2
+        # rotate: (SA1 geometry of next, fresh later levels) -> current; fresh SA1 geometry -> next
+        dsts, srcs = [], []
+        for dst, src in zip(self.geo_cur, [self.geo_a_next] + geo_b[1:]):
+            for k in dst:
+                dsts.append(dst[k])
+                srcs.append(src[k])
+        torch._foreach_copy_(dsts + [self.cur], srcs + [self.next])
+        keys = list(self.geo_a_next)
+        torch._foreach_copy_([self.geo_a_next[k] for k in keys] + [self.next],
+                             [box["a"][0][k] for k in keys] + [self.next2])
+        return loss
+
+    def __call__(self, batch_after_next, non_blocking=True):
+        self.next2.copy_(batch_after_next, non_blocking=non_blocking)
         self.graph.replay()
         return self.static_loss
 

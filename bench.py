@@ -62,7 +62,10 @@ def parse():
                     help="launch every kernel from Python instead of replaying the captured step")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="geometry pre-pass of a batch inside its own step (not one step ahead)")
-    ap.add_argument("--fps-cluster", type=int, default=4,
+    ap.add_argument("--pipeline-depth", type=int, default=1, choices=[1, 2],
+                    help="pipelined step: 1 = whole geometry pre-pass of batch i+1 beside step i; 2 = SA1 "
+                         "geometry of batch i+2 and the later levels' of batch i+1 beside step i")
+    ap.add_argument("--fps-cluster", type=int, default=5,
                     help="pipelined step: CTAs per scene of the next batch's FPS")
     ap.add_argument("--trace", default="",
                     help="after timing, trace 3 steps with torch.profiler (CUPTI) and write a per-kernel "
@@ -417,7 +420,8 @@ def run_b2r(a):
     pipelined = not (a.no_graph or a.no_pipeline)
     if not a.no_graph:
         try:
-            from backtoreality_b200.train_step import CapturedTrainStep, PipelinedTrainStep
+            from backtoreality_b200.train_step import (CapturedTrainStep, PipelinedTrainStep,
+                                                       PipelinedTrainStep2)
             stage("capturing the step into a CUDA graph")
             if pipelined:
                 # the vote-aggregation block has no pre-pass level of its own: give its kernels the
@@ -428,10 +432,17 @@ def run_b2r(a):
                     caps = [tuple(int(v) for v in c.split(":")) for c in a.sm_caps.split(",")]
                     caps, head_cap = caps[:4], caps[4]
                 net.pnet.vote_aggregation.sm_limit = head_cap
-                graphed = PipelinedTrainStep(net.backbone_net, step if capture_all else fwd_bwd,
-                                             resident[0], fps_cluster=a.fps_cluster, sm_caps=caps,
-                                             after_warmup_step=None if capture_all else finish,
-                                             start_after_level=start)
+                if a.pipeline_depth == 2:
+                    graphed = PipelinedTrainStep2(net.backbone_net, step if capture_all else fwd_bwd,
+                                                  resident[0], resident[1], fps_cluster=a.fps_cluster,
+                                                  sm_caps=caps,
+                                                  after_warmup_step=None if capture_all else finish,
+                                                  start_after_level=start)
+                else:
+                    graphed = PipelinedTrainStep(net.backbone_net, step if capture_all else fwd_bwd,
+                                                 resident[0], fps_cluster=a.fps_cluster, sm_caps=caps,
+                                                 after_warmup_step=None if capture_all else finish,
+                                                 start_after_level=start)
             else:
                 graphed = CapturedTrainStep(step if capture_all else fwd_bwd, resident[0],
                                             after_warmup_step=None if capture_all else finish)
@@ -452,11 +463,17 @@ def run_b2r(a):
 
     # pipelined: call i submits batch i+1 (whose geometry pre-pass runs in this call) and trains
     # on batch i; resident[0] was submitted by the constructor
-    nxt = 1 if pipelined else 0
+    nxt = (a.pipeline_depth if pipelined else 0)
+
+    def prime():
+        if pipelined and a.pipeline_depth == 2:
+            graphed.prime(resident[0], resident[1])
+        elif pipelined:
+            graphed.prime(resident[0])
+
     for i in range(3):
         run_step(resident[(i + nxt) % pool_n])
-    if pipelined:
-        graphed.prime(resident[0])
+    prime()
     sampler = ClockSampler(dev) if rank == 0 else None
     time.sleep(0.3)
 
@@ -484,8 +501,7 @@ def run_b2r(a):
         pc = host[i % pool_n].to(dev, non_blocking=True)
         return float(step(pc).item())
 
-    if pipelined:
-        graphed.prime(resident[0])
+    prime()
     for i in range(2):
         e2e_step(i)
     up0 = pre.bytes_uploaded if pre is not None else 0

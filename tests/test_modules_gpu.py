@@ -343,6 +343,55 @@ def test_pipelined_train_step_matches_sequential(cuda, start_after_level):
         assert rel_l2(p2.grad.cpu().numpy(), p1.grad.cpu().numpy()) < 3e-2, n1
 
 
+@pytest.mark.parametrize("start_after_level", [None, 1])
+def test_pipelined_train_step_depth2_matches_sequential(cuda, start_after_level):
+    """train_step.PipelinedTrainStep2: SA1's geometry of batch i+2 and the later levels' geometry
+    of batch i+1 run beside the step of batch i.  Same contract as the depth-1 pipeline: call i
+    returns the eager loss of batch i, the rotated buffers hold what a fresh pre-pass computes."""
+    from backtoreality_b200.train_step import PipelinedTrainStep2
+    from backtoreality_b200.votenet import VoteNet
+
+    def make():
+        torch.manual_seed(5)
+        net = VoteNet(4, 1, 4, np.ones((4, 3), np.float32), input_feature_dim=1, num_proposal=64,
+                      vote_factor=1, sampling="vote_fps").to(cuda).train()
+        opt = torch.optim.SGD(net.parameters(), lr=0.0)
+
+        def step(pc, geometry=None):
+            for p in net.parameters():
+                p.grad = None
+            ep = net({"point_clouds": pc, "geometry": geometry})
+            loss = (ep["proposal_scores_raw"] ** 2).mean() + ((ep["vote_xyz"] - ep["seed_xyz"]) ** 2).mean()
+            loss.backward()
+            opt.step()
+            return loss.detach()
+        return net, step
+
+    batches = [torch.from_numpy(scenes.batch(300 + 2 * i, 2, 12000, C=1, kind="room", dup=0.2)).to(cuda)
+               for i in range(5)]
+    net_e, step_e = make()
+    eager = [float(step_e(b)) for b in batches]
+    net_p, step_p = make()
+    net_p.pnet.vote_aggregation.sm_limit = (100, 120)
+    pipe = PipelinedTrainStep2(net_p.backbone_net, step_p, batches[0], batches[1], warmup=2,
+                               fps_cluster=3, start_after_level=start_after_level)
+    pipe.prime(batches[0], batches[1])
+    got = [float(pipe(batches[(i + 2) % 5])) for i in range(5)]   # call i trains on batch i
+    assert len(set(got)) == 5
+    for g, e in zip(got, eager):
+        assert abs(g - e) <= 1e-5 * abs(e), (got, eager)
+    # after five calls the current batch is batches[0] again and the next one batches[1]
+    torch.cuda.synchronize()
+    assert torch.equal(pipe.cur, batches[0]) and torch.equal(pipe.next, batches[1])
+    fresh = net_p.backbone_net.geometry_prepass(batches[0][..., :3].contiguous())
+    fresh1 = net_p.backbone_net.geometry_prepass(batches[1][..., :3].contiguous())
+    torch.cuda.synchronize()
+    for lv_p, lv_f in zip(pipe.geo_cur + [pipe.geo_a_next], fresh + [fresh1[0]]):
+        for k in lv_p:
+            n = int(lv_f["cmeta"][8]) if k in ("cidx", "ccen") else None
+            assert torch.equal(lv_p[k][:n], lv_f[k][:n]), k
+
+
 def test_geometry_stream_matches_serial_path(cuda):
     """Pointnet2Backbone with the geometry pre-pass on a side stream (FPS / centre gather / ball
     query of all levels ahead of the MLPs, MLP grids capped to leave SMs free) must compute what
