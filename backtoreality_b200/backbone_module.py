@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import _ext, fused_sa, pointnet2_utils
-from .pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
+from .pointnet2_modules import PointnetFPModule, PointnetSAModuleCenters, PointnetSAModuleVotes
 
 # FPS, centre gather and ball query of ALL four levels depend only on xyz:
 # run them as a chain on a side stream so that FPS of level l+1 overlaps the MLP of level l.
@@ -24,10 +24,15 @@ _GEO_STREAMS = {}   # device -> side stream (module-level: nn.Module copies stay
 
 class Pointnet2Backbone(nn.Module):
     """input_feature_dim: channels per point beyond xyz (1 = height for VoteNet, 0 for GF3D).
-    fp2_out: 256 (VoteNet) or 288 (GroupFree3D)."""
+    fp2_out: 256 (VoteNet) or 288 (GroupFree3D).  width / depth: accepted for signature parity
+    with the GroupFree3D reference (models/backbone_module.py:21-33), whose constructor takes
+    them; only the published configuration width = 1, depth = 2 is built (it fixes the SA / FP
+    channel tables above and the state-dict layout)."""
 
-    def __init__(self, input_feature_dim=0, fp2_out=256):
+    def __init__(self, input_feature_dim=0, fp2_out=256, width=1, depth=2):
         super().__init__()
+        if width != 1 or depth != 2:
+            raise NotImplementedError("only width=1, depth=2 (the reference's defaults) are built")
         self.sa1 = PointnetSAModuleVotes(npoint=2048, radius=0.2, nsample=64,
                                          mlp=[input_feature_dim, 64, 64, 128],
                                          use_xyz=True, normalize_xyz=True)
@@ -201,4 +206,30 @@ class Pointnet2Backbone(nn.Module):
         end_points['fp2_inds'] = end_points['sa1_inds'][:, 0:num_seed]
         if not end_points.pop('_prepacked', False):
             fused_sa.prepack_join()
+        return end_points
+
+
+class Pointnet2Backbone_jitter(Pointnet2Backbone):
+    """The CenterRefine backbone (reference models/backbone_module.py:136-262): Pointnet2Backbone
+    plus `ctjt_head`, a PointnetSAModuleCenters(npoint=64, radius=0.8, nsample=16, mlp=[256,128],
+    normalize_xyz=False) that pools the fp2 seed features around externally supplied (jittered)
+    object centres and appends their one-hot class.  Same sub-module names / state-dict keys.
+
+    forward(pointcloud, center_xyz (B,64,3) | None, center_cls (B,64) int | None, end_points)
+        -> end_points (+ 'center_features' (B, 128 + 22, 64) when center_xyz is given)
+    """
+    NUM_CLASS = 22    # torch.eye(22) in the reference (:260)
+
+    def __init__(self, input_feature_dim=0):
+        super().__init__(input_feature_dim=input_feature_dim, fp2_out=256)
+        self.ctjt_head = PointnetSAModuleCenters(npoint=64, radius=0.8, nsample=16, mlp=[256, 128],
+                                                 use_xyz=True, normalize_xyz=False)
+
+    def forward(self, pointcloud, center_xyz=None, center_cls=None, end_points=None, geometry=None):
+        end_points = super().forward(pointcloud, end_points, geometry=geometry)
+        if center_xyz is not None:
+            center_features = self.ctjt_head(end_points['sa2_xyz'], end_points['fp2_features'],
+                                             center_xyz)
+            onehot = torch.eye(self.NUM_CLASS, device=center_features.device)[center_cls.long()]
+            end_points['center_features'] = torch.cat([center_features, onehot.transpose(1, 2)], dim=1)
         return end_points

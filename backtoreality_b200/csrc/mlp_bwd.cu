@@ -360,7 +360,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
       // ---- X tile ---------------------------------------------------------------------------
       if (kMode == 0) {
         // indices of this tile were requested one tile ago (nidx): no dependent global wait here
-        if (ptid < NT) {
+        if constexpr (kProdThreads < NT) {
+          // fewer producer threads than rows (8 epilogue warps leave 3 producer warps: a one-layer
+          // block, gather AND pooled top, on 128-position tiles): plain loop, no register prefetch
+          for (int r = ptid; r < NT; r += kProdThreads) {
+            if constexpr (CMP) {
+              s_idx[r] = __ldg(a.cidx + pos0 + r);
+              s_cen[r] = __ldg(a.ccen + pos0 + r);
+            } else {
+              s_idx[r] = __ldg(a.idx + pos0 + r);
+            }
+          }
+        } else if (ptid < NT) {
           if constexpr (CMP) {
             s_idx[ptid] = (k == 0) ? a.cidx[pos0 + ptid] : nidx;
             s_cen[ptid] = (k == 0) ? a.ccen[pos0 + ptid] : ncen;

@@ -6,6 +6,9 @@ the detectors instantiate:
     PointnetSAModuleVotes    (:164-272)   used by Pointnet2Backbone and ProposalModule
     PointnetFPModule         (:454-514)   used by Pointnet2Backbone
     PointnetSAModuleCenters  (:357-451)   used by the CenterRefine backbones
+    PointnetSAModuleOffset   GroupFree3D/pointnet2/pointnet2_modules.py:481-576 (imported by
+                             models/detector_DA.py:16)
+    ThreeNNInterpolate       GroupFree3D/pointnet2/pointnet2_modules.py:722-730
 
 Constructor keyword arguments, forward signatures, return tuples, sub-module names
 (`grouper`, `mlp_module`, `mlp`) and therefore state-dict keys are the reference's.  The
@@ -154,6 +157,31 @@ class PointnetSAModuleCenters(_SAVotesBase):
 
     def forward(self, xyz: torch.Tensor, features: torch.Tensor, centers: torch.Tensor):
         return self._abstract(xyz, centers, features)[0]
+
+
+class PointnetSAModuleOffset(_SAVotesBase):
+    """Set abstraction around externally supplied points (GroupFree3D reference
+    pointnet2/pointnet2_modules.py:481-576): same computation as PointnetSAModuleCenters with the
+    third argument named `new_xyz`, plus the `ret_unique_cnt` return form (new_features,
+    unique_cnt), which -- like in PointnetSAModuleVotes -- runs the unfused QueryAndGroup.
+
+    forward(xyz (B,N,3), features (B,C,N), new_xyz (B,npoint,3)) -> new_features (B,mlp[-1],npoint)
+    """
+
+    def forward(self, xyz: torch.Tensor, features: torch.Tensor, new_xyz: torch.Tensor):
+        if self.ret_unique_cnt:
+            grouped_features, grouped_xyz, unique_cnt = self.grouper(xyz, new_xyz, features)
+            new_features = self.mlp_module(grouped_features)
+            return _pool(new_features, grouped_xyz, self.pooling, self.sigma, self.nsample), unique_cnt
+        return self._abstract(xyz, new_xyz, features)[0]
+
+
+def ThreeNNInterpolate(known_feats, known_xyz, unknown_xyz):
+    """Inverse-distance 3-NN interpolation of known_feats (B,C,m) at unknown_xyz (B,n,3)
+    (GroupFree3D reference pointnet2/pointnet2_modules.py:722-730; the front half of
+    PointnetFPModule.forward as a free function) -> (B,C,n)."""
+    idx, weight = PointnetFPModule.interpolation_weights(unknown_xyz, known_xyz)
+    return pointnet2_utils.three_interpolate(known_feats, idx, weight)
 
 
 class PointnetFPModule(nn.Module):

@@ -20,8 +20,9 @@ _V = os.path.join(REF_ROOT, "detection", "Votenet")
 _G = os.path.join(REF_ROOT, "detection", "GroupFree3D")
 
 
-def available():
-    return os.path.isfile(os.path.join(_V, "pointnet2", "pointnet2_utils.py"))
+def available(ref_root=None):
+    v = _V if ref_root is None else os.path.join(ref_root, "detection", "Votenet")
+    return os.path.isfile(os.path.join(v, "pointnet2", "pointnet2_utils.py"))
 
 
 def _load(name, path, aliases=()):
@@ -37,12 +38,20 @@ def _load(name, path, aliases=()):
 class RefStack:
     """Holds the reference modules for one flavour ('votenet' or 'groupfree3d')."""
 
-    def __init__(self, flavour="votenet"):
-        from . import fake_ext
+    def __init__(self, flavour="votenet", ref_root=None, ext=None):
+        """ref_root: a tree laid out like the reference (default /root/reference; the GPU tests
+        pass the vendored copy under baseline/_ref).  ext: the module to serve as `pointnet2._ext`
+        (default: the CPU oracle facade; the GPU tests pass the product's shim, i.e. the
+        reference's unmodified Python then runs on libb2r.so -- INTEGRATION.md option A)."""
+        if ext is None:
+            from . import fake_ext
+        else:
+            fake_ext = ext
 
-        if not available():
-            raise RuntimeError("reference tree not present at %s" % REF_ROOT)
-        root = _V if flavour == "votenet" else _G
+        if not available(ref_root):
+            raise RuntimeError("reference tree not present at %s" % (ref_root or REF_ROOT))
+        base = REF_ROOT if ref_root is None else ref_root
+        root = os.path.join(base, "detection", "Votenet" if flavour == "votenet" else "GroupFree3D")
         saved = {k: sys.modules.get(k) for k in
                  ("pointnet2", "pointnet2._ext", "pointnet2_utils", "pytorch_utils",
                   "pointnet2_modules")}
@@ -53,7 +62,7 @@ class RefStack:
             pkg._ext = fake_ext
             sys.modules["pointnet2"] = pkg
             sys.modules["pointnet2._ext"] = fake_ext
-            tag = "_b2r_ref_%s_" % flavour
+            tag = "_b2r_ref_%s_%s_" % (flavour, "cpu" if ext is None else "gpu")
             self.pytorch_utils = _load(tag + "pytorch_utils",
                                        os.path.join(root, "pointnet2", "pytorch_utils.py"),
                                        aliases=("pytorch_utils",))
@@ -68,6 +77,8 @@ class RefStack:
             if flavour == "votenet":
                 self.voting_module = _load(tag + "voting_module",
                                            os.path.join(root, "models", "voting_module.py"))
+                self.proposal_module = _load(tag + "proposal_module",
+                                             os.path.join(root, "models", "proposal_module.py"))
         finally:
             for k, v in saved.items():
                 if v is None:
@@ -75,3 +86,19 @@ class RefStack:
                 else:
                     sys.modules[k] = v
             sys.path[:] = saved_path
+
+
+class cuda_is_identity:
+    """The reference hard-codes `.cuda()` in a few places on this path (decode_scores,
+    proposal_module.py:40; Pointnet2Backbone_jitter.forward, backbone_module.py:260): inside this
+    context Tensor.cuda() returns the tensor itself so those lines run on the CPU oracle."""
+
+    def __enter__(self):
+        import torch
+        self._saved = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.Tensor.cuda = self._saved

@@ -112,6 +112,113 @@ def fp_case(seed):
             "g_uf": sub(uf.grad), "g_kf": kf.grad.numpy().copy()}
 
 
+def centers_case(seed):
+    """PointnetSAModuleCenters (pointnet2_modules.py:357-451) as the CenterRefine head uses it
+    (backbone_module.py:188-195): external centres, normalize_xyz=False, a ONE-layer MLP."""
+    rs = ref_python.RefStack("votenet")
+    torch.manual_seed(seed)
+    head = rs.pointnet2_modules.PointnetSAModuleCenters(npoint=32, radius=0.8, nsample=16,
+                                                        mlp=[64, 32], use_xyz=True,
+                                                        normalize_xyz=False)
+    g = torch.Generator().manual_seed(seed + 1)
+    xyz = (torch.rand(2, 300, 3, generator=g) * 3.0).requires_grad_(True)
+    feats = torch.randn(2, 64, 300, generator=g).requires_grad_(True)
+    centers = (xyz.detach()[:, :32] + 0.05 * torch.randn(2, 32, 3, generator=g)).requires_grad_(True)
+    y = head(xyz, feats, centers)
+    patt = pattern_like(y)
+    (y * patt).sum().backward()
+    out = {"seed": seed, "wsum": weight_checksum(head), "y": y.detach().numpy(),
+           "g_xyz": xyz.grad.numpy().copy(), "g_centers": centers.grad.numpy().copy(),
+           "g_feats": sub(feats.grad), "g_w": head.mlp_module.layer0.conv.weight.grad.numpy().copy()}
+    # GroupFree3D's PointnetSAModuleOffset (pointnet2_modules.py:481-576): three layers
+    rg = ref_python.RefStack("groupfree3d")
+    torch.manual_seed(seed)
+    off = rg.pointnet2_modules.PointnetSAModuleOffset(npoint=32, radius=0.6, nsample=16,
+                                                      mlp=[64, 32, 32, 48], use_xyz=True,
+                                                      normalize_xyz=True)
+    y2 = off(xyz.detach(), feats.detach(), centers.detach())
+    out.update({"wsum_off": weight_checksum(off), "y_off": y2.detach().numpy()})
+    # ... and its free-function interpolation (:722-730)
+    known_xyz = xyz.detach()[:, :40].contiguous()
+    out["tni"] = rg.pointnet2_modules.ThreeNNInterpolate(feats.detach()[:, :, :40].contiguous(), known_xyz,
+                                                        xyz.detach()[:, 100:180].contiguous()).numpy()
+    return out
+
+
+def jitter_backbone_case(seed):
+    """Pointnet2Backbone_jitter (backbone_module.py:136-262) with centres: the reference's
+    `.cuda()` on the one-hot classes (:260) is neutralised for the CPU run."""
+    rs = ref_python.RefStack("votenet")
+    torch.manual_seed(seed)
+    net = rs.backbone_module.Pointnet2Backbone_jitter(input_feature_dim=1)
+    net.train(True)
+    pc = torch.from_numpy(scenes.batch(60, 2, 3000, C=1, kind="room", dup=0.2))
+    g = torch.Generator().manual_seed(seed + 1)
+    center_xyz = pc[:, :64, :3].clone() + 0.1 * torch.randn(2, 64, 3, generator=g)
+    center_cls = torch.randint(0, 22, (2, 64), generator=g)
+    with ref_python.cuda_is_identity():
+        ep = net(pc, center_xyz, center_cls)
+    cf = ep["center_features"]
+    patt = pattern_like(cf)
+    (cf * patt).sum().backward()
+    return {"seed": seed, "wsum": weight_checksum(net), "center_xyz": center_xyz.numpy(),
+            "center_cls": center_cls.numpy(), "center_features": cf.detach().numpy(),
+            "fp2_features": sub(ep["fp2_features"]),
+            "g_ctjt": net.ctjt_head.mlp_module.layer0.conv.weight.grad.numpy().copy(),
+            "g_fp2_l1": sub(net.fp2.mlp.layer1.conv.weight.grad),
+            "g_sa1_l0": sub(net.sa1.mlp_module.layer0.conv.weight.grad)}
+
+
+def vote_heads_case(seed, train):
+    """VotingModule (voting_module.py:15-65) -> L2 normalisation (votenet.py:93-94) ->
+    ProposalModule (proposal_module.py:52-120, seed_fps sampling so that the proposals do not
+    depend on the votes' last bits): the callers on either side of the vote aggregation."""
+    rs = ref_python.RefStack("votenet")
+    torch.manual_seed(seed)
+    vgen = rs.voting_module.VotingModule(1, 256)
+    msa = np.linspace(0.3, 2.0, 4 * 3).reshape(4, 3).astype(np.float32)
+    pnet = rs.proposal_module.ProposalModule(4, 2, 4, msa, 32, "seed_fps")
+    for m in list(vgen.modules()) + list(pnet.modules()):
+        if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            m.momentum = 0.2
+            if not train:     # non-trivial running statistics for the eval case
+                m.running_mean.data = torch.randn(m.running_mean.shape) * 0.1
+                m.running_var.data = torch.rand(m.running_var.shape) + 0.5
+    vgen.train(train)
+    pnet.train(train)
+    g = torch.Generator().manual_seed(seed + 1)
+    seed_xyz = (torch.rand(2, 256, 3, generator=g) * 3.0).requires_grad_(True)
+    seed_feat = torch.randn(2, 256, 256, generator=g).requires_grad_(True)
+    vote_xyz, vote_feat = vgen(seed_xyz, seed_feat)
+    vote_feat = vote_feat.div(torch.norm(vote_feat, p=2, dim=1).unsqueeze(1))
+    with ref_python.cuda_is_identity():
+        ep = pnet(vote_xyz, vote_feat, {"seed_xyz": seed_xyz})
+    loss = ((ep["objectness_scores"] * 0.7).sum() + (ep["center"] * 0.3).sum() +
+            (ep["size_residuals"] * pattern_like(ep["size_residuals"])).sum() +
+            (ep["sem_cls_scores"] * pattern_like(ep["sem_cls_scores"])).sum() +
+            (vote_xyz * 0.11).sum())
+    loss.backward()
+    out = {"seed": seed, "train": int(train), "wsum": weight_checksum(vgen) + weight_checksum(pnet),
+           "msa": msa, "vote_xyz": vote_xyz.detach().numpy(), "vote_feat": sub(vote_feat),
+           "inds": ep["aggregated_vote_inds"].numpy(),
+           "agg_xyz": ep["aggregated_vote_xyz"].detach().numpy(),
+           "agg_feat": sub(ep["aggregated_vote_features"]),
+           "objectness": ep["objectness_scores"].detach().numpy(),
+           "center": ep["center"].detach().numpy(),
+           "size_residuals": sub(ep["size_residuals"]), "sem_cls": ep["sem_cls_scores"].detach().numpy(),
+           "pred_size": ep["pred_size"].detach().numpy(),
+           "g_seed_xyz": seed_xyz.grad.numpy().copy(), "g_seed_feat": sub(seed_feat.grad),
+           "g_vgen_c1": sub(vgen.conv1.weight.grad), "g_vgen_c3": sub(vgen.conv3.weight.grad),
+           "g_vgen_c3_b": vgen.conv3.bias.grad.numpy().copy(),
+           "g_vgen_bn2": vgen.bn2.weight.grad.numpy().copy(),
+           "g_pnet_c1": sub(pnet.conv1.weight.grad), "g_pnet_c3_b": pnet.conv3.bias.grad.numpy().copy(),
+           "g_pnet_c2_b": pnet.conv2.bias.grad.numpy().copy()}
+    if train:
+        out["rm_vgen_bn1"] = vgen.bn1.running_mean.numpy().copy()
+        out["rv_pnet_bn2"] = pnet.bn2.running_var.numpy().copy()
+    return out
+
+
 def main():
     if not ref_python.available():
         raise SystemExit("reference tree not found; fixtures can only be generated in the "
@@ -124,6 +231,10 @@ def main():
                         **backbone_case("groupfree3d", 0, 288, 3000, 2, 4321, train=True))
     np.savez_compressed(os.path.join(HERE, "vote_aggregation.npz"), **vote_aggregation_case(77))
     np.savez_compressed(os.path.join(HERE, "fp_module.npz"), **fp_case(99))
+    np.savez_compressed(os.path.join(HERE, "centers_offset.npz"), **centers_case(55))
+    np.savez_compressed(os.path.join(HERE, "backbone_jitter.npz"), **jitter_backbone_case(2468))
+    np.savez_compressed(os.path.join(HERE, "vote_heads_train.npz"), **vote_heads_case(31, True))
+    np.savez_compressed(os.path.join(HERE, "vote_heads_eval.npz"), **vote_heads_case(31, False))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -70,3 +70,36 @@ def test_fp_module_port():
     (y * pattern_like(y)).sum().backward()
     assert rel_l2(kf.grad.numpy(), g["g_kf"]) < 1e-4
     assert rel_l2(sub(uf.grad), g["g_uf"]) < 1e-4
+
+
+def test_new_module_parameter_layouts_match_the_reference_checksums():
+    """the product's restatements of PointnetSAModuleCenters / Offset,
+    Pointnet2Backbone_jitter, VotingModule and ProposalModule create their parameters in the
+    reference's order and shapes: seeded initialisation reproduces the weight checksums stored in
+    the fixtures that tests/golden/make_golden.py generated from the reference's own modules."""
+    import numpy as np
+    import torch
+    from _util import golden, weight_checksum
+    from backtoreality_b200.backbone_module import Pointnet2Backbone_jitter
+    from backtoreality_b200.pointnet2_modules import PointnetSAModuleCenters, PointnetSAModuleOffset
+    from backtoreality_b200.votenet import ProposalModule, VotingModule
+    g = golden("centers_offset.npz")
+    torch.manual_seed(int(g["seed"]))
+    head = PointnetSAModuleCenters(npoint=32, radius=0.8, nsample=16, mlp=[64, 32], use_xyz=True,
+                                   normalize_xyz=False)
+    assert abs(weight_checksum(head) - float(g["wsum"])) < 1e-6 * float(g["wsum"])
+    torch.manual_seed(int(g["seed"]))
+    off = PointnetSAModuleOffset(npoint=32, radius=0.6, nsample=16, mlp=[64, 32, 32, 48],
+                                 use_xyz=True, normalize_xyz=True)
+    assert abs(weight_checksum(off) - float(g["wsum_off"])) < 1e-6 * float(g["wsum_off"])
+    g = golden("backbone_jitter.npz")
+    torch.manual_seed(int(g["seed"]))
+    net = Pointnet2Backbone_jitter(input_feature_dim=1)
+    assert abs(weight_checksum(net) - float(g["wsum"])) < 1e-6 * float(g["wsum"])
+    assert "ctjt_head.mlp_module.layer0.conv.weight" in net.state_dict()
+    g = golden("vote_heads_train.npz")
+    torch.manual_seed(int(g["seed"]))
+    vgen = VotingModule(1, 256)
+    pnet = ProposalModule(4, 2, 4, g["msa"], 32, "seed_fps")
+    assert abs(weight_checksum(vgen) + weight_checksum(pnet) - float(g["wsum"])) < 1e-6 * float(g["wsum"])
+    assert pnet.conv3.out_channels == 2 + 3 + 2 * 2 + 4 * 4 + 4

@@ -531,3 +531,134 @@ def test_two_forwards_one_backward_is_the_sum_of_two_steps(cuda):
     for n in both:
         want = (ga[n] + gb[n]).cpu().numpy()
         assert rel_l2(both[n].cpu().numpy(), want) < 3e-2, n
+
+
+# ---------------- goldens from the reference's own Python (make_golden.py) ----
+def test_centers_offset_and_three_nn_interpolate_golden(cuda, fp32_mlp):
+    """PointnetSAModuleCenters (V pointnet2_modules.py:357-451), GroupFree3D's
+    PointnetSAModuleOffset (:481-576) and ThreeNNInterpolate (:722-730) against fixtures generated
+    from the reference's unmodified modules."""
+    from backtoreality_b200.pointnet2_modules import (PointnetSAModuleCenters, PointnetSAModuleOffset,
+                                                      ThreeNNInterpolate)
+    g = golden("centers_offset.npz")
+    ftol, gtol = fp32_mlp
+    seed = int(g["seed"])
+    torch.manual_seed(seed)
+    head = PointnetSAModuleCenters(npoint=32, radius=0.8, nsample=16, mlp=[64, 32], use_xyz=True,
+                                   normalize_xyz=False)
+    assert abs(weight_checksum(head) - float(g["wsum"])) < 1e-6 * float(g["wsum"])
+    head = head.to(cuda)
+    gen = torch.Generator().manual_seed(seed + 1)
+    xyz0 = torch.rand(2, 300, 3, generator=gen) * 3.0
+    feats0 = torch.randn(2, 64, 300, generator=gen)
+    centers0 = xyz0[:, :32] + 0.05 * torch.randn(2, 32, 3, generator=gen)
+    xyz = xyz0.to(cuda).requires_grad_(True)
+    feats = feats0.to(cuda).requires_grad_(True)
+    centers = centers0.to(cuda).requires_grad_(True)
+    y = head(xyz, feats, centers)
+    assert rel_l2(y.detach().cpu().numpy(), g["y"]) < ftol
+    (y * pattern_like(y)).sum().backward()
+    assert rel_l2(xyz.grad.cpu().numpy(), g["g_xyz"]) < gtol
+    assert rel_l2(centers.grad.cpu().numpy(), g["g_centers"]) < gtol
+    assert rel_l2(sub(feats.grad), g["g_feats"]) < gtol
+    assert rel_l2(head.mlp_module.layer0.conv.weight.grad.cpu().numpy(), g["g_w"]) < gtol
+    torch.manual_seed(seed)
+    off = PointnetSAModuleOffset(npoint=32, radius=0.6, nsample=16, mlp=[64, 32, 32, 48],
+                                 use_xyz=True, normalize_xyz=True)
+    assert abs(weight_checksum(off) - float(g["wsum_off"])) < 1e-6 * float(g["wsum_off"])
+    y2 = off.to(cuda)(xyz.detach(), feats.detach(), centers.detach())
+    assert rel_l2(y2.detach().cpu().numpy(), g["y_off"]) < ftol
+    tni = ThreeNNInterpolate(feats.detach()[:, :, :40].contiguous(), xyz.detach()[:, :40].contiguous(),
+                             xyz.detach()[:, 100:180].contiguous())
+    assert rel_l2(tni.cpu().numpy(), g["tni"]) < 1e-6
+
+
+def test_jitter_backbone_golden(cuda):
+    """Pointnet2Backbone_jitter (V models/backbone_module.py:136-262) with centres, product path
+    (fused SA blocks + dense FP layers) against the reference's fp32 CPU run."""
+    from backtoreality_b200.backbone_module import Pointnet2Backbone_jitter
+    g = golden("backbone_jitter.npz")
+    torch.manual_seed(int(g["seed"]))
+    net = Pointnet2Backbone_jitter(input_feature_dim=1)
+    assert abs(weight_checksum(net) - float(g["wsum"])) < 1e-6 * float(g["wsum"])
+    net = net.to(cuda).train()
+    pc = torch.from_numpy(scenes.batch(60, 2, 3000, C=1, kind="room", dup=0.2)).to(cuda)
+    cx = torch.from_numpy(g["center_xyz"]).to(cuda)
+    cc = torch.from_numpy(g["center_cls"]).to(cuda)
+    ep = net(pc, cx, cc)
+    cf = ep["center_features"]
+    assert cf.shape == (2, 128 + 22, 64)
+    assert torch.equal(cf[:, 128:].detach().cpu(), torch.from_numpy(g["center_features"][:, 128:]))
+    # five TF32 blocks + two dense FP modules deep
+    assert rel_l2(sub(ep["fp2_features"]), g["fp2_features"]) < 2e-2
+    assert rel_l2(cf.detach().cpu().numpy(), g["center_features"]) < 2e-2
+    (cf * pattern_like(cf)).sum().backward()
+    # gradients through stacked TF32/BF16 blocks: compared by direction and magnitude (see
+    # profiles/r01/tf32_gradient_noise_cudnn_vs_fused.log for the cuDNN-TF32 noise floor)
+    for name, got in (("g_ctjt", net.ctjt_head.mlp_module.layer0.conv.weight.grad.cpu().numpy()),
+                      ("g_fp2_l1", sub(net.fp2.mlp.layer1.conv.weight.grad)),
+                      ("g_sa1_l0", sub(net.sa1.mlp_module.layer0.conv.weight.grad))):
+        want = g[name]
+        cos = float((got.ravel() * want.ravel()).sum() /
+                    (np.linalg.norm(got) * np.linalg.norm(want) + 1e-30))
+        assert cos > 0.95, (name, cos)
+        assert rel_l2(got, want) < 0.35, name
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_vote_heads_golden(cuda, train):
+    """VotingModule -> L2 normalisation -> ProposalModule (seed_fps) against fixtures from the
+    reference's voting_module.py:38-65 / votenet.py:93-94 / proposal_module.py:52-120: the dense
+    tcgen05 heads around the fused vote aggregation."""
+    from backtoreality_b200 import dense_mlp
+    from backtoreality_b200.votenet import ProposalModule, VotingModule
+    g = golden("vote_heads_train.npz" if train else "vote_heads_eval.npz")
+    seed = int(g["seed"])
+    torch.manual_seed(seed)
+    vgen = VotingModule(1, 256)
+    pnet = ProposalModule(4, 2, 4, g["msa"], 32, "seed_fps")
+    assert abs(weight_checksum(vgen) + weight_checksum(pnet) - float(g["wsum"])) < 1e-6 * float(g["wsum"])
+    for m in list(vgen.modules()) + list(pnet.modules()):
+        if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            m.momentum = 0.2
+            if not train:
+                m.running_mean.data = torch.randn(m.running_mean.shape) * 0.1
+                m.running_var.data = torch.rand(m.running_var.shape) + 0.5
+    vgen = vgen.to(cuda).train(train)
+    pnet = pnet.to(cuda).train(train)
+    gen = torch.Generator().manual_seed(seed + 1)
+    seed_xyz = (torch.rand(2, 256, 3, generator=gen) * 3.0).to(cuda).requires_grad_(True)
+    seed_feat = torch.randn(2, 256, 256, generator=gen).to(cuda).requires_grad_(True)
+    assert dense_mlp.enabled()
+    res = vgen.forward_normalized(seed_xyz, seed_feat)
+    assert res is not None
+    vote_xyz, vote_feat, vote_feat_pm = res
+    ep = pnet(vote_xyz, vote_feat, {"seed_xyz": seed_xyz}, features_pm=vote_feat_pm)
+    assert np.array_equal(ep["aggregated_vote_inds"].cpu().numpy(), g["inds"])
+    tol = 1e-2
+    assert rel_l2(vote_xyz.detach().cpu().numpy(), g["vote_xyz"]) < tol
+    assert rel_l2(sub(vote_feat), g["vote_feat"]) < tol
+    assert rel_l2(ep["aggregated_vote_xyz"].detach().cpu().numpy(), g["agg_xyz"]) < tol
+    assert rel_l2(sub(ep["aggregated_vote_features"]), g["agg_feat"]) < 3e-2
+    assert rel_l2(ep["objectness_scores"].detach().cpu().numpy(), g["objectness"]) < 5e-2
+    assert rel_l2(ep["center"].detach().cpu().numpy(), g["center"]) < 2e-2
+    assert rel_l2(sub(ep["size_residuals"]), g["size_residuals"]) < 5e-2
+    assert rel_l2(ep["sem_cls_scores"].detach().cpu().numpy(), g["sem_cls"]) < 5e-2
+    loss = ((ep["objectness_scores"] * 0.7).sum() + (ep["center"] * 0.3).sum() +
+            (ep["size_residuals"] * pattern_like(ep["size_residuals"])).sum() +
+            (ep["sem_cls_scores"] * pattern_like(ep["sem_cls_scores"])).sum() + (vote_xyz * 0.11).sum())
+    loss.backward()
+    got = {"g_seed_xyz": seed_xyz.grad.cpu().numpy(), "g_seed_feat": sub(seed_feat.grad),
+           "g_vgen_c1": sub(vgen.conv1.weight.grad), "g_vgen_c3": sub(vgen.conv3.weight.grad),
+           "g_vgen_c3_b": vgen.conv3.bias.grad.cpu().numpy(), "g_vgen_bn2": vgen.bn2.weight.grad.cpu().numpy(),
+           "g_pnet_c1": sub(pnet.conv1.weight.grad), "g_pnet_c3_b": pnet.conv3.bias.grad.cpu().numpy()}
+    for name, v in got.items():
+        want = g[name]
+        cos = float((v.ravel() * want.ravel()).sum() / (np.linalg.norm(v) * np.linalg.norm(want) + 1e-30))
+        assert cos > 0.97 and rel_l2(v, want) < 0.25, (name, cos, rel_l2(v, want))
+    if train:
+        assert rel_l2(vgen.bn1.running_mean.cpu().numpy(), g["rm_vgen_bn1"]) < 1e-2
+        assert rel_l2(pnet.bn2.running_var.cpu().numpy(), g["rv_pnet_bn2"]) < 3e-2
+        assert float(pnet.conv2.bias.grad.abs().max()) < 1e-3      # bias before a training-mode BN
+    else:
+        assert rel_l2(pnet.conv2.bias.grad.cpu().numpy(), g["g_pnet_c2_b"]) < 0.25
