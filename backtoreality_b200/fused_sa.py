@@ -188,34 +188,23 @@ def supported(mlp_module, xyz, features, idx, pooling="max"):
     return True
 
 
-def _fwd_bytes(B, N, NP, NS, Cin, Cout, gather, pooled):
-    """ALGORITHMIC HBM bytes of one b2r_sa_layer_fwd launch (DESIGN.md "Kernels"): inputs read
-    once, outputs written once, weights ignored.  Gather layers read every source row at most
-    once (min(unique rows, gathered rows)) + the indices; dense layers read z_prev; epilogue 0/2
-    write (M,Cout), the pooling epilogue writes max/min + their indices per (centre, channel)."""
+def _layer_work(B, N, NP, NS, Cin, Cout, gather, pooled, backward):
+    """ALGORITHMIC work of one fused layer launch as SURVEY.md 8(d) counts it, -> (bytes, flops):
+    flops 2 * B*NP*NS * Cin * Cout of the PADDED computation (backward counted 2x forward;
+    recomputation not credited, copies of a ball's first hit not discounted); bytes = this
+    layer's share of the BLOCK-level compulsory traffic (features in + xyz + idx for the gather
+    layer, the pooled output for the top layer, the weights for each; backward 2x) -- the
+    inter-layer activations are not compulsory and are not counted."""
     M = B * NP * NS
+    flops = 2.0 * M * Cin * Cout
+    byts = 4.0 * Cin * Cout
     if gather:
-        rd = 4 * M + min(B * N, M) * 4 * Cin + 12 * B * NP
-    else:
-        rd = 4 * M * Cin
-    wr = 16 * B * NP * Cout if pooled else 4 * M * Cout
-    return rd + wr
-
-
-def _bwd_bytes(B, N, NP, NS, Cin, Cout, gather, top, dgrad):
-    """ALGORITHMIC HBM bytes of one b2r_sa_layer_bwd launch: dense layers read gr and z once, the
-    pooled top layer reads only the routed (centre, channel) gradient + index (its z is recomputed
-    in the kernel); the layer input is read once; gr_prev is written once (dense) / the scatter
-    target is read-modify-written (gather layer with dgrad)."""
-    M = B * NP * NS
-    rd = 8 * B * NP * Cout if top else 8 * M * Cout
-    if gather:
-        rd += 4 * M + min(B * N, M) * 4 * Cin + 12 * B * NP
-        wr = 2 * min(B * N, M) * 4 * Cin if dgrad else 0
-    else:
-        rd += 4 * M * Cin
-        wr = 4 * M * Cin
-    return rd + wr
+        byts += B * (4.0 * (Cin - 3) * N + 12.0 * N + 4.0 * NP * NS)
+    if pooled:
+        byts += 4.0 * Cout * B * NP
+    if backward:
+        flops, byts = 2 * flops, 2 * byts
+    return (byts, flops)
 
 
 def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module, training,
@@ -281,7 +270,7 @@ def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
             z = torch.empty((rows, Cout), dtype=torch.float32, device=dev)
             d.z = _ptr(z)
         d.stats = _ptr(stats)
-        with _ext._timed("sa_layer_fwd", _fwd_bytes(B, N, NP, NS, Cin, Cout, i == 0, last)):
+        with _ext._timed("sa_layer_fwd", _layer_work(B, N, NP, NS, Cin, Cout, i == 0, last, False)):
             _lib.check(lib.b2r_sa_layer_fwd(ctypes.byref(d), st), "sa_layer_fwd")
         # BatchNorm scale / shift of THIS layer (applied by the next layer's prologue / finalize)
         if training:
@@ -424,8 +413,7 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
             if image is None:
                 image = pack_weight_bf16(weights[l], gather=(l == 0))
         b.w_image_bf16 = _ptr(image)
-        with _ext._timed("sa_layer_bwd", _bwd_bytes(B, N, NP, NS, Cin, Cout, l == 0, l == top,
-                                                    need_dgrad)):
+        with _ext._timed("sa_layer_bwd", _layer_work(B, N, NP, NS, Cin, Cout, l == 0, l == top, True)):
             _lib.check(lib.b2r_sa_layer_bwd(ctypes.byref(b), st), "sa_layer_bwd")
         if l > 0:
             mean, invstd, _, _ = bn[l - 1]

@@ -220,3 +220,46 @@ class VoteNet(nn.Module):
             fused_sa.prepack_join()
             dense_mlp.prepack_join()
         return end_points
+
+
+class _GradReverse(torch.autograd.Function):
+    """Identity in forward, -1 x gradient in backward (votenet_DA.py:30-44)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output * -1.0
+
+
+def grad_reverse(x):
+    return _GradReverse.apply(x)
+
+
+class VoteNet_DA(VoteNet):
+    """VoteNet with the global / local domain discriminators of the "Back to Reality" training
+    step (reference models/votenet_DA.py:47-176; BASELINE.json configs[2]): same backbone, voting
+    and proposal modules -- the hot path -- plus two small gradient-reversed heads on the seed
+    features and on the aggregated vote features.  The discriminators stay plain torch (they are
+    not on the set-abstraction path); attribute names / state-dict keys are the reference's."""
+
+    def __init__(self, num_class, num_heading_bin, num_size_cluster, mean_size_arr,
+                 input_feature_dim=0, num_proposal=128, vote_factor=1, sampling='vote_fps'):
+        super().__init__(num_class, num_heading_bin, num_size_cluster, mean_size_arr,
+                         input_feature_dim, num_proposal, vote_factor, sampling)
+        self.global_netD1 = nn.Sequential(nn.Conv1d(256, 256, 1), nn.BatchNorm1d(256), nn.ReLU(),
+                                          nn.Conv1d(256, 128, 1), nn.BatchNorm1d(128), nn.ReLU())
+        self.global_netD2 = nn.Linear(128, 2)
+        self.local_netD = nn.Sequential(nn.Conv1d(128, 128, 1), nn.BatchNorm1d(128), nn.ReLU(),
+                                        nn.Conv1d(128, 128, 1), nn.BatchNorm1d(128), nn.ReLU(),
+                                        nn.Conv1d(128, 1, 1))
+
+    def forward(self, inputs):
+        end_points = super().forward(inputs)
+        g = self.global_netD1(grad_reverse(end_points['seed_features']))
+        end_points['global_d_pred'] = self.global_netD2(torch.mean(g, dim=2))
+        local = self.local_netD(grad_reverse(end_points['aggregated_vote_features']))
+        end_points['local_d_pred'] = torch.sigmoid(local)
+        return end_points

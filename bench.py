@@ -54,9 +54,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b2r", choices=["b2r", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="scenes per GPU per step")
-    ap.add_argument("--npoints", type=int, default=40000)
-    ap.add_argument("--cpu-scenes", type=int, default=2, help="scenes per CPU-baseline step")
+    ap.add_argument("--workload", default="votenet", choices=["votenet", "br", "gf3d"],
+                    help="votenet: BASELINE.json configs[1] (the metric's config, default); br: configs[2], "
+                         "the VoteNet_DA 'Back to Reality' step (source forward + target forward + one "
+                         "backward, batch 8+8 per GPU); gf3d: configs[3], the GroupFree3D backbone "
+                         "(50k points, batch 4 per GPU, fp2 width 288)")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="scenes per GPU per step (default: 8; br: 8 source + 8 target; gf3d: 4)")
+    ap.add_argument("--npoints", type=int, default=0, help="points per scene (default 40000; gf3d 50000)")
+    ap.add_argument("--cpu-scenes", type=int, default=0,
+                    help="scenes per CPU step (default: the GPU arm's batch)")
+    ap.add_argument("--leg", default="", help=argparse.SUPPRESS)   # internal: subprocess legs
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every kernel from Python instead of replaying the captured step")
@@ -76,30 +84,61 @@ def parse():
     ap.add_argument("--sm-caps", default="",
                     help="pipelined step: persistent-grid caps 'fwd:bwd' of sa1,sa2,sa3,sa4,vote-agg "
                          "(comma separated, 0 = every SM); default: see PipelinedTrainStep")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.batch <= 0:
+        a.batch = 4 if a.workload == "gf3d" else 8
+    if a.npoints <= 0:
+        a.npoints = 50000 if a.workload == "gf3d" else 40000
+    if a.cpu_scenes <= 0:
+        a.cpu_scenes = a.batch
+    return a
+
+
+WORKLOADS = {
+    "votenet": "VoteNet FSB backbone+vote head fwd/bwd (BASELINE.json configs[1]): "
+               "Pointnet2Backbone(input_feature_dim=1) + VotingModule + ProposalModule("
+               "vote_aggregation, 256 proposals), train-mode BN, Adam step",
+    "br": "VoteNet BR training step (BASELINE.json configs[2]): VoteNet_DA, source forward + target "
+          "forward + one backward (train_Votenet_BR.py:277-289), 8 + 8 scenes per GPU, train-mode BN, "
+          "Adam step; the domain discriminators stay in torch",
+    "gf3d": "GroupFree3D FSB backbone fwd/bwd (BASELINE.json configs[3]): Pointnet2Backbone("
+            "input_feature_dim=0, fp2 width 288), num_point 50000, batch 4 per GPU, train-mode BN, Adam step",
+}
+LOSSES = {
+    "votenet": "synthetic scalar: mean(proposal_scores^2) + mean((vote_xyz-seed_xyz)^2)",
+    "br": "synthetic scalar: the votenet loss of the source AND the target forward + mean(global_d_pred^2) "
+          "+ mean(local_d_pred^2) of both",
+    "gf3d": "synthetic scalar: mean(fp2_features^2)",
+}
+
+
+def scenes_per_step(a):
+    """scenes one GPU processes per step"""
+    return 2 * a.batch if a.workload == "br" else a.batch
 
 
 def workload_config(a, world):
     return {
-        "workload": "VoteNet FSB backbone+vote head fwd/bwd (BASELINE.json configs[1]): "
-                    "Pointnet2Backbone(input_feature_dim=1) + VotingModule + ProposalModule("
-                    "vote_aggregation, 256 proposals), train-mode BN, Adam step",
-        "scenes_per_gpu": a.batch, "global_batch": a.batch * world, "points_per_scene": a.npoints,
+        "workload": WORKLOADS[a.workload],
+        "scenes_per_gpu": scenes_per_step(a), "global_batch": scenes_per_step(a) * world,
+        "points_per_scene": a.npoints,
         "scene_kind": "room (ScanNet-shaped surfaces, 20% duplicate points), seeds 1000+i",
-        "loss": "synthetic scalar: mean(proposal_scores^2) + mean((vote_xyz-seed_xyz)^2)",
+        "loss": LOSSES[a.workload],
         "parallelism": "dp%d (scenes sharded, flat-gradient NCCL all-reduce)" % world,
         "l2": "256 MB buffer written between steps (flush) + 4 rotating input batches",
         "e2e_input": "pinned host -> device on a copy stream, one step ahead (train_step.HostPrefetcher)",
         "launch": ("whole step (fwd+bwd+Adam) captured in one CUDA graph, replayed per batch" if world == 1
                    else "fwd+bwd replayed from one CUDA graph; NCCL all-reduce + fused Adam eager"),
-        "pipeline": ("none: FPS / ball query of a batch run inside its own step" if a.no_pipeline or a.no_graph
-                     else "geometry pre-pass (FPS, centre gather, ball query of sa1..sa4) of batch i+1 runs "
-                          "beside the step of batch i in the same graph (%d-CTA FPS clusters, started after "
-                          "SA2's forward so the wide first-level kernels keep every SM); every timed "
-                          "step = one pre-pass + one fwd/bwd/Adam; e2e copies batch i+1 from pinned host "
-                          "memory and reads the loss of batch i" % a.fps_cluster),
-        "mlp_math": "SA blocks: fused tcgen05, forward TF32 / backward BF16 operands, fp32 accumulate; "
-                    "FP/vote heads: cuDNN with TF32 allowed (torch default, as the reference runs)",
+        "pipeline": ("none: FPS / ball query of a batch run inside its own step (geometry stream)"
+                     if a.no_pipeline or a.no_graph or a.workload == "br"
+                     else "geometry pre-pass (FPS, centre gather, ball query, pad-free plans of sa1..sa4) of "
+                          "batch i+1 runs beside the step of batch i in the same graph (%d-CTA FPS clusters, "
+                          "started after SA level %d's forward; depth %d); every timed step = one pre-pass + "
+                          "one fwd/bwd/Adam; e2e copies a later batch from pinned host memory and reads the "
+                          "loss of batch i" % (a.fps_cluster, a.prepass_after + 1, a.pipeline_depth)),
+        "mlp_math": "SA blocks: fused tcgen05 in the pad-free position space (copies of a ball's first hit "
+                    "are not recomputed), forward TF32 / backward BF16 operands, fp32 accumulate; FP / "
+                    "voting / proposal MLPs: dense tcgen05 layers, TF32 forward and backward",
     }
 
 
@@ -107,23 +146,63 @@ def synthetic_loss(ep):
     return (ep["proposal_scores_raw"] ** 2).mean() + ((ep["vote_xyz"] - ep["seed_xyz"]) ** 2).mean()
 
 
-# ------------------------------------------------------------------------- CPU baseline ----
-def cpu_steps(a, steps, warmup, scenes_per_step):
-    """The oracle's CPU port of the same training step.  Returns (scenes/s, ms/step, cores)."""
+def workload_loss(workload, net, pc, geometry=None):
+    """forward + synthetic loss of one step of `workload` (shared by the GPU arm and the CPU port:
+    `net` takes {"point_clouds": ..} or, gf3d, the point cloud itself)"""
+    if workload == "votenet":
+        ep = net({"point_clouds": pc, "geometry": geometry} if geometry is not None else {"point_clouds": pc})
+        if "seed_xyz" not in ep:
+            ep["seed_xyz"] = ep["fp2_xyz"]
+        return synthetic_loss(ep)
+    if workload == "br":
+        half = pc.shape[0] // 2
+        loss = 0.0
+        for part in (pc[:half], pc[half:]):      # source forward, then target forward
+            ep = net({"point_clouds": part})
+            if "seed_xyz" not in ep:
+                ep["seed_xyz"] = ep["fp2_xyz"]
+            loss = loss + synthetic_loss(ep)
+            if "global_d_pred" in ep:
+                loss = loss + (ep["global_d_pred"] ** 2).mean() + (ep["local_d_pred"] ** 2).mean()
+        return loss
+    ep = net(pc, geometry=geometry) if geometry is not None else net(pc)
+    return (ep["fp2_features"] ** 2).mean()
+
+
+def make_batch(a, index):
+    """one step's input for one GPU: (scenes_per_step, N, 3 + C) float32 numpy"""
     from backtoreality_b200 import scenes
-    from oracle import cpu_modules, cpu_ops
+    n = scenes_per_step(a)
+    return scenes.batch(index * n, n, a.npoints, C=0 if a.workload == "gf3d" else 1, kind="room", dup=0.2)
+
+
+# ------------------------------------------------------------------------- CPU baseline ----
+def port_model(a):
+    """The oracle's CPU port (oracle/cpu_modules.py) of the workload's model; also the model the
+    `reference_gpu` leg runs over the reference's own CUDA kernels."""
+    from oracle import cpu_modules
+    if a.workload == "gf3d":
+        return cpu_modules.Backbone(input_feature_dim=0, fp2_out=288)
+    return cpu_modules.VoteNetCPU(input_feature_dim=1, num_proposal=256)
+
+
+def cpu_steps(a, steps, warmup, per_step):
+    """The oracle's CPU port of the same training step on `per_step` scenes (br: half source,
+    half target; its domain discriminators -- 0.1 % of the work -- are not part of the port).
+    Returns (scenes/s, ms/step, cores)."""
+    from backtoreality_b200 import scenes
+    from oracle import cpu_ops
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    net = cpu_modules.VoteNetCPU(input_feature_dim=1, num_proposal=256).train()
+    net = port_model(a).train()
     opt = torch.optim.Adam(net.parameters(), lr=1e-3)
-    pool = [torch.from_numpy(scenes.batch(100 + i * scenes_per_step, scenes_per_step, a.npoints,
-                                          C=1, kind="room", dup=0.2)) for i in range(2)]
+    pool = [torch.from_numpy(scenes.batch(100 + i * per_step, per_step, a.npoints,
+                                          C=0 if a.workload == "gf3d" else 1, kind="room", dup=0.2))
+            for i in range(2)]
 
     def one(i):
-        ep = net({"point_clouds": pool[i % len(pool)]})
-        ep["seed_xyz"] = ep["fp2_xyz"]
-        loss = synthetic_loss(ep)
+        loss = workload_loss(a.workload, net, pool[i % len(pool)])
         loss.backward()
         opt.step()
         opt.zero_grad()
@@ -135,10 +214,10 @@ def cpu_steps(a, steps, warmup, scenes_per_step):
     for i in range(steps):
         one(i)
     dt = time.perf_counter() - t0
-    return scenes_per_step * steps / dt, 1e3 * dt / steps, max(cores, cpu_ops.num_threads())
+    return per_step * steps / dt, 1e3 * dt / steps, max(cores, cpu_ops.num_threads())
 
 
-def reference_gpu_steps(a, dev, steps=3, warmup=1):
+def reference_gpu_steps(a, dev, steps=10, warmup=3):
     """The reference's OWN CUDA kernels (oracle/_ref/_ext.so: its _ext_src compiled for sm_100a by
     oracle/Makefile) under the unfused restatement of its Python stack (oracle/cpu_modules.py:
     group, -=, /=, cat, cuDNN SharedMLP with TF32 allowed, max_pool2d), same model / loss / Adam,
@@ -157,15 +236,14 @@ def reference_gpu_steps(a, dev, steps=3, warmup=1):
     cpu_modules._ext = ref_ext
     try:
         torch.manual_seed(0)
-        net = cpu_modules.VoteNetCPU(input_feature_dim=1, num_proposal=256).to(dev).train()
+        torch.backends.cudnn.benchmark = True
+        net = port_model(a).to(dev).train()
         opt = torch.optim.Adam(net.parameters(), lr=1e-3)
-        pool = [torch.from_numpy(scenes.batch(100 + i * a.batch, a.batch, a.npoints, C=1,
-                                              kind="room", dup=0.2)).to(dev) for i in range(2)]
+        n = scenes_per_step(a)
+        pool = [torch.from_numpy(make_batch(a, 100 + i)).to(dev) for i in range(2)]
 
         def one(i):
-            ep = net({"point_clouds": pool[i % 2]})
-            ep["seed_xyz"] = ep["fp2_xyz"]
-            loss = synthetic_loss(ep)
+            loss = workload_loss(a.workload, net, pool[i % 2])
             loss.backward()
             opt.step()
             opt.zero_grad()
@@ -180,23 +258,47 @@ def reference_gpu_steps(a, dev, steps=3, warmup=1):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        return {"value": a.batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+        return {"value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+                "warmup": warmup,
                 "what": "reference CUDA kernels (oracle/_ref/_ext.so, sm_100a build of its "
-                        "_ext_src) + unfused Python stack + cuDNN (TF32 allowed), eager, same "
-                        "model/loss/Adam, %d scenes x %d points" % (a.batch, a.npoints)}
+                        "_ext_src) + unfused Python stack + cuDNN (TF32 allowed, benchmark mode), "
+                        "eager, same model/loss/Adam, %d scenes x %d points" % (n, a.npoints)}
     finally:
         cpu_modules._ext = saved
+
+
+def run_leg(a):
+    """Internal (--leg): one of the product arm's reference legs, in its own process."""
+    if a.leg == "reference_gpu":
+        res = reference_gpu_steps(a, torch.device("cuda", 0)) if torch.cuda.is_available() else None
+        emit(res or {})
+    else:
+        per = scenes_per_step(a) if a.cpu_scenes >= a.batch else (
+            2 * a.cpu_scenes if a.workload == "br" else a.cpu_scenes)
+        val, ms, cores = cpu_steps(a, 3, 1, per)
+        emit({"value": val, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
+              "sample": "%d scenes of %d points per step, 3 timed steps after 1 warm-up (same model, loss, "
+                        "optimizer; oracle/cpu_modules.py + b2r_oracle.c)" % (per, a.npoints)})
 
 
 def run_reference(a):
     """`--impl reference`: the CPU arm.  Rank 0 only; other ranks exit without work."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    per = a.cpu_scenes if (a.steps + a.warmup) <= 30 else 1
+    # one step = the GPU arm's per-GPU batch (same BatchNorm batch), fewer scenes only when the
+    # requested step count would take more than a few minutes
+    per = scenes_per_step(a) if a.cpu_scenes >= a.batch else (2 * a.cpu_scenes if a.workload == "br" else a.cpu_scenes)
+    if (a.steps + a.warmup) > 30:
+        per = 2 if a.workload == "br" else 1
     val, ms, cores = cpu_steps(a, a.steps, a.warmup, per)
-    cfg = workload_config(a, 1)
-    cfg["parallelism"] = "host CPU, %d threads" % cores
-    cfg["l2"] = "n/a (CPU)"
+    cfg = {"workload": WORKLOADS[a.workload], "scenes_per_gpu": scenes_per_step(a),
+           "global_batch": scenes_per_step(a), "points_per_scene": a.npoints,
+           "scene_kind": "room (ScanNet-shaped surfaces, 20% duplicate points), seeds 1000+i",
+           "loss": LOSSES[a.workload],
+           "parallelism": "host CPU, %d threads (the reference has no CPU path for these ops: this is "
+                          "the oracle's port of the same step, oracle/cpu_modules.py + b2r_oracle.c)" % cores,
+           "l2": "n/a (CPU)", "launch": "eager torch CPU + OpenMP C oracle ops", "pipeline": "none",
+           "mlp_math": "fp32"}
     sample = "%d scenes of %d points per step, %d steps" % (per, a.npoints, a.steps)
     emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
@@ -311,7 +413,8 @@ def trace_steps(path, fn, steps=3):
 def run_b2r(a):
     import torch.distributed as dist
     from backtoreality_b200 import _ext, _lib, dist_utils, scenes
-    from backtoreality_b200.votenet import VoteNet
+    from backtoreality_b200.backbone_module import Pointnet2Backbone
+    from backtoreality_b200.votenet import VoteNet, VoteNet_DA
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -327,13 +430,17 @@ def run_b2r(a):
         dist.init_process_group("nccl", device_id=dev)
     assert world == a.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % a.gpus
 
-    # the FP / voting / proposal heads are cuDNN 1x1 convolutions: let cuDNN pick its fastest
-    # algorithms during the warm-up steps (the reference's trainers leave the default heuristics;
-    # this only changes which library kernel runs, e.g. it avoids a 56 us grouped-direct wgrad)
+    # (only the br workload's domain discriminators still run cuDNN convolutions)
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(0)  # identical replicas
-    net = VoteNet(22, 1, 22, np.ones((22, 3), np.float32), input_feature_dim=1, num_proposal=256,
+    if a.workload == "gf3d":
+        net = Pointnet2Backbone(input_feature_dim=0, fp2_out=288).to(dev).train()
+        backbone = net
+    else:
+        cls = VoteNet_DA if a.workload == "br" else VoteNet
+        net = cls(22, 1, 22, np.ones((22, 3), np.float32), input_feature_dim=1, num_proposal=256,
                   vote_factor=1, sampling="vote_fps").to(dev).train()
+        backbone = net.backbone_net
     params = [p for p in net.parameters()]
     # N > 1: gradients are packed into one flat buffer for a single all-reduce per step
     bucket = dist_utils.FlatGradBucket(params, as_views=False) if world > 1 else None
@@ -341,17 +448,14 @@ def run_b2r(a):
     live = {"grads": None}   # the gradient tensors the last backward (or the graph) produced
 
     pool_n = 4
-    host = [torch.from_numpy(scenes.batch((rank * pool_n + i) * a.batch, a.batch, a.npoints, C=1,
-                                          kind="room", dup=0.2)).pin_memory()
-            for i in range(pool_n)]
+    host = [torch.from_numpy(make_batch(a, rank * pool_n + i)).pin_memory() for i in range(pool_n)]
     resident = [h.to(dev) for h in host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def fwd_bwd(pc, geometry=None):
         for p in params:          # autograd then ASSIGNS fresh gradients: no accumulate kernels,
             p.grad = None         # nothing to zero
-        ep = net({"point_clouds": pc, "geometry": geometry})
-        loss = synthetic_loss(ep)
+        loss = workload_loss(a.workload, net, pc, geometry)
         loss.backward()
         live["grads"] = [p.grad for p in params]
         return loss
@@ -417,7 +521,8 @@ def run_b2r(a):
     # 3-kernel fused Adam stay eager so no collective is ever captured)
     graphed = None
     capture_all = world == 1
-    pipelined = not (a.no_graph or a.no_pipeline)
+    # br runs two forwards per step: its geometry stays inside the step (geometry stream)
+    pipelined = not (a.no_graph or a.no_pipeline) and a.workload != "br"
     if not a.no_graph:
         try:
             from backtoreality_b200.train_step import (CapturedTrainStep, PipelinedTrainStep,
@@ -431,15 +536,16 @@ def run_b2r(a):
                 if a.sm_caps:
                     caps = [tuple(int(v) for v in c.split(":")) for c in a.sm_caps.split(",")]
                     caps, head_cap = caps[:4], caps[4]
-                net.pnet.vote_aggregation.sm_limit = head_cap
+                if a.workload == "votenet":
+                    net.pnet.vote_aggregation.sm_limit = head_cap
                 if a.pipeline_depth == 2:
-                    graphed = PipelinedTrainStep2(net.backbone_net, step if capture_all else fwd_bwd,
+                    graphed = PipelinedTrainStep2(backbone, step if capture_all else fwd_bwd,
                                                   resident[0], resident[1], fps_cluster=a.fps_cluster,
                                                   sm_caps=caps,
                                                   after_warmup_step=None if capture_all else finish,
                                                   start_after_level=start)
                 else:
-                    graphed = PipelinedTrainStep(net.backbone_net, step if capture_all else fwd_bwd,
+                    graphed = PipelinedTrainStep(backbone, step if capture_all else fwd_bwd,
                                                  resident[0], fps_cluster=a.fps_cluster, sm_caps=caps,
                                                  after_warmup_step=None if capture_all else finish,
                                                  start_after_level=start)
@@ -451,7 +557,8 @@ def run_b2r(a):
             log("CUDA-graph capture failed (%s: %s); timing the eager step" % (type(e).__name__, e))
             graphed = None
             pipelined = False
-            net.pnet.vote_aggregation.sm_limit = 0
+            if a.workload != "gf3d":
+                net.pnet.vote_aggregation.sm_limit = 0
 
     def run_step(pc):
         if graphed is None:
@@ -520,7 +627,7 @@ def run_b2r(a):
             dist.destroy_process_group()
         return
 
-    scenes_total = a.batch * world * a.steps
+    scenes_total = scenes_per_step(a) * world * a.steps
     out = {
         "metric": METRIC, "value": scenes_total / (ms_dev * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
@@ -537,43 +644,55 @@ def run_b2r(a):
         out["config"]["launch"] = "eager: every kernel launched from Python"
     k_div = k_steps
 
-    # roofline of the dominant HBM-bound libb2r kernel, from events recorded in the timed loop
+    # roofline of the dominant libb2r kernel class (the fused SA layers), SURVEY.md 8(d): the
+    # fused SA MLP is the path's only dense contraction, so it is measured against the TENSOR peak
+    # with the algorithmic flops 2*np*ns*sum(C_l*C_l+1) per scene (backward 2x, recomputation not
+    # credited, pad copies not discounted), live CUDA events around every launch; the same
+    # launches' block-level compulsory bytes against the HBM peak are reported beside it
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    # the dominant libb2r kernel class of the step: fused SA layer forward or backward
+    bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained / hbm_gbs)" if "hbm_gbs" in peaks
+                else "fallback 1400 TFLOP/s, 6650 GB/s")
     cand = {}
     for name, kern in (("sa_layer_fwd", "sa_layer_fwd_kernel"), ("sa_layer_bwd", "sa_layer_bwd_kernel")):
         ev = timed.get(name, [])
         if ev:
-            cand[name] = (sum(s_.elapsed_time(e_) for s_, e_, _ in ev), sum(b for _, _, b in ev),
-                          len(ev), kern)
+            cand[name] = (sum(s_.elapsed_time(e_) for s_, e_, _ in ev), sum(w[0] for _, _, w in ev),
+                          sum(w[1] for _, _, w in ev), len(ev), kern)
     if cand:
         name = max(cand, key=lambda k: cand[k][0])
-        tot_ms, tot_b, n, kern = cand[name]
-        ach = tot_b / (tot_ms * 1e-3) / 1e9
+        tot_ms, tot_b, tot_f, n, kern = cand[name]
+        tf = tot_f / (tot_ms * 1e-3) / 1e12
+        gbs = tot_b / (tot_ms * 1e-3) / 1e9
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
             traffic = (tj.get(name) or tj[kern])["dram_bytes_per_launch"]
         except Exception:
             pass
-        out["roofline"] = {"kernel": "%s: all %d launches/step of b2r_%s (fused tcgen05 SA layers; SA1's thin "
-                                     "first layer runs mlp_thin.cu's streaming kernel; tensor work is <10%% "
-                                     "of the time, the class is HBM-bound)" % (kern, n // k_div, name),
-                           "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                           "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                           "algorithmic_bytes_per_launch": tot_b / n,
-                           "avg_launch_us": 1e3 * tot_ms / n, "launches_timed": n,
-                           "ms_per_step": tot_ms / k_div,
-                           "other": {k: {"ms_per_step": v[0] / k_div,
-                                         "achieved_gbs": v[1] / (v[0] * 1e-3) / 1e9,
-                                         "launches_per_step": v[2] // k_div}
-                                     for k, v in cand.items() if k != name}}
+        # forward operands are TF32 (half the bf16 rate), backward operands BF16
+        peak = bf16_peak if name == "sa_layer_bwd" else bf16_peak / 2
+        out["roofline"] = {
+            "kernel": "%s: all %d launches/step of b2r_%s (fused tcgen05 SA layers of sa1..sa4 and the vote "
+                      "aggregation; SA1's thin first layer runs mlp_thin.cu's streaming kernel)"
+                      % (kern, n // k_div, name),
+            "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+            "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_flops_per_launch": tot_f / n, "algorithmic_bytes_per_launch": tot_b / n,
+            "avg_launch_us": 1e3 * tot_ms / n, "launches_timed": n, "ms_per_step": tot_ms / k_div,
+            "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                    "what": "SURVEY 8(d) block-level compulsory bytes (features + xyz + idx + weights + "
+                            "pooled output; backward 2x) of the same launches / their time"},
+            "other": {k: {"ms_per_step": v[0] / k_div, "achieved_tflops": v[2] / (v[0] * 1e-3) / 1e12,
+                          "frac_of_tensor_peak": v[2] / (v[0] * 1e-3) / 1e12 /
+                          (bf16_peak if k == "sa_layer_bwd" else bf16_peak / 2),
+                          "achieved_gbs": v[1] / (v[0] * 1e-3) / 1e9, "launches_per_step": v[3] // k_div}
+                      for k, v in cand.items() if k != name}}
     fp = timed.get("furthest_point_sampling", [])
     if fp:
         per_step = len(fp) // k_div
@@ -581,7 +700,9 @@ def run_b2r(a):
         # SA1 is the first FPS launch of every step: N points -> 2048 samples
         sa1 = [fp[i] for i in range(0, len(fp), per_step)]
         sa1_ms = float(np.mean([s.elapsed_time(e) for s, e, _ in sa1]))
-        upd = a.batch * (2048 - 1) * a.npoints  # point-updates per launch, 8 flop each
+        upd = scenes_per_step(a) * (2048 - 1) * a.npoints  # point-updates per step, 8 flop each
+        if a.workload == "br":
+            upd //= 2                                           # per launch: one of the two forwards
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6
         out["fps"] = {"kernel": "fps_cluster_kernel", "bound": "serial fp32 chain (not hbm/tensor)",
@@ -591,22 +712,25 @@ def run_b2r(a):
                       "sa1_frac_of_fp32_issue_peak": 8 * upd / (sa1_ms * 1e-3) / fp32_peak}
 
     if world == 1 and not a.no_cpu_baseline:
-        try:
-            log("timing the reference's own CUDA kernels + cuDNN on this GPU ...")
-            del graphed
-            torch.cuda.empty_cache()
-            ref_gpu = reference_gpu_steps(a, dev)
-            if ref_gpu is not None:
-                out["reference_gpu"] = ref_gpu
-        except Exception as e:
-            log("reference GPU arm failed: %s: %s" % (type(e).__name__, e))
-        log("timing the CPU port (oracle) on the host cores ...")
-        val, ms, cores = cpu_steps(a, 3, 1, a.cpu_scenes)
-        out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                               "ms_per_step": ms,
-                               "sample": "%d scenes of %d points per step, 3 timed steps after 1 "
-                                         "warm-up (same model, loss, optimizer)" % (a.cpu_scenes,
-                                                                                     a.npoints)}
+        # both reference legs run in their own processes (they load oracle/_ref/_ext.so and
+        # oracle/liborc.so: checkers, kept out of the product arm's process)
+        del graphed
+        torch.cuda.empty_cache()
+        for leg, key in (("reference_gpu", "reference_gpu"), ("cpu_baseline", "cpu_baseline")):
+            log("timing leg %s in a subprocess ..." % leg)
+            try:
+                cmd = [sys.executable, os.path.abspath(__file__), "--leg", leg, "--workload", a.workload,
+                       "--batch", str(a.batch), "--npoints", str(a.npoints), "--cpu-scenes", str(a.cpu_scenes)]
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+                line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                if line:
+                    res = json.loads(line[-1])
+                    if res:
+                        out[key] = res
+                else:
+                    log("leg %s printed no result: %s" % (leg, r.stderr[-400:]))
+            except Exception as e:
+                log("leg %s failed: %s: %s" % (leg, type(e).__name__, e))
     emit(out)
     if world > 1:
         dist.destroy_process_group()
@@ -620,7 +744,9 @@ def main():
     sys.stdout.flush()
     _RESULT_OUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
-    if a.impl == "reference":
+    if a.leg:
+        run_leg(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_b2r(a)
