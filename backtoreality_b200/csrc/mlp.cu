@@ -76,15 +76,20 @@ struct LayerArgs {
   const int *cidx, *ccen, *cmeta;   // compacted position space (csrc/compact.cu) or NULL
 };
 
-// Warp roles (12 warps = 3 per SM sub-partition -> 168 registers/thread):
-//   0-3  epilogue   one TMEM lane quadrant each: TMEM -> registers -> statistics, store / pool
-//   4    MMA issue  one elected thread
-//   5-11 producers  global loads (batched) -> BN+ReLU / gather -> TF32 -> swizzled smem tile
+// Warp roles (16 warps = 4 per SM sub-partition -> 128 registers/thread):
+//   0-7  epilogue   two warps per TMEM lane quadrant (warp & 3), each takes one half of the tile's
+//                   columns: TMEM -> registers (8 columns at a time, software-pipelined) ->
+//                   statistics, store / pool.  A rolled loop over 8-column sample groups: the
+//                   fully unrolled 128-column epilogue of round 1 was 1,500 straight-line
+//                   instructions per tile and spent 35 % of its issue slots waiting for
+//                   instruction fetch (ncu, profiles/r02/ncu_sa1_fwd_pooled_epilogue.txt)
+//   8    MMA issue  one elected thread
+//   9-15 producers  global loads (batched) -> BN+ReLU / gather -> TF32 -> swizzled smem tile
 // Two smem stages for the X tile and two TMEM stages for the accumulator, mbarrier hand-offs
 // (full / empty / mma_done / d_free): producers run up to two tiles ahead of the tensor core and
 // the epilogue's stores trail behind, so HBM reads, MMAs and HBM writes of different tiles overlap.
-constexpr int kFwdEpiThreads = 128, kFwdProdThreads = 224;
-constexpr int kFwdThreads = kFwdEpiThreads + 32 + kFwdProdThreads;   // 384
+constexpr int kFwdEpiThreads = 256, kFwdProdThreads = 224, kFwdMmaWarp = 8;
+constexpr int kFwdThreads = kFwdEpiThreads + 32 + kFwdProdThreads;   // 512
 
 struct FwdSmem {
   uint32_t w_off, w_bytes, x_off[2], x_bytes, raw_off[2], raw_bytes, scale_off, idx_off, cen_off,
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
     for (int i = 0; i < 11; ++i) mbar_init(bar(i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) tmem_alloc(smem_u32(s_tmem), kTmemCols);
+  if (warp == kFwdMmaWarp) tmem_alloc(smem_u32(s_tmem), kTmemCols);
   for (uint32_t i = tid * 16; i < 2u * L.x_bytes; i += kFwdThreads * 16)   // padding stays zero
     *reinterpret_cast<uint4 *>(base + L.x_off[0] + i) = make_uint4(0, 0, 0, 0);
   if (a.mode == 1)
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
     bulk_g2s(smem_u32(s_w), a.w_image, L.w_bytes, bar(8));
   }
 
-  if (warp > 4) {
+  if (warp > kFwdMmaWarp) {
     // =============================== PRODUCERS ==================================================
     const int ptid = tid - (kFwdEpiThreads + 32);
     const long long per_scene = (long long)a.NP * a.NS;
@@ -234,11 +239,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
         // raw[s] two tiles ago; producers only transform smem -> smem (BN + ReLU + TF32 + swizzle)
         const int CH = a.Cin >> 2;
         const int total = NT * CH;
+        const int chs = (CH & (CH - 1)) == 0 ? 31 - __clz(CH) : -1;   // log2(CH) or -1
         mbar_wait(bar(9 + s), (uint32_t)(n & 1));
         const float4 *src = reinterpret_cast<const float4 *>(base + L.raw_off[s]);
         for (int i = ptid; i < total; i += kFwdProdThreads) {
           const float4 t = src[i];
-          const int row = i / CH, ch = i - row * CH;
+          const int row = chs >= 0 ? (i >> chs) : (i / CH), ch = i - row * CH;
           const float4 sc = *reinterpret_cast<const float4 *>(s_scale + ch * 4);
           const float4 sh = *reinterpret_cast<const float4 *>(s_shift + ch * 4);
           uint4 out;
@@ -253,6 +259,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
         // 8 independent 16-byte loads per thread in flight, tile k+2 prefetched into L2
         const int CH = a.Cin >> 2;
         const int total = NT * CH;
+        const int chs = (CH & (CH - 1)) == 0 ? 31 - __clz(CH) : -1;
         if (ptid == 0 && tile + 2 * grid < num_tiles)
           prefetch_l2(a.z_prev + (size_t)(pos0 + 2ll * grid * NT) * a.Cin, (uint32_t)total * 16u);
         const float4 *src = reinterpret_cast<const float4 *>(a.z_prev + (size_t)pos0 * a.Cin);
@@ -267,7 +274,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
           for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * kFwdProdThreads;
             if (i < total) {
-              const int row = i / CH, ch = i - row * CH;
+              const int row = chs >= 0 ? (i >> chs) : (i / CH), ch = i - row * CH;
               const float4 sc = *reinterpret_cast<const float4 *>(s_scale + ch * 4);
               const float4 sh = *reinterpret_cast<const float4 *>(s_shift + ch * 4);
               uint4 out;
@@ -291,7 +298,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kFwdMmaWarp) {
     // =============================== MMA ISSUE (one thread) =====================================
     if (lane == 0) {
       mbar_wait(bar(8), 0);
@@ -319,11 +326,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
     }
     __syncwarp();
   } else {
-    // =============================== EPILOGUE ===================================================
-    const int q = warp;
+    // =============================== EPILOGUE (8 warps) =========================================
+    const int q = warp & 3, h = warp >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     double acc_s[2] = {0.0, 0.0}, acc_ss[2] = {0.0, 0.0};
-    const int ns_mask = a.NS - 1;
+    // the quadrant's two warps take one half of the tile's columns each -- whole centres when
+    // NT/2 >= nsample (a centre's running max must stay in one thread); otherwise warp h = 0 pools
+    // the whole tile alone.  Storing layers (epilogue 0) always split.
+    constexpr int kGroups = NT / 8;   // 8-column sample groups per tile
+    const bool split = a.epilogue == 0 || NT / 2 >= a.NS;
+    const int sg_begin = split ? h * (kGroups / 2) : 0;
+    const int sg_end = split ? sg_begin + kGroups / 2 : (h == 0 ? kGroups : 0);
     int ncen_e = -1;   // CMP pooling: centre of this thread's column in the NEXT tile
     if constexpr (CMP) {
       if (a.epilogue == 1) {
@@ -335,12 +348,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
     for (int k = 0, tile = blockIdx.x; tile < num_tiles; tile += grid, ++k) {
       const int s = k & 1, n = k >> 1;
       const long long pos0 = (long long)tile * NT;
-      TileClass tc{};
+      // per-tile class: samples per centre, live rows, extra weight of a centre's first sample
+      // (padded position space: the block's nsample, every row live, no extra weight)
+      TileClass tc;
+      tc.ns = a.NS; tc.live = NT; tc.wx = 0.f;
       if constexpr (CMP) {
         tc = tile_class(s_meta, pos0, a.NS);
         if (a.epilogue == 1 && tid < NT && tile + grid < num_tiles)
           ncen_e = __ldg(a.ccen + pos0 + (long long)grid * NT + tid);
       }
+      const int nsm = tc.ns - 1;
+      const int p64 = (int)(pos0 & 63);
       mbar_wait(bar(4 + s), (uint32_t)(n & 1));
       tc_fence_after();
 #pragma unroll
@@ -349,100 +367,82 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
         const int c = m * 128 + q * 32 + lane;   // output channel owned by this thread
         const bool c_ok = c < a.Cout;
         float ts = 0.f, tss = 0.f;
-        float mx = 0.f, mn = 0.f;   // running max / min (+ sample index) of the current centre
-        int ax = 0, an = 0;
+        // running max / min (+ sample index) of the current centre, as TWO independent chains
+        // (even / odd columns) merged at the centre's end: the epilogue is bound by the latency
+        // of these dependent compare-select chains, not by issue slots
+        float mx = 0.f, mn = 0.f, mx1 = 0.f, mn1 = 0.f;
+        int ax = 0, an = 0, ax1 = 0, an1 = 0;
+        const uint32_t t0 = tmem_base + lane_addr + (uint32_t)((s * MT + m) * NT);
+        // one 8-column sample group: wholly live or wholly dead, inside one centre; the centre's
+        // first sample stands for its NS - ns pad copies as well (weight 1 + wx)
+        auto process = [&](const uint32_t (&r)[8], int sg) {
+          if (!c_ok) return;
+          const int col0 = sg * 8;
+          if (a.epilogue == 0) {   // dead rows are stored too: later layers must read finite z
+            float *zp = a.z + (size_t)(pos0 + col0) * a.Cout + c;
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          uint32_t r[32];
-          cuda::ptx::tcgen05_ld_32x32b(
-              r, tmem_base + lane_addr + (uint32_t)((s * MT + m) * NT + ch * 32));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (!c_ok) continue;
-          if constexpr (CMP) {
-            // 8-column sample groups: wholly live or wholly dead, inside one centre; the centre's
-            // first sample stands for its NS - ns pad copies as well (weight 1 + wx)
-            const int nsm = tc.ns - 1;
-            const int p64 = (int)(pos0 & 63);
-#pragma unroll
-            for (int sg = 0; sg < 4; ++sg) {
-              const int col0 = ch * 32 + sg * 8;
-              if (col0 < tc.live) {
-                const int s0 = (p64 + col0) & nsm;
-                float t = 0.f, tt = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float x = __uint_as_float(r[sg * 8 + i]);
-                  t += x;
-                  tt = fmaf(x, x, tt);
-                }
-                if (s0 == 0) {
-                  const float x0 = __uint_as_float(r[sg * 8]);
-                  t = fmaf(tc.wx, x0, t);
-                  tt = fmaf(tc.wx * x0, x0, tt);
-                }
-                ts += t;
-                tss += tt;
-                if (a.epilogue == 1) {
-                  if (s0 == 0) {
-                    mx = -INFINITY; mn = INFINITY; ax = 0; an = 0;
-                  }
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    const float x = __uint_as_float(r[sg * 8 + i]);
-                    if (x > mx) { mx = x; ax = s0 + i; }
-                    if (x < mn) { mn = x; an = s0 + i; }
-                  }
-                  if (s0 + 8 == tc.ns) {
-                    const int centre = s_cene[(k & 1) * NT + col0];
-                    if (centre >= 0) {
-                      const size_t o = (size_t)centre * a.Cout + c;
-                      a.zmax[o] = mx; a.zmin[o] = mn; a.amax[o] = ax; a.amin[o] = an;
-                    }
-                  }
-                }
-              }
-            }
-            if (a.epilogue == 0) {   // dead rows are stored too: later layers must read finite z
-              float *zp = a.z + (size_t)(pos0 + ch * 32) * a.Cout + c;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) zp[(size_t)i * a.Cout] = __uint_as_float(r[i]);
-            }
-            continue;
+            for (int i = 0; i < 8; ++i) zp[(size_t)i * a.Cout] = __uint_as_float(r[i]);
           }
+          if (col0 >= tc.live) return;
+          const int s0 = (p64 + col0) & nsm;
+          float t = 0.f, tt = 0.f, tb = 0.f, ttb = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = __uint_as_float(r[i]);
-            ts += x;
-            tss = fmaf(x, x, tss);
+          for (int i = 0; i < 8; i += 2) {
+            const float x = __uint_as_float(r[i]), y = __uint_as_float(r[i + 1]);
+            t += x;
+            tt = fmaf(x, x, tt);
+            tb += y;
+            ttb = fmaf(y, y, ttb);
           }
-          if (a.epilogue == 0) {
-            float *zp = a.z + (size_t)(pos0 + ch * 32) * a.Cout + c;
+          t += tb;
+          tt += ttb;
+          if (CMP && s0 == 0) {
+            const float x0 = __uint_as_float(r[0]);
+            t = fmaf(tc.wx, x0, t);
+            tt = fmaf(tc.wx * x0, x0, tt);
+          }
+          ts += t;
+          tss += tt;
+          if (a.epilogue == 1) {
+            // max AND min over the centre's samples with strict compares: the first extremum
+            // wins, like max_pool2d
+            if (s0 == 0) {
+              mx = mx1 = -INFINITY; mn = mn1 = INFINITY; ax = an = ax1 = an1 = 0;
+            }
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              zp[(size_t)i * a.Cout] = __uint_as_float(r[i]);   // a warp writes 32 channels = 128 B
-          } else {
-            // max AND min over each centre's NS samples (16-column sub-groups; NS = 16/32/64 and
-            // tiles start on a centre boundary).  Strict compares: the first extremum wins, like
-            // max_pool2d.
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              const int col0 = ch * 32 + hf * 16;
-              const int s0 = col0 & ns_mask;
-              if (s0 == 0) {
-                mx = -INFINITY; mn = INFINITY; ax = 0; an = 0;
-              }
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float x = __uint_as_float(r[hf * 16 + i]);
-                if (x > mx) { mx = x; ax = s0 + i; }
-                if (x < mn) { mn = x; an = s0 + i; }
-              }
-              if (s0 + 16 == a.NS) {
-                const long long centre = (pos0 >> a.ns_shift) + (col0 >> a.ns_shift);
+            for (int i = 0; i < 8; i += 2) {
+              const float x = __uint_as_float(r[i]), y = __uint_as_float(r[i + 1]);
+              if (x > mx) { mx = x; ax = s0 + i; }
+              if (x < mn) { mn = x; an = s0 + i; }
+              if (y > mx1) { mx1 = y; ax1 = s0 + i + 1; }
+              if (y < mn1) { mn1 = y; an1 = s0 + i + 1; }
+            }
+            if (s0 + 8 == tc.ns) {
+              // merge the two chains: larger value wins, equal values -> the earlier sample
+              if (mx1 > mx || (mx1 == mx && ax1 < ax)) { mx = mx1; ax = ax1; }
+              if (mn1 < mn || (mn1 == mn && an1 < an)) { mn = mn1; an = an1; }
+              long long centre;
+              if constexpr (CMP) centre = s_cene[(k & 1) * NT + col0];
+              else centre = (pos0 + col0) >> a.ns_shift;
+              if (centre >= 0) {
                 const size_t o = (size_t)centre * a.Cout + c;
                 a.zmax[o] = mx; a.zmin[o] = mn; a.amax[o] = ax; a.amin[o] = an;
               }
             }
+          }
+        };
+        // software-pipelined TMEM loads: group sg+1 is in flight while group sg is processed
+        uint32_t ra[8], rb[8];
+        if (sg_begin < sg_end) cuda::ptx::tcgen05_ld_32x32b(ra, t0 + (uint32_t)(sg_begin * 8));
+#pragma unroll 1
+        for (int sg = sg_begin; sg < sg_end; sg += 2) {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (sg + 1 < sg_end) cuda::ptx::tcgen05_ld_32x32b(rb, t0 + (uint32_t)((sg + 1) * 8));
+          process(ra, sg);
+          if (sg + 1 < sg_end) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (sg + 2 < sg_end) cuda::ptx::tcgen05_ld_32x32b(ra, t0 + (uint32_t)((sg + 2) * 8));
+            process(rb, sg + 1);
           }
         }
         acc_s[m] += (double)ts;
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == kFwdMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // BatchNorm bookkeeping from the accumulated statistics (one thread per channel):

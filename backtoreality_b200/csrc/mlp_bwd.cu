@@ -275,6 +275,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
     // =============================== PRODUCERS (7 warps) ========================================
     const int ptid = tid - (kEpiThreads + 32);
     const int CH8 = a.Cout >> 3;     // 16-byte BF16 chunks per DZ row
+    const int ch8s = (CH8 & (CH8 - 1)) == 0 ? 31 - __clz(CH8) : -1;   // log2 or -1: no division
+    const int CHx = a.Cin >> 3;      // dense layers: 16-byte BF16 chunks per X row
+    const int chxs = (CHx > 0 && (CHx & (CHx - 1)) == 0) ? 31 - __clz(CHx) : -1;
     int nidx = 0, ncen = 0;   // prefetched ball-query index (centre) of the next tile
     for (int k = 0, tile = blockIdx.x; tile < num_tiles; tile += grid, ++k) {
       const int s = k & 1, n = k >> 1;
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
           for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * kProdThreads;
             if (i < total) {
-              const int row = i / CH8, ch = i - row * CH8;
+              const int row = ch8s >= 0 ? (i >> ch8s) : (i / CH8), ch = i - row * CH8;
               float v[8] = {g[u][0].x, g[u][0].y, g[u][0].z, g[u][0].w,
                             g[u][1].x, g[u][1].y, g[u][1].z, g[u][1].w};
               if (has_coef) {
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
           for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * kProdThreads;
             if (i < total) {
-              const int row = i / CH, ch = i - row * CH;
+              const int row = chxs >= 0 ? (i >> chxs) : (i / CH), ch = i - row * CH;
               const float *sc = s_scale + ch * 8, *sh = s_shift + ch * 8;
               const float x0 = fmaxf(fmaf(t[u][0].x, sc[0], sh[0]), 0.f);
               const float x1 = fmaxf(fmaf(t[u][0].y, sc[1], sh[1]), 0.f);
