@@ -13,8 +13,21 @@ QueryAndGroup -> SharedMLP(3 x [Conv2d 1x1 -> BatchNorm2d -> ReLU]) -> max_pool2
 Training-mode BatchNorm uses biased batch statistics over all B*npoint*nsample positions of the
 local batch, updates running_mean / running_var (unbiased) with the module's momentum and bumps
 num_batches_tracked, exactly like nn.BatchNorm2d (reference pytorch_utils.py:55-58).
-Math: TF32 operands (round-to-nearest), FP32 accumulate -- the precision the reference itself
-runs at by default (cuDNN TF32 convolutions on sm_80+).
+Math, FORWARD: TF32 operands (round-to-nearest), FP32 accumulate -- the precision the reference
+itself runs at by default (cuDNN TF32 convolutions on sm_80+).
+Math, BACKWARD (csrc/mlp_bwd.cu): BF16 operands (X, dz and W rounded to 8 mantissa bits -- NARROWER
+than the reference's cuDNN TF32 wgrad / dgrad), FP32 accumulate; the pooled top layer's z is
+recomputed in BF16 for the BatchNorm-backward term while the max-pool routing comes from the TF32
+forward.  Per layer that is <= 1e-2 rel-L2 against fp64 (measured ~3e-3; tests/test_mlp_gpu.py),
+below the 3-4e-2 per-block gradient noise any TF32 forward already causes by flipping ReLU masks /
+pool winners (DESIGN.md "Tolerances").  Why BF16: tcgen05 reads the transposed (MN-major) operand
+views the weight gradient needs from the same bytes only for 16-bit data.
+To take the backward out of the comparison, set `fused_sa.ENABLED = False` (or B2R_FUSED=0): the
+block then runs QueryAndGroup + torch SharedMLP + max_pool2d, forward and backward, at whatever
+precision torch.backends.cudnn.allow_tf32 selects -- the tests' fp32 arm.
+
+Pad-free position space (COMPACT, csrc/compact.cu): blocks with nsample >= 32 do not recompute the
+copies of a ball's first hit that the ball query pads with; see `compact_plan`.
 """
 import ctypes
 import os
@@ -515,6 +528,7 @@ def sa_block(xyz, new_xyz, features, idx, radius, normalize_xyz, mlp_module, tra
 
 NUM_SMS = 148   # B200
 
-# Set to False to route PointnetSAModuleVotes through the unfused path (QueryAndGroup kernel +
-# cuDNN SharedMLP + max_pool2d) -- used by the parity tests as the fp32 comparison arm.
-ENABLED = True
+# Set to False (or B2R_FUSED=0) to route PointnetSAModuleVotes through the unfused path
+# (QueryAndGroup kernel + cuDNN SharedMLP + max_pool2d) -- used by the parity tests as the fp32
+# comparison arm; it also switches the dense FP / voting / proposal layers off (dense_mlp.enabled).
+ENABLED = os.environ.get("B2R_FUSED", "1") not in ("0", "")

@@ -6,7 +6,8 @@ dist2 (B,M) f32, idx2 (B,M) i64).  The reference tiles both clouds to (B,N,M,C);
 `b2r_nn_argmin` finds the two index vectors without any N*M tensor, and the distances are
 evaluated on the matched pairs with the reference's own elementwise formula, so values and
 gradients (which torch.min's backward sends to the arg-min pair only) are the same.
-CPU tensors take the reference formulation unchanged (the losses are also used in CPU tests).
+No CPU or torch fallback: CPU tensors raise "CPU not supported" like every other op of the
+drop-in (the reference's tile-and-min formulation lives in oracle/cpu_modules.py as the checker).
 """
 import torch
 
@@ -29,13 +30,10 @@ def _pair_cost(diff, l1smooth, delta, l1):
 
 
 def nn_distance(pc1, pc2, l1smooth=False, delta=1.0, l1=False):
-    if not pc1.is_cuda or pc1.size(-1) > 4:
-        N, M = pc1.shape[1], pc2.shape[1]
-        diff = pc1.unsqueeze(2).repeat(1, 1, M, 1) - pc2.unsqueeze(1).repeat(1, N, 1, 1)
-        pc_dist = _pair_cost(diff, l1smooth, delta, l1)
-        dist1, idx1 = torch.min(pc_dist, dim=2)
-        dist2, idx2 = torch.min(pc_dist, dim=1)
-        return dist1, idx1, dist2, idx2
+    if not pc1.is_cuda or not pc2.is_cuda:
+        raise RuntimeError("CPU not supported")
+    if pc1.size(-1) > 4:
+        raise RuntimeError("nn_distance: at most 4 coordinates per point (got %d)" % pc1.size(-1))
     B, N, C = pc1.shape
     M = pc2.shape[1]
     a = pc1.detach().contiguous().float()

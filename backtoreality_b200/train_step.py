@@ -10,16 +10,35 @@ Values that are baked in at capture time: tensor addresses (the input is a stati
 `__call__` copies into), BatchNorm momentum (a Python float the reference's BNMomentumScheduler
 changes once per epoch, pytorch_utils.py:262-296 -> call `recapture()` after changing it) and the
 learning rate unless it is a tensor.
+
+The warm-up steps that precede a capture are REAL steps on the static batch.  Pass
+`snapshot=[model, optimizer, ...]` (anything with state_dict / load_state_dict) and their state
+-- weights, BatchNorm running statistics and num_batches_tracked, optimizer moments and step
+counts -- is saved before the warm-up and restored after it, so a (re)capture leaves training
+exactly where it was (a recapture per epoch, after BNMomentumScheduler.step(), would otherwise
+add `warmup` weight updates on duplicated data each time).
 """
+import copy
+
 import torch
+
+
+def _save_state(objs):
+    return [copy.deepcopy(o.state_dict()) for o in (objs or [])]
+
+
+def _restore_state(objs, saved):
+    for o, sd in zip(objs or [], saved):
+        o.load_state_dict(sd)
 
 
 class CapturedTrainStep:
     """`step_fn(static_input) -> loss tensor` runs fwd + bwd + all-reduce + optimizer, eagerly.
     This wraps it: `loss = captured(batch)` copies `batch` into the static input and replays."""
 
-    def __init__(self, step_fn, example_input, warmup=3, after_warmup_step=None):
+    def __init__(self, step_fn, example_input, warmup=3, after_warmup_step=None, snapshot=None):
         self.step_fn = step_fn
+        self.snapshot = snapshot
         self.after_warmup_step = after_warmup_step   # e.g. the eager optimizer / gradient reset
         self.static_in = example_input.clone()
         self.warmup = warmup
@@ -32,6 +51,7 @@ class CapturedTrainStep:
         from . import _ext
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        saved = _save_state(self.snapshot)
         with torch.cuda.stream(side):
             for _ in range(self.warmup):
                 self.step_fn(self.static_in)
@@ -39,6 +59,7 @@ class CapturedTrainStep:
                     self.after_warmup_step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        _restore_state(self.snapshot, saved)
         saved_ops = set(_ext.TIME_OPS)
         _ext.TIME_OPS.clear()          # timing events cannot be recorded inside a capture
         l0 = _ext.LAUNCHES
@@ -106,9 +127,10 @@ class PipelinedTrainStep:
         return cls.GEO_KEYS + tuple(k for k in cls.PLAN_KEYS + cls.FP_KEYS if k in level)
 
     def __init__(self, backbone, step_fn, first_batch, warmup=3, fps_cluster=4, sm_caps=None,
-                 after_warmup_step=None, start_after_level=1):
+                 after_warmup_step=None, start_after_level=1, snapshot=None):
         self.backbone = backbone
         self.step_fn = step_fn
+        self.snapshot = snapshot
         self.after_warmup_step = after_warmup_step
         self.fps_cluster = int(fps_cluster)
         if sm_caps is None:
@@ -189,6 +211,7 @@ class PipelinedTrainStep:
         from . import _ext
         warm = torch.cuda.Stream()
         warm.wait_stream(torch.cuda.current_stream())
+        saved = _save_state(getattr(self, "snapshot", None))
         with torch.cuda.stream(warm):
             for _ in range(self.warmup):
                 self._pipelined()
@@ -196,6 +219,7 @@ class PipelinedTrainStep:
                     self.after_warmup_step()
         torch.cuda.current_stream().wait_stream(warm)
         torch.cuda.synchronize()
+        _restore_state(getattr(self, "snapshot", None), saved)
         saved_ops = set(_ext.TIME_OPS)
         _ext.TIME_OPS.clear()          # timing events cannot be recorded inside a capture
         l0 = _ext.LAUNCHES
@@ -236,9 +260,10 @@ class PipelinedTrainStep2(PipelinedTrainStep):
     """
 
     def __init__(self, backbone, step_fn, first_batch, second_batch, warmup=3, fps_cluster=4,
-                 sm_caps=None, after_warmup_step=None, start_after_level=1):
+                 sm_caps=None, after_warmup_step=None, start_after_level=1, snapshot=None):
         self.backbone = backbone
         self.step_fn = step_fn
+        self.snapshot = snapshot
         self.after_warmup_step = after_warmup_step
         self.fps_cluster = int(fps_cluster)
         if sm_caps is None:

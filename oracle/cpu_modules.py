@@ -218,3 +218,21 @@ class VoteNetCPU(nn.Module):
         net = F.relu(p.bn2(p.conv2(net)))
         ep['proposal_scores_raw'] = p.conv3(net)
         return ep
+
+
+def nn_distance(pc1, pc2, l1smooth=False, delta=1.0, l1=False):
+    """The reference's tile-and-min formulation (utils/nn_distance.py:34-61), restated: the checker
+    of backtoreality_b200.nn_distance."""
+    N, M = pc1.shape[1], pc2.shape[1]
+    diff = pc1.unsqueeze(2).repeat(1, 1, M, 1) - pc2.unsqueeze(1).repeat(1, N, 1, 1)
+    if l1smooth:
+        a = torch.abs(diff)
+        q = torch.clamp(a, max=delta)
+        cost = torch.sum(0.5 * q ** 2 + delta * (a - q), dim=-1)
+    elif l1:
+        cost = torch.sum(torch.abs(diff), dim=-1)
+    else:
+        cost = torch.sum(diff ** 2, dim=-1)
+    dist1, idx1 = torch.min(cost, dim=2)
+    dist2, idx2 = torch.min(cost, dim=1)
+    return dist1, idx1, dist2, idx2

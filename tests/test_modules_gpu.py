@@ -282,6 +282,15 @@ def test_captured_train_step_matches_eager(cuda):
     bn_e = net_e.backbone_net.sa1.mlp_module.layer0.bn.bn
     bn_g = net_g.backbone_net.sa1.mlp_module.layer0.bn.bn
     assert int(bn_e.num_batches_tracked) == 4 and int(bn_g.num_batches_tracked) == 7
+    # ... unless the caller asks for the warm-up steps to be rolled back (snapshot=): the capture
+    # then leaves weights, running statistics and step counts where they were
+    net_s, step_s = make()
+    before = {k: v.clone() for k, v in net_s.state_dict().items()}
+    cap_s = CapturedTrainStep(step_s, batches[0], warmup=3, snapshot=[net_s])
+    for k, v in net_s.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    cap_s(batches[1])
+    assert int(net_s.backbone_net.sa1.mlp_module.layer0.bn.bn.num_batches_tracked) == 1
 
 
 @pytest.mark.parametrize("start_after_level", [None, 1, 3])

@@ -64,9 +64,10 @@ def test_product_modules_have_the_reference_state_dict_layout():
         mine.load_state_dict(sd_r)
 
 
-def test_nn_distance_mirror_equals_reference_module_on_cpu():
-    """The host mirror of utils/nn_distance.py (CPU branch = the reference formulation) against
-    the reference's own module, when the reference tree is present (build container)."""
+def test_nn_distance_oracle_equals_reference_module_on_cpu():
+    """The oracle's restatement of utils/nn_distance.py (the checker of the product's arg-min
+    kernel in tests/test_ops_gpu.py) against the reference's own module, when the reference tree
+    is present (build container); the product itself has no CPU path."""
     import importlib.util
     import os
 
@@ -79,11 +80,14 @@ def test_nn_distance_mirror_equals_reference_module_on_cpu():
     ref = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(ref)
     from backtoreality_b200 import nn_distance as nd
+    from oracle import cpu_modules
     g = torch.Generator().manual_seed(4)
     p1, p2 = torch.rand(3, 40, 3, generator=g), torch.rand(3, 17, 3, generator=g)
     for kw in ({}, {"l1": True}, {"l1smooth": True, "delta": 0.25}):
-        got, want = nd.nn_distance(p1, p2, **kw), ref.nn_distance(p1, p2, **kw)
+        got, want = cpu_modules.nn_distance(p1, p2, **kw), ref.nn_distance(p1, p2, **kw)
         for a, b in zip(got, want):
             assert torch.equal(a, b)
     e = torch.randn(50, generator=g)
     assert torch.equal(nd.huber_loss(e, 0.4), ref.huber_loss(e, 0.4))
+    with pytest.raises(RuntimeError, match="CPU not supported"):
+        nd.nn_distance(p1, p2)
