@@ -12,6 +12,8 @@ device inputs raise RuntimeError with the reference's messages; CPU tensors rais
 "CPU not supported" (sampling.cpp:38-40).  A failing kernel launch raises instead of calling
 exit(-1) (cuda_utils.h:35-44).
 """
+import os
+
 import torch
 
 from . import _lib
@@ -96,18 +98,31 @@ class _on_device:
             torch.cuda.set_device(self.prev)
 
 
+# B2R_FPS_LEGACY=1 keeps round 1's kernel (csrc/fps.cu: every point updated every iteration,
+# warp -> CTA -> cluster reduction) for A/B measurements; the indices are identical either way
+FPS_LEGACY = os.environ.get("B2R_FPS_LEGACY", "0") not in ("0", "")
+
+
 def furthest_point_sampling(points, nsamples, cluster=0):
     """(B,N,3) f32 -> (B,nsamples) i32.  Replaces sampling.cpp:70-91.  `cluster` (not in the
     reference's signature, default 0 = lowest latency) caps the CTAs one scene holds; the
-    indices do not depend on it (include/b2r.h: b2r_fps_ex)."""
+    indices do not depend on it (include/b2r.h: b2r_fps_ws / b2r_fps_ex)."""
     _chk_contig(points, "points")
     _chk_float(points, "points")
     _chk_cuda(points, [])
     B, N = points.size(0), points.size(1)
     out = torch.empty((B, nsamples), dtype=torch.int32, device=points.device)
     with _on_device(points), _timed("furthest_point_sampling"):
-        _lib.check(_lib.lib().b2r_fps_ex(points.data_ptr(), B, N, int(nsamples), out.data_ptr(),
-                                         int(cluster), _stream()), "furthest_point_sampling")
+        l = _lib.lib()
+        if FPS_LEGACY:
+            _lib.check(l.b2r_fps_ex(points.data_ptr(), B, N, int(nsamples), out.data_ptr(),
+                                    int(cluster), _stream()), "furthest_point_sampling")
+        else:
+            nbytes = int(l.b2r_fps_workspace_bytes(B, N))
+            ws = torch.empty((max(nbytes, 4),), dtype=torch.uint8, device=points.device)
+            _lib.check(l.b2r_fps_ws(points.data_ptr(), B, N, int(nsamples), out.data_ptr(),
+                                    int(cluster), ws.data_ptr(), nbytes, _stream()),
+                       "furthest_point_sampling")
     return out
 
 

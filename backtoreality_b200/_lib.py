@@ -24,6 +24,8 @@ SIGNATURES = {
     "b2r_fps": [_vp, _i, _i, _i, _vp, _vp],
     "b2r_fps_ex": [_vp, _i, _i, _i, _vp, _i, _vp],
     "b2r_fps_plan": [_i, _i, _ip, _ip, _ip, _ip],
+    "b2r_fps_workspace_bytes": [_i, _i],
+    "b2r_fps_ws": [_vp, _i, _i, _i, _vp, _i, _vp, ctypes.c_longlong, _vp],
     "b2r_gather_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "b2r_gather_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "b2r_ball_query": [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp],
@@ -39,6 +41,7 @@ SIGNATURES = {
     "b2r_query_group_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp],
 }
 _RESTYPES = {"b2r_status_string": ctypes.c_char_p, "b2r_last_error": ctypes.c_char_p,
+             "b2r_fps_workspace_bytes": ctypes.c_longlong,
              "b2r_ball_query_workspace_bytes": ctypes.c_longlong,
              "b2r_mlp_weight_image_bytes": ctypes.c_longlong}
 

@@ -20,6 +20,7 @@ GEOMETRY_STREAM = True
 # whole register file), so the concurrent MLP kernels leave this many SMs free
 GEOMETRY_SMS = 8
 _GEO_STREAMS = {}   # device -> side stream (module-level: nn.Module copies stay picklable)
+_QUERY_STREAMS = {}  # device -> second side stream (ball queries beside the next level's FPS)
 
 
 class Pointnet2Backbone(nn.Module):
@@ -76,6 +77,12 @@ class Pointnet2Backbone(nn.Module):
             if side is None:
                 side = _GEO_STREAMS[xyz.device] = torch.cuda.Stream(device=xyz.device)
         side.wait_stream(main)
+        # ball query + pad-free plan of a level run on a SECOND side stream, beside the next
+        # level's FPS (both only need this level's centres): the serial FPS chain
+        # sa1 -> sa2 -> sa3 -> sa4 is the longest dependency chain of the pre-pass
+        query = _QUERY_STREAMS.get(xyz.device)
+        if query is None:
+            query = _QUERY_STREAMS[xyz.device] = torch.cuda.Stream(device=xyz.device)
         levels, cur = list(prev) if prev is not None else [], xyz
         assert len(levels) == first
         with torch.cuda.stream(side), torch.no_grad():
@@ -83,13 +90,17 @@ class Pointnet2Backbone(nn.Module):
                 inds = _ext.furthest_point_sampling(cur, sa.npoint, cluster=fps_cluster)
                 new_xyz = pointnet2_utils.gather_operation(
                     cur.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
-                idx = pointnet2_utils.ball_query(sa.radius, sa.nsample, cur, new_xyz)
-                # the block's pad-free position space (fused_sa.compact_plan) is geometry too
-                plan = {}
-                if fused_sa.ENABLED and fused_sa.compact_wanted(sa.nsample):
-                    plan = fused_sa.compact_plan(idx, cur.shape[1])
-                ev = torch.cuda.Event()
-                ev.record(side)
+                query.wait_stream(side)
+                with torch.cuda.stream(query):
+                    idx = pointnet2_utils.ball_query(sa.radius, sa.nsample, cur, new_xyz)
+                    # the block's pad-free position space (fused_sa.compact_plan) is geometry too
+                    plan = {}
+                    if fused_sa.ENABLED and fused_sa.compact_wanted(sa.nsample):
+                        plan = fused_sa.compact_plan(idx, cur.shape[1])
+                    ev = torch.cuda.Event()
+                    ev.record(query)
+                cur.record_stream(query)
+                new_xyz.record_stream(query)
                 for t in (inds, new_xyz, idx) + tuple(plan.values()):
                     t.record_stream(main)
                 levels.append(dict(plan, inds=inds, new_xyz=new_xyz, idx=idx, event=ev,
@@ -97,6 +108,7 @@ class Pointnet2Backbone(nn.Module):
                                    else sm_limit))
                 cur = new_xyz
             if last < 3:
+                side.wait_stream(query)   # joining `side` joins the whole pre-pass
                 return levels
             # the FP modules' 3-NN indices and inverse-distance weights are geometry too:
             # fp1 interpolates sa4 -> sa3, fp2 sa3 -> sa2 (stored with the last level, whose
@@ -109,6 +121,7 @@ class Pointnet2Backbone(nn.Module):
             for t in (i1, w1, i2, w2):
                 t.record_stream(main)
             levels[3].update(fp1_idx=i1, fp1_weight=w1, fp2_idx=i2, fp2_weight=w2, fp_event=ev)
+            side.wait_stream(query)       # joining `side` joins the whole pre-pass
         if sm_limit is None:
             levels[-1]["sm_limit"] = 0   # nothing runs beside sa4's MLP
         return levels

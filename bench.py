@@ -407,6 +407,24 @@ def trace_steps(path, fn, steps=3):
         f.write("sum of kernel durations %.1f us (overlap across streams counted twice)\n" % tot)
         for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
             f.write("%4d %9.1f us %5.1f%%  %s\n" % (n, us, 100 * us / tot, k))
+    # time-ordered timeline of the last step with the stream of every record (critical-path view)
+    try:
+        kev = [k for k in prof.profiler.kineto_results.events()
+               if "cuda" in str(k.device_type()).lower() and k.duration_ns() > 0]
+        kev.sort(key=lambda k: k.start_ns())
+        t1 = max(k.start_ns() + k.duration_ns() for k in kev)
+        t0 = t1 - span * 1e3
+        streams = {}
+        with open(path.replace(".txt", "") + "_timeline.txt", "w") as f:
+            f.write("# last traced step: start us (from step begin), duration us, stream, kernel\n")
+            for k in kev:
+                if k.start_ns() < t0:
+                    continue
+                sid = streams.setdefault(k.device_resource_id(), len(streams))
+                f.write("%9.1f %8.1f  s%d  %s\n" % ((k.start_ns() - t0) / 1e3, k.duration_ns() / 1e3, sid,
+                                                  k.name()[:110]))
+    except Exception as e:  # the timeline is a diagnostic; the summary above is the artifact
+        print("timeline dump failed: %r" % (e,), file=sys.stderr)
 
 
 # ------------------------------------------------------------------------- GPU arm ---------

@@ -74,6 +74,19 @@ B2R_API int b2r_fps(const float *xyz, int B, int N, int npoint, int *idx, void *
 B2R_API int b2r_fps_ex(const float *xyz, int B, int N, int npoint, int *idx, int cluster_hint,
                        void *stream);
 
+/* The same sampling on spatially sorted buckets (csrc/fps_bucket.cu) -- the variant the Python
+ * shim calls.  Points are first ordered by a Morton cell code (one counting sort per scene); every
+ * warp owns a compact bucket with its bounding box and SKIPS an iteration's distance updates when
+ * the new sample is provably too far to lower any of its running min-distances (the bound is
+ * evaluated with the reference's own rounding sequence, so only updates that would change nothing
+ * are skipped: indices stay bit-identical to b2r_fps and to the reference).  Warps exchange
+ * candidates in one DSMEM hop into a table replicated in every CTA of the scene's cluster.
+ * workspace: b2r_fps_workspace_bytes(B,N) bytes of device memory (the sorted order), caller-owned
+ * so the call allocates nothing (CUDA-graph capturable).  cluster_hint as in b2r_fps_ex. */
+B2R_API long long b2r_fps_workspace_bytes(int B, int N);
+B2R_API int b2r_fps_ws(const float *xyz, int B, int N, int npoint, int *idx, int cluster_hint,
+                       void *workspace, long long workspace_bytes, void *stream);
+
 /* Launch geometry b2r_fps would use for (B,N): cluster size, threads per CTA, points per thread
  * and dynamic shared memory bytes.  Any out pointer may be NULL. */
 B2R_API int b2r_fps_plan(int B, int N, int *cluster_size, int *threads, int *points_per_thread,

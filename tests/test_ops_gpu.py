@@ -94,6 +94,35 @@ def test_fps_cluster_hint_does_not_change_indices(cuda, hint):
     assert np.array_equal(got, cpu_ops.fps(small, 256))
 
 
+@pytest.mark.parametrize("N,npoint", [(40000, 1024), (3000, 256), (300, 64)])
+def test_fps_legacy_kernel_still_exact(cuda, N, npoint, monkeypatch):
+    """csrc/fps.cu (every point updated every iteration; b2r_fps / b2r_fps_ex) stays in the
+    library as the workspace-free entry point: same indices as the bucket kernel and the oracle."""
+    from backtoreality_b200 import _ext
+    xyz = scenes.batch(21, 2, N, C=0, kind="room", dup=0.2)[..., :3]
+    want = cpu_ops.fps(xyz, npoint)
+    monkeypatch.setattr(_ext, "FPS_LEGACY", True)
+    assert np.array_equal(_ext.furthest_point_sampling(_t(xyz, cuda), npoint).cpu().numpy(), want)
+    monkeypatch.setattr(_ext, "FPS_LEGACY", False)
+    assert np.array_equal(_ext.furthest_point_sampling(_t(xyz, cuda), npoint).cpu().numpy(), want)
+
+
+def test_fps_bucket_kernel_degenerate_geometry(cuda):
+    """Cases that stress the bucket bound: all points on a line / in one cell, coordinates far
+    from the origin, a few far outliers (huge bounding box, every other point in one cell)."""
+    rng = np.random.default_rng(31)
+    line = np.zeros((2, 6000, 3), np.float32)
+    line[..., 0] = rng.random((2, 6000), dtype=np.float32) * 50 + 1
+    _fps_check(line, 200, cuda)
+    far = rng.random((2, 9000, 3), dtype=np.float32) * 2 + np.float32(4000.0)
+    _fps_check(far, 200, cuda)
+    out = rng.random((2, 20000, 3), dtype=np.float32) + 1
+    out[:, :5] *= 1e4
+    _fps_check(out, 300, cuda)
+    grid = np.stack(np.meshgrid(np.arange(20), np.arange(20), np.arange(20)), -1).reshape(1, -1, 3)
+    _fps_check((grid.astype(np.float32) + 1.0), 400, cuda)     # massive exact ties (lattice)
+
+
 def test_fps_npoint_zero_and_one(cuda):
     from backtoreality_b200 import _ext
     xyz = torch.rand(2, 100, 3, device=cuda)
