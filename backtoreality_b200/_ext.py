@@ -202,6 +202,54 @@ def group_points(points, idx):
     return out
 
 
+# B2R_SCATTER_ATOMIC=1 keeps round 1's RED.ADD.F32 scatter kernels (b2r_group_bwd /
+# b2r_three_interp_bwd: unordered sums, atomics-bound) for A/B measurements
+SCATTER_ATOMIC = os.environ.get("B2R_SCATTER_ATOMIC", "0") not in ("0", "")
+# B2R_DETERMINISTIC=1: always take the plan path (run-to-run bit-identical gradients of
+# group_points / three_interpolate), also where the atomic scatter would be faster
+DETERMINISTIC = os.environ.get("B2R_DETERMINISTIC", "0") not in ("0", "")
+_PLAN_CACHE = {}   # (ptr, version, shape, N, weight ptr/version) -> plan tensor; a few entries
+
+
+def scatter_plan(idx, N, weight=None):
+    """Inverse index of `idx` for the deterministic backward kernels (include/b2r.h:
+    b2r_scatter_plan).  idx (B,NP,NS) for grouping, (B,n,3) + weight for three_interpolate.  The
+    same index tensor is scattered through twice per QueryAndGroup (xyz and features), so plans
+    are cached on (storage, version) outside CUDA-graph capture."""
+    B = idx.size(0)
+    E = idx.numel() // max(B, 1)
+    K = 3 if weight is not None else 1
+    capturing = torch.cuda.is_current_stream_capturing()
+    key = (idx.data_ptr(), idx._version, tuple(idx.shape), int(N),
+           None if weight is None else (weight.data_ptr(), weight._version))
+    if not capturing and key in _PLAN_CACHE:
+        return _PLAN_CACHE[key]
+    l = _lib.lib()
+    nbytes = int(l.b2r_scatter_plan_bytes(B, E, int(N), K, int(weight is not None)))
+    plan = torch.empty((nbytes,), dtype=torch.uint8, device=idx.device)
+    _lib.check(l.b2r_scatter_plan(idx.data_ptr(), None if weight is None else weight.data_ptr(), B, E,
+                                  int(N), K, plan.data_ptr(), nbytes, _stream()), "scatter_plan")
+    if not capturing:
+        if len(_PLAN_CACHE) >= 8:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+        # the key holds raw pointers: keep the tensors alive with the plan so they cannot be
+        # recycled under the same address + version
+        _PLAN_CACHE[key] = plan
+        plan._b2r_keepalive = (idx, weight)
+    return plan
+
+
+def _plan_pays(entries, targets, per_source, rows):
+    """The plan kernels walk every (source tile, target) pair of a row and run one CTA per (b,c) row:
+    they beat the atomic scatter when lists are not mostly empty (entries >= 2 x tiles x targets) and
+    there are rows enough to fill the GPU; otherwise the atomic kernels stay (measured:
+    profiles/r02/movers_roofline.log)."""
+    if DETERMINISTIC:
+        return True
+    tiles = -(-(entries // per_source) // 16384)
+    return entries >= 2 * tiles * targets and rows >= 96
+
+
 def group_points_grad(grad_out, idx, n):
     """(B,C,NP,NS), (B,NP,NS), n -> (B,C,n).  Replaces group_points.cpp:42-65."""
     _chk_contig(grad_out, "grad_out")
@@ -212,8 +260,14 @@ def group_points_grad(grad_out, idx, n):
     B, C, NP, NS = grad_out.shape
     out = torch.empty((B, C, int(n)), dtype=torch.float32, device=grad_out.device)
     with _on_device(grad_out), _timed("group_points_grad"):
-        _lib.check(_lib.lib().b2r_group_bwd(grad_out.data_ptr(), idx.data_ptr(), B, C, int(n), NP,
-                                            NS, out.data_ptr(), _stream()), "group_points_grad")
+        if SCATTER_ATOMIC or B * C * NP * NS == 0 or int(n) == 0 or not _plan_pays(NP * NS, int(n), 1, B * C):
+            _lib.check(_lib.lib().b2r_group_bwd(grad_out.data_ptr(), idx.data_ptr(), B, C, int(n), NP,
+                                                NS, out.data_ptr(), _stream()), "group_points_grad")
+        else:
+            plan = scatter_plan(idx, int(n))
+            _lib.check(_lib.lib().b2r_group_bwd_plan(grad_out.data_ptr(), plan.data_ptr(), B, C, int(n),
+                                                     NP, NS, out.data_ptr(), _stream()),
+                       "group_points_grad")
     return out
 
 
@@ -266,10 +320,16 @@ def three_interpolate_grad(grad_out, idx, weight, m):
     B, C, n = grad_out.shape
     out = torch.empty((B, C, int(m)), dtype=torch.float32, device=grad_out.device)
     with _on_device(grad_out), _timed("three_interpolate_grad"):
-        _lib.check(_lib.lib().b2r_three_interp_bwd(grad_out.data_ptr(), idx.data_ptr(),
-                                                   weight.data_ptr(), B, C, n, int(m),
-                                                   out.data_ptr(), _stream()),
-                   "three_interpolate_grad")
+        if SCATTER_ATOMIC or B * C * n == 0 or int(m) == 0 or not _plan_pays(3 * n, int(m), 3, B * C):
+            _lib.check(_lib.lib().b2r_three_interp_bwd(grad_out.data_ptr(), idx.data_ptr(),
+                                                       weight.data_ptr(), B, C, n, int(m),
+                                                       out.data_ptr(), _stream()),
+                       "three_interpolate_grad")
+        else:
+            plan = scatter_plan(idx, int(m), weight)
+            _lib.check(_lib.lib().b2r_three_interp_bwd_plan(grad_out.data_ptr(), plan.data_ptr(), B, C,
+                                                            n, int(m), out.data_ptr(), _stream()),
+                       "three_interpolate_grad")
     return out
 
 

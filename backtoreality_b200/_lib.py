@@ -36,12 +36,17 @@ SIGNATURES = {
     "b2r_three_nn": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "b2r_three_interp_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "b2r_three_interp_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "b2r_scatter_plan_bytes": [_i, ctypes.c_longlong, _i, _i, _i],
+    "b2r_scatter_plan": [_vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, ctypes.c_longlong, _vp],
+    "b2r_group_bwd_plan": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "b2r_three_interp_bwd_plan": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "b2r_nn_argmin": [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp],
     "b2r_query_group_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp],
     "b2r_query_group_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp],
 }
 _RESTYPES = {"b2r_status_string": ctypes.c_char_p, "b2r_last_error": ctypes.c_char_p,
              "b2r_fps_workspace_bytes": ctypes.c_longlong,
+             "b2r_scatter_plan_bytes": ctypes.c_longlong,
              "b2r_ball_query_workspace_bytes": ctypes.c_longlong,
              "b2r_mlp_weight_image_bytes": ctypes.c_longlong}
 

@@ -20,7 +20,7 @@ GEOMETRY_STREAM = True
 # whole register file), so the concurrent MLP kernels leave this many SMs free
 GEOMETRY_SMS = 8
 _GEO_STREAMS = {}   # device -> side stream (module-level: nn.Module copies stay picklable)
-_QUERY_STREAMS = {}  # device -> second side stream (ball queries beside the next level's FPS)
+_QUERY_STREAMS = {}  # (device, side stream) -> second side stream (ball queries beside the next level's FPS)
 
 
 class Pointnet2Backbone(nn.Module):
@@ -80,9 +80,10 @@ class Pointnet2Backbone(nn.Module):
         # ball query + pad-free plan of a level run on a SECOND side stream, beside the next
         # level's FPS (both only need this level's centres): the serial FPS chain
         # sa1 -> sa2 -> sa3 -> sa4 is the longest dependency chain of the pre-pass
-        query = _QUERY_STREAMS.get(xyz.device)
+        qkey = (xyz.device, side.cuda_stream)     # one per side stream: independent chains
+        query = _QUERY_STREAMS.get(qkey)          # (train_step.PipelinedTrainStep2) stay independent
         if query is None:
-            query = _QUERY_STREAMS[xyz.device] = torch.cuda.Stream(device=xyz.device)
+            query = _QUERY_STREAMS[qkey] = torch.cuda.Stream(device=xyz.device)
         levels, cur = list(prev) if prev is not None else [], xyz
         assert len(levels) == first
         with torch.cuda.stream(side), torch.no_grad():

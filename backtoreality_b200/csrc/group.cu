@@ -10,9 +10,21 @@
 // random reads confined to one feature row (<= 4*N bytes, L1/L2 resident).
 // Backward passes zero-fill the output with cudaMemsetAsync and accumulate with fire-and-forget
 // RED.ADD.F32 (same unordered-sum contract as the reference's atomicAdd).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b2r {
+// movers_staged.cu: source row staged in shared memory (true if it took the call)
+bool group_fwd_staged(const float *f, const int *idx, int B, int C, int N, long long L, float *out,
+                      cudaStream_t st, cudaError_t *err);
+bool movers_legacy() {   // B2R_MOVERS_LEGACY=1: round 1's direct-from-global kernels (A/B timing)
+  static const bool v = []() {
+    const char *e = getenv("B2R_MOVERS_LEGACY");
+    return e && *e && *e != '0';
+  }();
+  return v;
+}
 namespace {
 
 constexpr int kThreads = 256;
@@ -249,6 +261,13 @@ extern "C" int b2r_group_fwd(const float *features, const int *idx, int B, int C
   B2R_REQUIRE(features && idx && out, "b2r_group_fwd: null pointer");
   B2R_REQUIRE(B <= 65535, "b2r_group_fwd: B too large");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!movers_legacy()) {
+    cudaError_t e = cudaSuccess;
+    if (group_fwd_staged(features, idx, B, C, N, L, out, st, &e)) {
+      B2R_CUDA(e);
+      return B2R_OK;
+    }
+  }
   const bool vec = (L % 4 == 0) && aligned16(idx) && aligned16(out);
   const int xb = ceil_div(L, (long long)kThreads * (vec ? 4 : 1));
   const int cpb = pick_cpb(xb, C, B);

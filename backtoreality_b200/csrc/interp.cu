@@ -16,6 +16,10 @@
 #include "common.cuh"
 
 namespace b2r {
+// movers_staged.cu: source rows staged in shared memory (true if it took the call)
+bool interp_fwd_staged(const float *f, const int *idx, const float *w, int B, int C, int m, int n,
+                       float *out, cudaStream_t st, cudaError_t *err);
+bool movers_legacy();
 namespace {
 
 constexpr int kNnThreads = 128;
@@ -165,6 +169,13 @@ extern "C" int b2r_three_interp_fwd(const float *features, const int *idx, const
   if (B == 0 || C == 0 || n == 0) return B2R_OK;
   B2R_REQUIRE(features && idx && weight && out, "b2r_three_interp_fwd: null pointer");
   B2R_REQUIRE(B <= 65535, "b2r_three_interp_fwd: B too large");
+  if (!movers_legacy()) {
+    cudaError_t e = cudaSuccess;
+    if (interp_fwd_staged(features, idx, weight, B, C, m, n, out, static_cast<cudaStream_t>(stream), &e)) {
+      B2R_CUDA(e);
+      return B2R_OK;
+    }
+  }
   const int xb = ceil_div(n, kIpThreads);
   const int cpb = pick_cpb(xb, C, B);
   dim3 grid(xb, ceil_div(C, cpb), B);

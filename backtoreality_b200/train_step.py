@@ -260,8 +260,12 @@ class PipelinedTrainStep2(PipelinedTrainStep):
     """
 
     def __init__(self, backbone, step_fn, first_batch, second_batch, warmup=3, fps_cluster=4,
-                 sm_caps=None, after_warmup_step=None, start_after_level=1, snapshot=None):
+                 sm_caps=None, after_warmup_step=None, start_after_level=1, snapshot=None,
+                 b_from_start=False):
         self.backbone = backbone
+        # False: both geometry chains start from the same hook (after SA level
+        # `start_after_level`'s forward), so the wide first-level kernels keep every SM
+        self.b_from_start = bool(b_from_start)
         self.step_fn = step_fn
         self.snapshot = snapshot
         self.after_warmup_step = after_warmup_step
@@ -306,14 +310,20 @@ class PipelinedTrainStep2(PipelinedTrainStep):
         xyz_next2 = self._xyz(self.next2)     # referenced until the side streams are joined
         box = {}
 
+        lvl0 = dict(self.geo_a_next, event=None, sm_limit=0)
+
         def launch_a():
             box["a"] = self.backbone.geometry_prepass(xyz_next2, fps_cluster=self.fps_cluster,
                                                       sm_limit=0, side=self.side, first=0, last=0)
+            if not self.b_from_start:
+                launch_b()
 
-        # B from the start of the step: one-CTA-per-scene FPS launches, 8 SMs
-        lvl0 = dict(self.geo_a_next, event=None, sm_limit=0)
-        geo_b = self.backbone.geometry_prepass(self.geo_a_next["new_xyz"], sm_limit=0,
-                                               side=self.side_b, first=1, last=3, prev=[lvl0])
+        def launch_b():   # one-CTA-per-scene FPS launches: 8 SMs + the ball queries
+            box["b"] = self.backbone.geometry_prepass(self.geo_a_next["new_xyz"], sm_limit=0,
+                                                      side=self.side_b, first=1, last=3, prev=[lvl0])
+
+        if self.b_from_start:
+            launch_b()
         levels = self._levels(self.geo_cur)
         if self.start_after_level is None:
             launch_a()
@@ -322,6 +332,7 @@ class PipelinedTrainStep2(PipelinedTrainStep):
         loss = self.step_fn(self.cur, levels)
         if "a" not in box:
             launch_a()
+        geo_b = box["b"]
         main.wait_stream(self.side)
         main.wait_stream(self.side_b)
         del xyz_next2

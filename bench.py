@@ -73,7 +73,7 @@ def parse():
     ap.add_argument("--pipeline-depth", type=int, default=1, choices=[1, 2],
                     help="pipelined step: 1 = whole geometry pre-pass of batch i+1 beside step i; 2 = SA1 "
                          "geometry of batch i+2 and the later levels' of batch i+1 beside step i")
-    ap.add_argument("--fps-cluster", type=int, default=5,
+    ap.add_argument("--fps-cluster", type=int, default=4,
                     help="pipelined step: CTAs per scene of the next batch's FPS")
     ap.add_argument("--trace", default="",
                     help="after timing, trace 3 steps with torch.profiler (CUPTI) and write a per-kernel "

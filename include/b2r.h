@@ -161,6 +161,28 @@ B2R_API int b2r_three_interp_bwd(const float *grad_out, const int *idx, const fl
                          int n, int m, float *grad_features, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Deterministic, atomic-free backward of grouping / three_interpolate (csrc/movers_staged.cu).
+ * The reference scatters with atomicAdd (group_points_gpu.cu:48-69, interpolate_gpu.cu:121-148):
+ * the L2 atomic units cap that at a few percent of the HBM roofline and the sum order changes
+ * from run to run.  Here the index is inverted once per index tensor into a plan (entries sorted
+ * by target, each list by entry id) and every (b,c) row is gathered from shared-memory staged
+ * tiles of grad_out in that fixed order: bit-identical results across runs, no memset.
+ *   entries = NP*NS with entries_per_source = 1 (grouping: idx (B,NP,NS), targets in [0,N))
+ *   entries = 3*n   with entries_per_source = 3 (three_interpolate: idx (B,n,3), targets in [0,m),
+ *             weight (B,n,3) is permuted into the plan; pass NULL for grouping)
+ * plan: b2r_scatter_plan_bytes(...) bytes of device memory, caller-owned. */
+B2R_API long long b2r_scatter_plan_bytes(int B, long long entries, int N, int entries_per_source,
+                                         int weighted);
+B2R_API int b2r_scatter_plan(const int *idx, const float *weight, int B, long long entries, int N,
+                             int entries_per_source, void *plan, long long plan_bytes, void *stream);
+/* group_points_grad through a plan of idx (B,NP,NS): grad_out (B,C,NP,NS) -> grad_features (B,C,N) */
+B2R_API int b2r_group_bwd_plan(const float *grad_out, const void *plan, int B, int C, int N, int NP,
+                               int NS, float *grad_features, void *stream);
+/* three_interpolate_grad through a plan of (idx, weight): grad_out (B,C,n) -> grad_features (B,C,m) */
+B2R_API int b2r_three_interp_bwd_plan(const float *grad_out, const void *plan, int B, int C, int n,
+                                      int m, float *grad_features, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused QueryAndGroup tail (reference Python: pointnet2_utils.py:347-366, i.e. two
  * grouping_operation calls + in-place `-= new_xyz` + `/= radius` + torch.cat, five HBM passes)
  * in ONE pass:

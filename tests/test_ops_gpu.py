@@ -289,6 +289,55 @@ def test_three_interpolate_fwd_bwd(cuda, C, m, n):
     np.testing.assert_allclose(gf, cpu_ops.interp_grad(g, idx, w, m), rtol=1e-4, atol=1e-4)
 
 
+def test_scatter_backward_is_deterministic_and_matches_atomic_path(cuda, monkeypatch):
+    """group_points_grad / three_interpolate_grad through the scatter plan (csrc/movers_staged.cu):
+    bit-identical over repeated runs (no atomics), equal to the oracle and to round 1's atomic
+    kernels within summation-order tolerance; shapes with several source tiles (NP*NS > 16384),
+    hot targets (every ball pads with index 0), a row length that is not a multiple of 4."""
+    from backtoreality_b200 import _ext
+    monkeypatch.setattr(_ext, "DETERMINISTIC", True)   # plan path for every shape (B2R_DETERMINISTIC=1)
+    rng = np.random.default_rng(77)
+    for (C, N, NP, NS) in [(5, 40000, 2048, 64), (64, 2048, 1024, 32), (3, 301, 37, 5)]:
+        idx = rng.integers(0, N, (2, NP, NS)).astype(np.int32)
+        idx[:, :, NS // 2:] = idx[:, :, :1]          # padded balls: heavy duplicates
+        idx[0, : NP // 2, 0] = 0                        # one hot target
+        g = rng.standard_normal((2, C, NP, NS)).astype(np.float32)
+        gt, it = _t(g, cuda), _t(idx, cuda)
+        runs = [_ext.group_points_grad(gt, it, N) for _ in range(3)]
+        assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+        np.testing.assert_allclose(runs[0].cpu().numpy(), cpu_ops.group_grad(g, idx, N), rtol=2e-4, atol=2e-4)
+        monkeypatch.setattr(_ext, "SCATTER_ATOMIC", True)
+        atomic = _ext.group_points_grad(gt, it, N)
+        monkeypatch.setattr(_ext, "SCATTER_ATOMIC", False)
+        torch.testing.assert_close(runs[0], atomic, rtol=2e-4, atol=2e-4)
+    for (C, m, n) in [(16, 2048, 40000), (7, 33, 10001)]:
+        idx = rng.integers(0, m, (2, n, 3)).astype(np.int32)
+        w = rng.random((2, n, 3), dtype=np.float32)
+        g = rng.standard_normal((2, C, n)).astype(np.float32)
+        gt, it, wt = _t(g, cuda), _t(idx, cuda), _t(w, cuda)
+        runs = [_ext.three_interpolate_grad(gt, it, wt, m) for _ in range(3)]
+        assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+        np.testing.assert_allclose(runs[0].cpu().numpy(), cpu_ops.interp_grad(g, idx, w, m), rtol=2e-4, atol=3e-4)
+        monkeypatch.setattr(_ext, "SCATTER_ATOMIC", True)
+        atomic = _ext.three_interpolate_grad(gt, it, wt, m)
+        monkeypatch.setattr(_ext, "SCATTER_ATOMIC", False)
+        torch.testing.assert_close(runs[0], atomic, rtol=2e-4, atol=3e-4)
+
+
+def test_scatter_plan_cache_follows_in_place_index_updates(cuda):
+    """the plan cache is keyed on (storage, version): an index tensor modified in place gets a new plan"""
+    from backtoreality_b200 import _ext
+    rng = np.random.default_rng(5)
+    idx = _t(rng.integers(0, 64, (1, 16, 8)).astype(np.int32), cuda)
+    g = _t(rng.standard_normal((1, 4, 16, 8)).astype(np.float32), cuda)
+    a = _ext.group_points_grad(g, idx, 64)
+    idx.copy_(_t(rng.integers(0, 64, (1, 16, 8)).astype(np.int32), cuda))
+    b = _ext.group_points_grad(g, idx, 64)
+    np.testing.assert_allclose(b.cpu().numpy(), cpu_ops.group_grad(g.cpu().numpy(), idx.cpu().numpy(), 64),
+                               rtol=1e-4, atol=1e-4)
+    assert not torch.equal(a, b)
+
+
 # ------------------------------------------------------------------ fused QueryAndGroup -----
 @pytest.mark.parametrize("C,N,NP,NS,norm", [(1, 5000, 512, 64, True), (128, 2048, 1024, 32, True),
                                             (0, 3000, 100, 16, True), (4, 300, 13, 3, False)])
