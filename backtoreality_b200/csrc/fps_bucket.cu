@@ -37,14 +37,9 @@
 namespace b2r {
 namespace {
 
-constexpr int kTable = 256;  // max warps (buckets) per scene: 16 CTAs x 16 warps
+[[maybe_unused]] constexpr int kTable = 256;  // max warps (buckets) per scene: 16 CTAs x 16 warps
 constexpr int kMaxCta = 16;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
@@ -488,6 +483,168 @@ __global__ void __launch_bounds__(NT, 1)
   if (csize > 1) cluster_sync_all();  // nobody exits while a peer may still address its smem
 }
 
+// ------------------------------------------------------------------ one CTA, few fat warps --
+// Scenes of <= 4096 points (the later SA levels: 2048 -> 1024 -> 512 -> 256, vote aggregation):
+// one CTA holds the scene and the iteration is a pure latency chain.  fps.cu runs it on 16 warps
+// (update, 2 redux, record, bar.sync over 16 warps, 16-record redux round, ballot, lookup: ~775
+// cycles).  Here 4 (8 above 2048 points) warps own 4x the points each -- the update loop is
+// ILP-scheduled, so a fatter thread costs little -- the barrier has 4 arrivals, and every thread
+// reduces the 4-8 warp records itself with plain compares (no second redux round, no ballot; the
+// winner's record slot rides in the key).  Points are not sorted and no bucket is skipped: with
+// 4 buckets per scene there is nothing to skip.
+template <int P, int NT>
+__global__ void __launch_bounds__(NT, 1)
+    fps_small_kernel(const float *__restrict__ xyz, int N, int npoint, int *__restrict__ idx, int L,
+                     int SB) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  float(*s_pts)[P * NT] = reinterpret_cast<float(*)[P * NT]>(s_dyn);        // [3][P*NT]
+  uint32_t *s_lo = reinterpret_cast<uint32_t *>(s_dyn) + 3 * P * NT;        // [P*NT]
+  __shared__ Rec s_rec[2][NT / 32];
+  constexpr int NW = NT / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  xyz += (size_t)blockIdx.x * N * 3;
+  idx += (size_t)blockIdx.x * npoint;
+  if (npoint <= 0) return;
+  if (npoint == 1 || N <= 0) {
+    if (tid == 0) idx[0] = 0;
+    return;
+  }
+  const uint32_t rmask = (1u << (L + SB)) - 1u;
+  for (int i = 0; i < P; ++i) {
+    const int k = tid + i * NT;
+    float x = __int_as_float(0x7fc00000), y = x, z = x;
+    uint32_t lo = 0u;
+    if (k < N) {
+      const float gx = xyz[k * 3 + 0], gy = xyz[k * 3 + 1], gz = xyz[k * 3 + 2];
+      const float mag = sumsq_ref(gx, gy, gz);
+      if (!((double)mag <= 1e-3)) {  // reference: `if (mag <= 1e-3) continue;` in double
+        x = gx; y = gy; z = gz;
+        const uint32_t t = (uint32_t)k & ((1u << L) - 1u);
+        const uint32_t rank = ((L ? (__brev(t) >> (32 - L)) : 0u) << SB) | ((uint32_t)k >> L);
+        lo = 0x80000000u | (((~rank) & rmask) << 8) | (uint32_t)warp;
+      }
+    }
+    s_pts[0][i * NT + tid] = x;
+    s_pts[1][i * NT + tid] = y;
+    s_pts[2][i * NT + tid] = z;
+    s_lo[i * NT + tid] = lo;
+  }
+  // the thread's slots in ascending rank (descending lo, invalid last): see fps_bucket_kernel
+  for (int i = 1; i < P; ++i) {
+    const uint32_t lo = s_lo[i * NT + tid];
+    const float x = s_pts[0][i * NT + tid], y = s_pts[1][i * NT + tid], z = s_pts[2][i * NT + tid];
+    int j = i - 1;
+    while (j >= 0 && s_lo[j * NT + tid] < lo) {
+      s_lo[(j + 1) * NT + tid] = s_lo[j * NT + tid];
+      s_pts[0][(j + 1) * NT + tid] = s_pts[0][j * NT + tid];
+      s_pts[1][(j + 1) * NT + tid] = s_pts[1][j * NT + tid];
+      s_pts[2][(j + 1) * NT + tid] = s_pts[2][j * NT + tid];
+      --j;
+    }
+    s_lo[(j + 1) * NT + tid] = lo;
+    s_pts[0][(j + 1) * NT + tid] = x;
+    s_pts[1][(j + 1) * NT + tid] = y;
+    s_pts[2][(j + 1) * NT + tid] = z;
+  }
+  float px[P], py[P], pz[P], pt[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    px[i] = s_pts[0][i * NT + tid];
+    py[i] = s_pts[1][i * NT + tid];
+    pz[i] = s_pts[2][i * NT + tid];
+    pt[i] = s_lo[i * NT + tid] != 0u ? 1e10f : -1.0f;  // reference scratch fill (sampling.cpp:78-80)
+  }
+  float ox = xyz[0], oy = xyz[1], oz = xyz[2];  // idx[0] = 0, valid or not (sampling_gpu.cu:92-93)
+  if (tid == 0) idx[0] = 0;
+
+  for (int it = 0; it < npoint - 1; ++it) {
+    const int par = it & 1;
+    float best = -1.0f;
+    int bi = 0;
+#pragma unroll
+    for (int g = 0; g < P; g += 4) {   // four points side by side + a compare tree (ILP)
+      float m[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (g + u < P) {
+          const float dx = __fsub_rn(px[g + u], ox), dy = __fsub_rn(py[g + u], oy),
+                      dz = __fsub_rn(pz[g + u], oz);
+          m[u] = fminf(sumsq_ref(dx, dy, dz), pt[g + u]);
+          pt[g + u] = m[u];
+        } else {
+          m[u] = -2.0f;
+        }
+      }
+      const bool s01 = m[1] > m[0], s23 = m[3] > m[2];
+      const float v01 = s01 ? m[1] : m[0], v23 = s23 ? m[3] : m[2];
+      const int i01 = s01 ? g + 1 : g, i23 = s23 ? g + 3 : g + 2;
+      const bool sg = v23 > v01;
+      const float vg = sg ? v23 : v01;
+      const int ig = sg ? i23 : i01;
+      if (vg > best) {
+        best = vg;
+        bi = ig;
+      }
+    }
+    const bool has = best >= 0.0f;
+    const uint32_t hi = has ? __float_as_uint(best) : 0u;
+    const uint32_t lo = has ? s_lo[bi * NT + tid] : 0u;
+    uint32_t whi, wlo;
+    warp_argmax(hi, lo, whi, wlo);
+    if (wlo == 0u ? lane == 0 : (hi == whi && lo == wlo)) {
+      Rec r;
+      r.hi = whi; r.lo = wlo;
+      r.x = s_pts[0][bi * NT + tid];
+      r.y = s_pts[1][bi * NT + tid];
+      r.z = s_pts[2][bi * NT + tid];
+      r.pad0 = r.pad1 = r.pad2 = 0;
+      *reinterpret_cast<uint4 *>(&s_rec[par][warp]) = *reinterpret_cast<uint4 *>(&r);
+      s_rec[par][warp].z = r.z;
+    }
+    __syncthreads();
+    uint32_t khi = 0u, klo = 0u;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const uint2 k = *reinterpret_cast<const uint2 *>(&s_rec[par][w]);
+      if (k.x > khi || (k.x == khi && k.y > klo)) { khi = k.x; klo = k.y; }
+    }
+    if (klo != 0u) {
+      const Rec *w = &s_rec[par][klo & 0xffu];
+      ox = w->x; oy = w->y; oz = w->z;
+    }
+    if (tid == 0) {
+      int old = 0;
+      if (klo != 0u) {
+        const uint32_t rank = (~(klo >> 8)) & rmask;
+        const uint32_t tb = rank >> SB;
+        const uint32_t tt = L ? (__brev(tb) >> (32 - L)) : 0u;
+        old = (int)(tt + ((rank & ((1u << SB) - 1u)) << L));
+      }
+      idx[it + 1] = old;
+    }
+  }
+}
+
+template <int P, int NT>
+cudaError_t launch_small(const float *xyz, int B, int N, int npoint, int *idx, int L, int SB,
+                         cudaStream_t st) {
+  auto kern = fps_small_kernel<P, NT>;
+  constexpr int smem = 4 * P * NT * (int)sizeof(float);
+  if (smem > 48 * 1024) {
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+  }
+  kern<<<B, NT, smem, st>>>(xyz, N, npoint, idx, L, SB);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------ host side --
 struct Plan {
   int L, SB, csize, NT, P, smem, bits;
@@ -629,7 +786,22 @@ extern "C" int b2r_fps_ws(const float *xyz, int B, int N, int npoint, int *idx, 
   }
   // one CTA holds the scene: no DSMEM hop to shorten and (16 buckets) little to skip -- fps.cu's
   // warp -> CTA reduction is the shorter chain there (scripts/fps_sweep.py, profiles/r02)
-  if (N <= b2r::kSingleCtaMaxN && !b2r::g_bucket_small) return b2r_fps_ex(xyz, B, N, npoint, idx, 0, stream);
+  if (N <= b2r::kSingleCtaMaxN && !b2r::g_bucket_small) {
+    b2r::Plan sp;
+    if (!b2r::make_plan(B, N, 0, &sp)) return b2r_fps_ex(xyz, B, N, npoint, idx, 0, stream);
+    cudaError_t e;
+    if (N <= 128) e = b2r::launch_small<1, 128>(xyz, B, N, npoint, idx, sp.L, sp.SB, st);
+    else if (N <= 256) e = b2r::launch_small<2, 128>(xyz, B, N, npoint, idx, sp.L, sp.SB, st);
+    else if (N <= 512) e = b2r::launch_small<4, 128>(xyz, B, N, npoint, idx, sp.L, sp.SB, st);
+    else if (N <= 1024) e = b2r::launch_small<8, 128>(xyz, B, N, npoint, idx, sp.L, sp.SB, st);
+    else if (N <= 2048) e = b2r::launch_small<16, 128>(xyz, B, N, npoint, idx, sp.L, sp.SB, st);
+    else e = b2r::launch_small<16, 256>(xyz, B, N, npoint, idx, sp.L, sp.SB, st);
+    if (e != cudaSuccess) {
+      b2r::set_error("b2r_fps_ws (single-CTA kernel, N=%d) launch failed: %s", N, cudaGetErrorString(e));
+      return B2R_ERR_CUDA;
+    }
+    return B2R_OK;
+  }
   B2R_REQUIRE(workspace != nullptr && workspace_bytes >= b2r_fps_workspace_bytes(B, N),
               "b2r_fps_ws: workspace of %lld bytes, %lld needed", workspace_bytes,
               b2r_fps_workspace_bytes(B, N));
