@@ -32,6 +32,11 @@ def _restore_state(objs, saved):
         o.load_state_dict(sd)
 
 
+# "thread_local": CUDA calls of OTHER threads (the NCCL watchdog polling its events) neither
+# invalidate nor dead-lock a capture -- needed when the step's gradient all-reduce is captured too
+CAPTURE_ERROR_MODE = "thread_local"
+
+
 class CapturedTrainStep:
     """`step_fn(static_input) -> loss tensor` runs fwd + bwd + all-reduce + optimizer, eagerly.
     This wraps it: `loss = captured(batch)` copies `batch` into the static input and replays."""
@@ -65,7 +70,7 @@ class CapturedTrainStep:
         l0 = _ext.LAUNCHES
         try:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode=CAPTURE_ERROR_MODE):
                 loss = self.step_fn(self.static_in)
             self.graph, self.static_loss = g, loss
             self.launches_per_step = _ext.LAUNCHES - l0
@@ -225,7 +230,7 @@ class PipelinedTrainStep:
         l0 = _ext.LAUNCHES
         try:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode=CAPTURE_ERROR_MODE):
                 loss = self._pipelined()
             self.graph, self.static_loss = g, loss
             self.launches_per_step = _ext.LAUNCHES - l0

@@ -128,7 +128,10 @@ def workload_config(a, world):
         "l2": "256 MB buffer written between steps (flush) + 4 rotating input batches",
         "e2e_input": "pinned host -> device on a copy stream, one step ahead (train_step.HostPrefetcher)",
         "launch": ("whole step (fwd+bwd+Adam) captured in one CUDA graph, replayed per batch" if world == 1
-                   else "fwd+bwd replayed from one CUDA graph; NCCL all-reduce + fused Adam eager"),
+                   else ("fwd+bwd replayed from one CUDA graph; NCCL all-reduce + fused Adam eager"
+                         if os.environ.get("B2R_EAGER_COLLECTIVE", "0") not in ("0", "")
+                         else "whole step (fwd+bwd + gradient pack + NCCL all-reduce + Adam) captured in one "
+                              "CUDA graph per rank, replayed per batch")),
         "pipeline": ("none: FPS / ball query of a batch run inside its own step (geometry stream)"
                      if a.no_pipeline or a.no_graph or a.workload == "br"
                      else "geometry pre-pass (FPS, centre gather, ball query, pad-free plans of sa1..sa4) of "
@@ -538,10 +541,12 @@ def run_b2r(a):
     # (N = 1: the optimizer too; N > 1: forward+backward are replayed, the NCCL all-reduce and the
     # 3-kernel fused Adam stay eager so no collective is ever captured)
     graphed = None
-    capture_all = world == 1
+    # B2R_EAGER_COLLECTIVE=1: round 1's arrangement (only forward+backward replayed; pack, NCCL
+    # all-reduce and Adam launched eagerly after every replay)
+    capture_all = world == 1 or os.environ.get("B2R_EAGER_COLLECTIVE", "0") in ("0", "")
     # br runs two forwards per step: its geometry stays inside the step (geometry stream)
     pipelined = not (a.no_graph or a.no_pipeline) and a.workload != "br"
-    if not a.no_graph:
+    for attempt in ((0, 1) if not a.no_graph else ()):
         try:
             from backtoreality_b200.train_step import (CapturedTrainStep, PipelinedTrainStep,
                                                        PipelinedTrainStep2)
@@ -571,7 +576,17 @@ def run_b2r(a):
                 graphed = CapturedTrainStep(step if capture_all else fwd_bwd, resident[0],
                                             after_warmup_step=None if capture_all else finish)
             stage("captured (%d libb2r launches per step)" % graphed.launches_per_step)
-        except Exception as e:  # report, then measure the eager loop instead
+            break
+        except Exception as e:
+            if capture_all and world > 1 and attempt == 0:
+                # the captured collective is the only new ingredient: retry with the all-reduce and
+                # the optimizer launched eagerly after every replay (round 1's arrangement)
+                log("capture with the NCCL all-reduce inside failed (%s: %s); retrying with an eager "
+                    "collective" % (type(e).__name__, e))
+                capture_all = False
+                torch.cuda.synchronize()
+                continue
+            # report, then measure the eager loop instead
             log("CUDA-graph capture failed (%s: %s); timing the eager step" % (type(e).__name__, e))
             graphed = None
             pipelined = False
@@ -641,9 +656,11 @@ def run_b2r(a):
         trace_steps(a.trace, lambda i: run_step(resident[(i + nxt) % pool_n]))
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        # leave without tearing NCCL down (see the end of this function): rank 0 still runs its
+        # single-GPU timing legs and does not need this rank any more
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
     scenes_total = scenes_per_step(a) * world * a.steps
     out = {
@@ -751,7 +768,14 @@ def run_b2r(a):
                 log("leg %s failed: %s: %s" % (leg, type(e).__name__, e))
     emit(out)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: destroying a process group whose collectives live
+        # inside a CUDA graph blocks in the communicator's destructor (seen on 2 GPUs: the result
+        # was printed, the workers never exited).  All timed work is done, the other ranks left
+        # the same way after the last timed barrier, and the OS reclaims everything.
+        torch.cuda.synchronize()
+        _RESULT_OUT.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
