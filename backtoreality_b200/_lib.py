@@ -40,6 +40,8 @@ SIGNATURES = {
     "b2r_scatter_plan": [_vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, ctypes.c_longlong, _vp],
     "b2r_group_bwd_plan": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "b2r_three_interp_bwd_plan": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "b2r_adam_state_bytes": [],
+    "b2r_adam_flat_step": [_vp, _vp, _vp, _vp, ctypes.c_longlong, _vp, _f, _f, _f, _f, _f, _f, _vp],
     "b2r_nn_argmin": [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp],
     "b2r_query_group_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp],
     "b2r_query_group_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp],

@@ -55,7 +55,7 @@ class Pointnet2Backbone(nn.Module):
         return xyz, features
 
     def geometry_prepass(self, xyz, fps_cluster=0, sm_limit=None, side=None, first=0, last=3,
-                         prev=None):
+                         prev=None, copy_to=None):
         """inds / new_xyz / ball-query idx of sa1..sa4 for xyz (B,N,3), issued as one chain on a
         side stream with one event per level.  Returns the list of four per-level dicts that
         `forward(..., geometry=)` and `PointnetSAModuleVotes.forward(..., geometry=)` take.
@@ -70,7 +70,11 @@ class Pointnet2Backbone(nn.Module):
         (returned in front of the new ones); the FP modules' interpolation weights are computed
         with level 3.  Lets a caller run SA1's geometry -- 2047 dependent FPS iterations over the
         whole scene -- and the later levels' as two independent chains
-        (train_step.PipelinedTrainStep with depth 2)."""
+        (train_step.PipelinedTrainStep with depth 2).
+        copy_to: optional list of four dicts of preallocated tensors; every level's results are
+        also copied into copy_to[level][key] on the side streams as soon as they exist
+        (train_step.PipelinedTrainStepPP: the static buffers of the NEXT graph, filled off the
+        critical path)."""
         main = torch.cuda.current_stream()
         if side is None:
             side = _GEO_STREAMS.get(xyz.device)
@@ -98,6 +102,11 @@ class Pointnet2Backbone(nn.Module):
                     plan = {}
                     if fused_sa.ENABLED and fused_sa.compact_wanted(sa.nsample):
                         plan = fused_sa.compact_plan(idx, cur.shape[1])
+                    if copy_to is not None:
+                        dst = copy_to[len(levels)]
+                        keys = [k for k in dst if k in plan or k in ("inds", "new_xyz", "idx")]
+                        src = dict(plan, inds=inds, new_xyz=new_xyz, idx=idx)
+                        torch._foreach_copy_([dst[k] for k in keys], [src[k] for k in keys])
                     ev = torch.cuda.Event()
                     ev.record(query)
                 cur.record_stream(query)
@@ -122,6 +131,9 @@ class Pointnet2Backbone(nn.Module):
             for t in (i1, w1, i2, w2):
                 t.record_stream(main)
             levels[3].update(fp1_idx=i1, fp1_weight=w1, fp2_idx=i2, fp2_weight=w2, fp_event=ev)
+            if copy_to is not None:
+                fpk = [k for k in ("fp1_idx", "fp1_weight", "fp2_idx", "fp2_weight") if k in copy_to[3]]
+                torch._foreach_copy_([copy_to[3][k] for k in fpk], [levels[3][k] for k in fpk])
             side.wait_stream(query)       # joining `side` joins the whole pre-pass
         if sm_limit is None:
             levels[-1]["sm_limit"] = 0   # nothing runs beside sa4's MLP

@@ -625,22 +625,30 @@ __global__ void __launch_bounds__(NT, 1)
   }
 }
 
+// `exclusive`: the launch asks for kExclusiveSmem bytes of shared memory it does not use, so that
+// no CTA of the step's persistent MLP kernels (167-198 KB each) can become co-resident on its SM.
+// An FPS iteration is a dependent chain of a few hundred cycles on 4 warps; sharing the SM's issue
+// slots with 16 busy warps stretched the 2048-point level from 0.36 to 0.91 ms inside the
+// pipelined step (profiles/r02/cupti_trace_before_exclusive_fps.txt).  The MLP grids are capped
+// to leave these SMs free (train_step.PipelinedTrainStep.default_caps).
+constexpr int kExclusiveSmem = 100 * 1024;
+
 template <int P, int NT>
 cudaError_t launch_small(const float *xyz, int B, int N, int npoint, int *idx, int L, int SB,
-                         cudaStream_t st) {
+                         bool exclusive, cudaStream_t st) {
   auto kern = fps_small_kernel<P, NT>;
-  constexpr int smem = 4 * P * NT * (int)sizeof(float);
-  if (smem > 48 * 1024) {
-    static bool attr_done[64] = {};
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
+  constexpr int own = 4 * P * NT * (int)sizeof(float);
+  constexpr int attr = own > kExclusiveSmem ? own : kExclusiveSmem;
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, attr);
     if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return e;
-      if (dev >= 0 && dev < 64) attr_done[dev] = true;
-    }
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
+  const int smem = exclusive ? attr : own;
   kern<<<B, NT, smem, st>>>(xyz, N, npoint, idx, L, SB);
   return cudaGetLastError();
 }
@@ -789,13 +797,14 @@ extern "C" int b2r_fps_ws(const float *xyz, int B, int N, int npoint, int *idx, 
   if (N <= b2r::kSingleCtaMaxN && !b2r::g_bucket_small) {
     b2r::Plan sp;
     if (!b2r::make_plan(B, N, 0, &sp)) return b2r_fps_ex(xyz, B, N, npoint, idx, 0, stream);
+    const bool excl = cluster_hint > 0;   // "runs beside other kernels" (b2r_fps_ex's hint)
     cudaError_t e;
-    if (N <= 128) e = b2r::launch_small<1, 128>(xyz, B, N, npoint, idx, sp.L, sp.SB, st);
-    else if (N <= 256) e = b2r::launch_small<2, 128>(xyz, B, N, npoint, idx, sp.L, sp.SB, st);
-    else if (N <= 512) e = b2r::launch_small<4, 128>(xyz, B, N, npoint, idx, sp.L, sp.SB, st);
-    else if (N <= 1024) e = b2r::launch_small<8, 128>(xyz, B, N, npoint, idx, sp.L, sp.SB, st);
-    else if (N <= 2048) e = b2r::launch_small<16, 128>(xyz, B, N, npoint, idx, sp.L, sp.SB, st);
-    else e = b2r::launch_small<16, 256>(xyz, B, N, npoint, idx, sp.L, sp.SB, st);
+    if (N <= 128) e = b2r::launch_small<1, 128>(xyz, B, N, npoint, idx, sp.L, sp.SB, excl, st);
+    else if (N <= 256) e = b2r::launch_small<2, 128>(xyz, B, N, npoint, idx, sp.L, sp.SB, excl, st);
+    else if (N <= 512) e = b2r::launch_small<4, 128>(xyz, B, N, npoint, idx, sp.L, sp.SB, excl, st);
+    else if (N <= 1024) e = b2r::launch_small<8, 128>(xyz, B, N, npoint, idx, sp.L, sp.SB, excl, st);
+    else if (N <= 2048) e = b2r::launch_small<16, 128>(xyz, B, N, npoint, idx, sp.L, sp.SB, excl, st);
+    else e = b2r::launch_small<16, 256>(xyz, B, N, npoint, idx, sp.L, sp.SB, excl, st);
     if (e != cudaSuccess) {
       b2r::set_error("b2r_fps_ws (single-CTA kernel, N=%d) launch failed: %s", N, cudaGetErrorString(e));
       return B2R_ERR_CUDA;

@@ -474,7 +474,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) sa_layer_fwd_kernel(const Laye
 // BatchNorm bookkeeping from the accumulated statistics (one thread per channel):
 //   scale = gamma / sqrt(var_biased + eps), shift = beta - mean * scale        (training)
 //   running_mean/var updated with `momentum` (unbiased variance), like nn.BatchNorm2d
-__global__ void bn_finalize_kernel(const double *__restrict__ stats, int Cch, double count,
+__global__ void bn_finalize_kernel(const double *__restrict__ stats, int Cch, double inv_count,
+                                   float unbias,
                                    const float *__restrict__ gamma, const float *__restrict__ beta,
                                    float eps, float momentum, float *__restrict__ running_mean,
                                    float *__restrict__ running_var, float *__restrict__ scale,
@@ -484,19 +485,23 @@ __global__ void bn_finalize_kernel(const double *__restrict__ stats, int Cch, do
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
   if (ch >= Cch) return;
-  const double mean = stats[ch] / count;
-  double var = stats[Cch + ch] / count - mean * mean;
+  // FP64 only where cancellation needs it (mean, E[z^2] - mean^2): two multiplies and one FMA.
+  // Divisions and the square root in double cost ~2 us of this single-CTA kernel on B200's few
+  // FP64 lanes, and it sits between two dependent layer kernels 23 times per step.
+  // (1/count and count/(count-1) come from the host.)
+  const double mean = stats[ch] * inv_count;
+  double var = fma(stats[Cch + ch], inv_count, -mean * mean);
   if (var < 0.0) var = 0.0;
-  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float invstd = 1.0f / sqrtf((float)var + eps);
   const float g = gamma ? gamma[ch] : 1.f, bta = beta ? beta[ch] : 0.f;
   scale[ch] = g * invstd;
   shift[ch] = bta - (float)mean * g * invstd;
   if (mean_out) mean_out[ch] = (float)mean;
   if (invstd_out) invstd_out[ch] = invstd;
   if (running_mean) {
-    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    const float unbiased = (float)var * unbias;
     running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mean;
-    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * unbiased;
   }
 }
 
@@ -720,7 +725,8 @@ extern "C" int b2r_bn_finalize(const double *stats, int C, double count, const f
                                float *invstd_out, long long *num_batches_tracked, void *stream) {
   B2R_REQUIRE(stats && scale && shift && C > 0 && count > 0, "b2r_bn_finalize: bad argument");
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      stats, C, count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift,
+      stats, C, 1.0 / count, count > 1.0 ? (float)(count / (count - 1.0)) : 1.0f, gamma, beta, eps,
+      momentum, running_mean, running_var, scale, shift,
       mean_out, invstd_out, num_batches_tracked);
   B2R_CHECK_LAUNCH();
   return B2R_OK;

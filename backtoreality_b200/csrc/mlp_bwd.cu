@@ -913,6 +913,7 @@ __global__ void pool_bwd_prep_kernel(const float *__restrict__ dout_cm,
 //    c = -gs*k1 - b*mean;       eval (running statistics): dz = gs*gr.
 // dgamma = (S2 - mean*S1)*invstd, dbeta = S1.  Also emits the epilogue-2 form (k1,k2,gs).
 __global__ void bn_bwd_finalize_kernel(const double *__restrict__ stats, int Cch, double count,
+                                       double inv_count,
                                        const float *__restrict__ gamma,
                                        const float *__restrict__ mean,
                                        const float *__restrict__ invstd, int training,
@@ -930,8 +931,8 @@ __global__ void bn_bwd_finalize_kernel(const double *__restrict__ stats, int Cch
   const double gs = g * is;
   double k1 = 0.0, k2 = 0.0;
   if (training) {
-    k1 = S1 / count;
-    k2 = sx / count;
+    k1 = S1 * inv_count;
+    k2 = sx * inv_count;
   }
   const double b = -gs * k2 * is;
   if (coef_a) coef_a[ch] = (float)gs;
@@ -1153,7 +1154,7 @@ extern "C" int b2r_bn_bwd_finalize_ex(const double *stats, int C, double count, 
                                       float *dbias_conv, void *stream) {
   B2R_REQUIRE(stats && mean && invstd && C > 0 && count > 0, "b2r_bn_bwd_finalize: bad argument");
   bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      stats, C, count, gamma, mean, invstd, training, coef_a, coef_b, coef_c, k1, k2, gs, dgamma,
+      stats, C, count, 1.0 / count, gamma, mean, invstd, training, coef_a, coef_b, coef_c, k1, k2, gs, dgamma,
       dbeta, dbias_conv);
   B2R_CHECK_LAUNCH();
   return B2R_OK;

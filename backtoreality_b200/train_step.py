@@ -243,6 +243,104 @@ class PipelinedTrainStep:
         return self.static_loss
 
 
+class PipelinedTrainStepPP(PipelinedTrainStep):
+    """PipelinedTrainStep without the buffer rotation on the critical path ("ping-pong").
+
+    The base class ends every step with a multi-tensor copy of the fresh geometry (and the next
+    batch) into the static buffers the captured step reads: ~45 small copy kernels (~70 us) after
+    the optimizer, where nothing can overlap them.  Here there are TWO sets of static buffers and
+    TWO captured graphs: graph p trains on set p while the pre-pass of the next batch fills set
+    1-p -- level by level, on the side streams, as soon as each level exists -- and the next call
+    replays graph 1-p.  Same contract as the base class: call i submits batch i+1 and returns the
+    loss of batch i; every call runs one complete pre-pass and one complete step."""
+
+    def prime(self, batch):
+        self.parity = 0
+        if getattr(self, "X", None) is None:
+            self.X = [batch.clone(), batch.clone()]
+            self.G = [None, None]
+        self.X[0].copy_(batch)
+        xyz = self._xyz(self.X[0])
+        levels = self.backbone.geometry_prepass(xyz, side=self.side)
+        torch.cuda.current_stream().wait_stream(self.side)
+        fresh = [{k: lv[k] for k in self._keys(lv)} for lv in levels]
+        if self.G[0] is None:
+            self.G = [[{k: v.clone() for k, v in lv.items()} for lv in fresh] for _ in range(2)]
+        else:
+            for dst, src in zip(self.G[0], fresh):
+                for k in dst:
+                    dst[k].copy_(src[k])
+        self._alias()
+
+    def _alias(self):   # the attributes the base class (and its tests) expose
+        self.cur, self.next = self.X[self.parity], self.X[1 - self.parity]
+        self.geo_cur = self.G[self.parity]
+
+    def _pipelined_pp(self, p):
+        main = torch.cuda.current_stream()
+        xyz_next = self._xyz(self.X[1 - p])   # referenced until the side stream has been joined
+        box = {}
+
+        def launch_prepass():
+            box["nxt"] = self.backbone.geometry_prepass(xyz_next, fps_cluster=self.fps_cluster,
+                                                        sm_limit=0, side=self.side, copy_to=self.G[1 - p])
+
+        levels = self._levels(self.G[p])
+        if self.start_after_level is None:
+            launch_prepass()
+        else:
+            levels[self.start_after_level]["after_forward"] = launch_prepass
+        loss = self.step_fn(self.X[p], levels)
+        if "nxt" not in box:
+            launch_prepass()
+        main.wait_stream(self.side)
+        del xyz_next
+        return loss
+
+    def _pipelined(self):   # one eager step on the current parity (warm-up)
+        loss = self._pipelined_pp(self.parity)
+        self.parity ^= 1
+        self._alias()
+        return loss
+
+    def recapture(self):
+        from . import _ext
+        warm = torch.cuda.Stream()
+        warm.wait_stream(torch.cuda.current_stream())
+        saved = _save_state(getattr(self, "snapshot", None))
+        self.X[1].copy_(self.X[0])
+        with torch.cuda.stream(warm):
+            for _ in range((self.warmup + 1) // 2 * 2):     # an even count: parity returns to 0
+                self._pipelined()
+                if self.after_warmup_step is not None:
+                    self.after_warmup_step()
+        torch.cuda.current_stream().wait_stream(warm)
+        torch.cuda.synchronize()
+        _restore_state(getattr(self, "snapshot", None), saved)
+        saved_ops = set(_ext.TIME_OPS)
+        _ext.TIME_OPS.clear()          # timing events cannot be recorded inside a capture
+        self.graphs, self.losses = [None, None], [None, None]
+        try:
+            for p in (0, 1):
+                l0 = _ext.LAUNCHES
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode=CAPTURE_ERROR_MODE):
+                    loss = self._pipelined_pp(p)
+                self.graphs[p], self.losses[p] = g, loss
+                self.launches_per_step = _ext.LAUNCHES - l0
+            self.graph, self.static_loss = self.graphs[0], self.losses[0]
+        finally:
+            _ext.TIME_OPS.update(saved_ops)
+
+    def __call__(self, next_batch, non_blocking=True):
+        p = self.parity
+        self.X[1 - p].copy_(next_batch, non_blocking=non_blocking)
+        self.graphs[p].replay()
+        self.parity ^= 1
+        self._alias()
+        return self.losses[p]
+
+
 class PipelinedTrainStep2(PipelinedTrainStep):
     """The pipelined step, two batches deep.  SA1's geometry (FPS of the whole 40k-point scene:
     2047 dependent iterations, ~2 ms on narrow clusters) and the later levels' (FPS 2048 -> 1024

@@ -125,6 +125,9 @@ def workload_config(a, world):
         "scene_kind": "room (ScanNet-shaped surfaces, 20% duplicate points), seeds 1000+i",
         "loss": LOSSES[a.workload],
         "parallelism": "dp%d (scenes sharded, flat-gradient NCCL all-reduce)" % world,
+        "optimizer": ("Adam, lr 1e-3, one streaming kernel over the flat parameter buffer (flat_adam.FlatAdam)"
+                      if os.environ.get("B2R_TORCH_ADAM", "0") in ("0", "")
+                      else "torch.optim.Adam(fused=True, capturable=True), lr 1e-3"),
         "l2": "256 MB buffer written between steps (flush) + 4 rotating input batches",
         "e2e_input": "pinned host -> device on a copy stream, one step ahead (train_step.HostPrefetcher)",
         "launch": ("whole step (fwd+bwd+Adam) captured in one CUDA graph, replayed per batch" if world == 1
@@ -464,8 +467,16 @@ def run_b2r(a):
         backbone = net.backbone_net
     params = [p for p in net.parameters()]
     # N > 1: gradients are packed into one flat buffer for a single all-reduce per step
-    bucket = dist_utils.FlatGradBucket(params, as_views=False) if world > 1 else None
-    opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
+    # optimizer: Adam over one flat buffer (flat_adam.FlatAdam: pack + [all-reduce] + ONE kernel);
+    # B2R_TORCH_ADAM=1 keeps torch.optim.Adam(fused) + FlatGradBucket (round 1's arrangement)
+    use_flat_adam = os.environ.get("B2R_TORCH_ADAM", "0") in ("0", "")
+    if use_flat_adam:
+        from backtoreality_b200.flat_adam import FlatAdam
+        bucket = None
+        opt = FlatAdam(params, lr=1e-3)
+    else:
+        bucket = dist_utils.FlatGradBucket(params, as_views=False) if world > 1 else None
+        opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
     live = {"grads": None}   # the gradient tensors the last backward (or the graph) produced
 
     pool_n = 4
@@ -482,6 +493,9 @@ def run_b2r(a):
         return loss
 
     def finish():
+        if use_flat_adam:         # pack, (N > 1) the step's only collective, one Adam kernel
+            opt.step(live["grads"])
+            return
         if bucket is not None:    # the step's only collective: one NCCL sum of the flat gradient
             bucket.reduce_from(live["grads"])
         opt.step()
@@ -549,7 +563,11 @@ def run_b2r(a):
     for attempt in ((0, 1) if not a.no_graph else ()):
         try:
             from backtoreality_b200.train_step import (CapturedTrainStep, PipelinedTrainStep,
-                                                       PipelinedTrainStep2)
+                                                       PipelinedTrainStep2, PipelinedTrainStepPP)
+            # B2R_PINGPONG=1: two graphs over two static buffer sets, no rotation copies after the
+            # optimizer (measured: 3.50 vs 3.48 ms -- the copies were not on the critical path)
+            Pipe = PipelinedTrainStepPP if os.environ.get("B2R_PINGPONG", "0") not in ("0", "") \
+                else PipelinedTrainStep
             stage("capturing the step into a CUDA graph")
             if pipelined:
                 # the vote-aggregation block has no pre-pass level of its own: give its kernels the
@@ -568,7 +586,7 @@ def run_b2r(a):
                                                   after_warmup_step=None if capture_all else finish,
                                                   start_after_level=start)
                 else:
-                    graphed = PipelinedTrainStep(backbone, step if capture_all else fwd_bwd,
+                    graphed = Pipe(backbone, step if capture_all else fwd_bwd,
                                                  resident[0], fps_cluster=a.fps_cluster, sm_caps=caps,
                                                  after_warmup_step=None if capture_all else finish,
                                                  start_after_level=start)

@@ -480,6 +480,18 @@ B2R_API int b2r_vote_tail_bwd(const float *g_out, const float *g_vote_xyz, const
 B2R_API int b2r_nn_argmin(const float *pc1, const float *pc2, int B, int N, int M, int C, int mode,
                           float delta, long long *idx1, long long *idx2, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Adam over one flat fp32 buffer (csrc/adam.cu) -- the optimizer step at the end of the training
+ * step (reference: optim.Adam over net.parameters(), train_Votenet_FSB.py:176-181) as ONE streaming
+ * kernel instead of three multi-tensor launches.  params / grads / exp_avg / exp_avg_sq: n floats
+ * each, 16-byte aligned; state: b2r_adam_state_bytes() bytes of zero-initialised device memory (the
+ * step counter, advanced on the device: graph-replayable).  grads are multiplied by grad_scale
+ * first (1/world_size after a sum all-reduce).  torch.optim.Adam arithmetic (amsgrad=False). */
+B2R_API int b2r_adam_state_bytes(void);
+B2R_API int b2r_adam_flat_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
+                               long long n, void *state, float lr, float beta1, float beta2, float eps,
+                               float weight_decay, float grad_scale, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

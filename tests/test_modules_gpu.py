@@ -293,8 +293,54 @@ def test_captured_train_step_matches_eager(cuda):
     assert int(net_s.backbone_net.sa1.mlp_module.layer0.bn.bn.num_batches_tracked) == 1
 
 
-@pytest.mark.parametrize("start_after_level", [None, 1, 3])
-def test_pipelined_train_step_matches_sequential(cuda, start_after_level):
+def test_pipelined_train_step_at_the_benched_configuration(cuda):
+    """bench.py's default arm exactly (BASELINE.json configs[1]): 8 scenes x 40000 points, the
+    22-class VoteNet head with 256 proposals, PipelinedTrainStep with 4-CTA FPS clusters, the
+    pre-pass started after SA level 2's forward and the default grid caps.  With lr = 0 call i must
+    return the eager loss of batch i, and the rotated geometry must equal a fresh pre-pass."""
+    from backtoreality_b200.train_step import PipelinedTrainStep
+    from backtoreality_b200.votenet import VoteNet
+
+    def make():
+        torch.manual_seed(0)
+        net = VoteNet(22, 1, 22, np.ones((22, 3), np.float32), input_feature_dim=1, num_proposal=256,
+                      vote_factor=1, sampling="vote_fps").to(cuda).train()
+        opt = torch.optim.SGD(net.parameters(), lr=0.0)
+
+        def step(pc, geometry=None):
+            for p in net.parameters():
+                p.grad = None
+            ep = net({"point_clouds": pc, "geometry": geometry})
+            loss = (ep["proposal_scores_raw"] ** 2).mean() + ((ep["vote_xyz"] - ep["seed_xyz"]) ** 2).mean()
+            loss.backward()
+            opt.step()
+            return loss.detach()
+        return net, step
+
+    batches = [torch.from_numpy(scenes.batch(1000 + 8 * i, 8, 40000, C=1, kind="room", dup=0.2)).to(cuda)
+               for i in range(3)]
+    net_e, step_e = make()
+    eager = [float(step_e(b)) for b in batches]
+    net_p, step_p = make()
+    caps, head_cap = PipelinedTrainStep.default_caps(8, 4, 1)
+    net_p.pnet.vote_aggregation.sm_limit = head_cap
+    from backtoreality_b200.train_step import PipelinedTrainStepPP
+    pipe = PipelinedTrainStepPP(net_p.backbone_net, step_p, batches[0], warmup=2, fps_cluster=4,
+                                sm_caps=caps, start_after_level=1)
+    got = [float(pipe(batches[(i + 1) % 3])) for i in range(3)]
+    for g, e in zip(got, eager):
+        assert abs(g - e) <= 2e-5 * abs(e), (got, eager)
+    torch.cuda.synchronize()
+    fresh = net_p.backbone_net.geometry_prepass(batches[0][..., :3].contiguous())
+    torch.cuda.synchronize()
+    for lv_p, lv_f in zip(pipe.geo_cur, fresh):
+        for k in ("inds", "new_xyz", "idx"):
+            assert torch.equal(lv_p[k], lv_f[k]), k
+
+
+@pytest.mark.parametrize("start_after_level,pingpong", [(None, False), (1, False), (3, False),
+                                                        (1, True), (None, True)])
+def test_pipelined_train_step_matches_sequential(cuda, start_after_level, pingpong):
     """train_step.PipelinedTrainStep (geometry pre-pass of batch i+1 beside the step of batch i,
     started with the step or from the hook after an SA level's forward, narrow FPS clusters,
     capped MLP grids) must train on the same batches in the same order as
@@ -302,8 +348,9 @@ def test_pipelined_train_step_matches_sequential(cuda, start_after_level):
     the summation order of the BatchNorm statistics under a different persistent grid), the
     rotated geometry buffers hold exactly the indices a fresh pre-pass computes, and the
     gradients agree within the atomics' run-to-run noise."""
-    from backtoreality_b200.train_step import PipelinedTrainStep
+    from backtoreality_b200.train_step import PipelinedTrainStep, PipelinedTrainStepPP
     from backtoreality_b200.votenet import VoteNet
+    Pipe = PipelinedTrainStepPP if pingpong else PipelinedTrainStep   # two graphs, no rotation copies
 
     def make():
         torch.manual_seed(5)
@@ -327,8 +374,8 @@ def test_pipelined_train_step_matches_sequential(cuda, start_after_level):
     eager = [float(step_e(b)) for b in batches]
     net_p, step_p = make()
     net_p.pnet.vote_aggregation.sm_limit = (100, 120)
-    pipe = PipelinedTrainStep(net_p.backbone_net, step_p, batches[0], warmup=2, fps_cluster=3,
-                              start_after_level=start_after_level)
+    pipe = Pipe(net_p.backbone_net, step_p, batches[0], warmup=2, fps_cluster=3,
+                start_after_level=start_after_level)
     assert pipe.launches_per_step > 50
     got = [float(pipe(batches[(i + 1) % 4])) for i in range(4)]   # call i trains on batch i
     assert len(set(got)) == 4
@@ -671,3 +718,55 @@ def test_vote_heads_golden(cuda, train):
         assert float(pnet.conv2.bias.grad.abs().max()) < 1e-3      # bias before a training-mode BN
     else:
         assert rel_l2(pnet.conv2.bias.grad.cpu().numpy(), g["g_pnet_c2_b"]) < 0.25
+
+
+def test_flat_adam_matches_torch_adam(cuda):
+    """flat_adam.FlatAdam (one kernel over the flat parameter buffer, device-side step counter)
+    against torch.optim.Adam on the same gradients, with and without weight decay, and replayed
+    from a CUDA graph."""
+    from backtoreality_b200.flat_adam import FlatAdam
+    for wd in (0.0, 0.01):
+        torch.manual_seed(3)
+        shapes = [(64, 4, 1, 1), (64,), (128, 131, 1, 1), (7,), (3, 5)]
+        ref = [torch.nn.Parameter(torch.randn(s, device=cuda)) for s in shapes]
+        ours = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+        o_ref = torch.optim.Adam(ref, lr=1e-2, weight_decay=wd)
+        o_b2r = FlatAdam(ours, lr=1e-2, weight_decay=wd)
+        for it in range(6):
+            grads = [torch.randn_like(p) * (it + 1) for p in ref]
+            for p, g in zip(ref, grads):
+                p.grad = g.clone()
+            o_ref.step()
+            o_b2r.step(grads)
+            for a, b in zip(ref, ours):
+                torch.testing.assert_close(b, a, rtol=2e-5, atol=2e-6)
+        # parameters are views of the flat buffer and their version counters moved
+        assert all(p.data_ptr() >= o_b2r.flat_p.data_ptr() for p in ours)
+        v0 = ours[0]._version
+        o_b2r.step([torch.zeros_like(p) for p in ours])
+        assert ours[0]._version > v0
+    # graph replay: the step counter advances on the device
+    p_g = [torch.nn.Parameter(torch.ones(1000, device=cuda))]
+    p_e = [torch.nn.Parameter(torch.ones(1000, device=cuda))]
+    og, oe = FlatAdam(p_g, lr=1e-2), torch.optim.Adam(p_e, lr=1e-2)
+    gstat = torch.full((1000,), 0.5, device=cuda)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        og.step([gstat])
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        og.step([gstat])
+    for _ in range(4):
+        g.replay()
+    for _ in range(6):      # 1 eager + 1 capture-time (not executed) ... count the executed ones
+        p_e[0].grad = gstat.clone()
+        oe.step()
+    torch.cuda.synchronize()
+    # warm-up step + 4 replays = 5 executed steps (the capture itself does not execute)
+    p_chk = [torch.nn.Parameter(torch.ones(1000, device=cuda))]
+    oc = torch.optim.Adam(p_chk, lr=1e-2)
+    for _ in range(5):
+        p_chk[0].grad = gstat.clone()
+        oc.step()
+    torch.testing.assert_close(p_g[0], p_chk[0], rtol=2e-5, atol=2e-6)
