@@ -74,6 +74,10 @@ class RefStack:
                                            aliases=("pointnet2_modules",))
             self.backbone_module = _load(tag + "backbone_module",
                                          os.path.join(root, "models", "backbone_module.py"))
+            if flavour == "groupfree3d":
+                # query sampling between backbone and decoder; the file does
+                # sys.path.append + `import pointnet2_utils`, served by the alias above
+                self.gf_modules = _load(tag + "gf_modules", os.path.join(root, "models", "modules.py"))
             if flavour == "votenet":
                 self.voting_module = _load(tag + "voting_module",
                                            os.path.join(root, "models", "voting_module.py"))

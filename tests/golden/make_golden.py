@@ -219,6 +219,42 @@ def vote_heads_case(seed, train):
     return out
 
 
+def gf3d_query_case(seed):
+    """GroupFree3D query sampling (G/models/modules.py:16-100, detector.py:150-175): the KPS
+    objectness head, both sampling modules and the learned position embedding, train-mode BN."""
+    rg = ref_python.RefStack("groupfree3d")
+    m = rg.gf_modules
+    torch.manual_seed(seed)
+    cls_head = m.PointsObjClsModule(288)
+    pos = m.PositionEmbeddingLearned(3, 288)
+    pos6 = m.PositionEmbeddingLearned(6, 288)
+    fps, gs = m.FPSModule(64), m.GeneralSamplingModule()
+    for mod in list(cls_head.modules()) + list(pos.modules()) + list(pos6.modules()):
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.momentum = 0.2
+    g = torch.Generator().manual_seed(seed + 1)
+    xyz = torch.rand(2, 256, 3, generator=g) * 3.0
+    feat = torch.randn(2, 288, 256, generator=g).requires_grad_(True)
+    logits = cls_head(feat)
+    kps_inds = torch.topk(torch.sigmoid(logits).squeeze(1), 64)[1].int()
+    k_xyz, k_feat, _ = gs(xyz, feat, kps_inds)
+    f_xyz, f_feat, f_inds = fps(xyz, feat)
+    emb = pos(f_xyz)
+    emb6 = pos6(torch.cat([f_xyz, f_xyz * 0.5 + 0.1], -1))
+    loss = ((logits * pattern_like(logits)).sum() + (k_feat * 0.3).sum() + (f_feat * pattern_like(f_feat)).sum() +
+            (emb * pattern_like(emb)).sum() + (emb6 * 0.01).sum())
+    loss.backward()
+    return {"seed": seed, "wsum": weight_checksum(cls_head) + weight_checksum(pos) + weight_checksum(pos6),
+            "logits": logits.detach().numpy(), "kps_inds": kps_inds.numpy(), "k_xyz": k_xyz.detach().numpy(),
+            "k_feat": sub(k_feat), "f_inds": f_inds.numpy(), "f_xyz": f_xyz.detach().numpy(),
+            "f_feat": sub(f_feat), "emb": sub(emb), "emb6": sub(emb6),
+            "g_feat": sub(feat.grad), "g_cls_c1": sub(cls_head.conv1.weight.grad),
+            "g_cls_c3_b": cls_head.conv3.bias.grad.numpy().copy(),
+            "g_pos_c0": pos.position_embedding_head[0].weight.grad.numpy().copy(),
+            "g_pos_c3": sub(pos.position_embedding_head[3].weight.grad),
+            "rm_cls_bn1": cls_head.bn1.running_mean.numpy().copy()}
+
+
 def main():
     if not ref_python.available():
         raise SystemExit("reference tree not found; fixtures can only be generated in the "
@@ -235,6 +271,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "backbone_jitter.npz"), **jitter_backbone_case(2468))
     np.savez_compressed(os.path.join(HERE, "vote_heads_train.npz"), **vote_heads_case(31, True))
     np.savez_compressed(os.path.join(HERE, "vote_heads_eval.npz"), **vote_heads_case(31, False))
+    np.savez_compressed(os.path.join(HERE, "gf3d_query_sampling.npz"), **gf3d_query_case(63))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -770,3 +770,56 @@ def test_flat_adam_matches_torch_adam(cuda):
         p_chk[0].grad = gstat.clone()
         oc.step()
     torch.testing.assert_close(p_g[0], p_chk[0], rtol=2e-5, atol=2e-6)
+
+
+def test_gf3d_query_sampling_golden(cuda):
+    """GroupFree3D query sampling against fixtures from the reference's
+    G/models/modules.py:16-100: KPS objectness head and learned position embedding on the dense
+    tcgen05 path (TF32), FPS / general sampling on libb2r's FPS + gather, gradients included."""
+    from backtoreality_b200 import gf3d_modules as m
+    g = golden("gf3d_query_sampling.npz")
+    seed = int(g["seed"])
+    torch.manual_seed(seed)
+    cls_head = m.PointsObjClsModule(288)
+    pos = m.PositionEmbeddingLearned(3, 288)
+    pos6 = m.PositionEmbeddingLearned(6, 288)
+    fps, gs = m.FPSModule(64), m.GeneralSamplingModule()
+    wsum = weight_checksum(cls_head) + weight_checksum(pos) + weight_checksum(pos6)
+    assert abs(wsum - float(g["wsum"])) < 1e-6 * float(g["wsum"])    # same init order as the reference
+    for mod in list(cls_head.modules()) + list(pos.modules()) + list(pos6.modules()):
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.momentum = 0.2
+    cls_head, pos, pos6 = cls_head.to(cuda).train(), pos.to(cuda).train(), pos6.to(cuda).train()
+    gen = torch.Generator().manual_seed(seed + 1)
+    xyz = (torch.rand(2, 256, 3, generator=gen) * 3.0).to(cuda)
+    feat = torch.randn(2, 288, 256, generator=gen).to(cuda).requires_grad_(True)
+    logits = cls_head(feat)
+    assert rel_l2(logits.detach().cpu().numpy(), g["logits"]) < 1e-2
+    # the top-k of near-equal TF32 scores may order differently: sample with the reference's indices
+    kps_inds = torch.from_numpy(g["kps_inds"]).to(cuda)
+    k_xyz, k_feat, _ = gs(xyz, feat, kps_inds)
+    f_xyz, f_feat, f_inds = fps(xyz, feat)
+    assert np.array_equal(f_inds.cpu().numpy(), g["f_inds"])
+    assert np.array_equal(k_xyz.cpu().numpy(), g["k_xyz"]) and np.array_equal(f_xyz.cpu().numpy(), g["f_xyz"])
+    assert np.array_equal(sub(k_feat), g["k_feat"]) and np.array_equal(sub(f_feat), g["f_feat"])
+    emb = pos(f_xyz)
+    emb6 = pos6(torch.cat([f_xyz, f_xyz * 0.5 + 0.1], -1))
+    assert rel_l2(sub(emb), g["emb"]) < 1e-2 and rel_l2(sub(emb6), g["emb6"]) < 1e-2
+    loss = ((logits * pattern_like(logits)).sum() + (k_feat * 0.3).sum() + (f_feat * pattern_like(f_feat)).sum() +
+            (emb * pattern_like(emb)).sum() + (emb6 * 0.01).sum())
+    loss.backward()
+    assert rel_l2(sub(feat.grad), g["g_feat"]) < 3e-2
+    assert rel_l2(sub(cls_head.conv1.weight.grad), g["g_cls_c1"]) < 5e-2
+    assert rel_l2(cls_head.conv3.bias.grad.cpu().numpy(), g["g_cls_c3_b"]) < 1e-3
+    assert rel_l2(pos.position_embedding_head[0].weight.grad.cpu().numpy(), g["g_pos_c0"]) < 5e-2
+    assert rel_l2(sub(pos.position_embedding_head[3].weight.grad), g["g_pos_c3"]) < 5e-2
+    assert rel_l2(cls_head.bn1.running_mean.cpu().numpy(), g["rm_cls_bn1"]) < 1e-2
+    # detector.py:150-175 restated: both branches fill the reference's end_points keys
+    ep = {"fp2_xyz": xyz, "fp2_features": feat.detach(), "fp2_inds": torch.arange(256, device=cuda).repeat(2, 1)}
+    cx, cf = m.sample_queries(ep, "fps", 64, fps_module=fps)
+    assert torch.equal(ep["query_points_sample_inds"], f_inds) and cx.shape == (2, 64, 3) and cf.shape == (2, 288, 64)
+    cx, cf = m.sample_queries(ep, "kps", 64, points_obj_cls=cls_head, gsample_module=gs)
+    assert ep["seeds_obj_cls_logits"].shape == (2, 1, 256) and ep["query_points_xyz"].shape == (2, 64, 3)
+    proj = torch.nn.Conv1d(288, 288, 1).to(cuda)
+    want = proj(feat.detach())
+    assert rel_l2(m.project_pm(proj, feat.detach()).detach().cpu().numpy(), want.detach().cpu().numpy()) < 5e-3

@@ -91,3 +91,27 @@ def test_nn_distance_oracle_equals_reference_module_on_cpu():
     assert torch.equal(nd.huber_loss(e, 0.4), ref.huber_loss(e, 0.4))
     with pytest.raises(RuntimeError, match="CPU not supported"):
         nd.nn_distance(p1, p2)
+
+
+def test_gf3d_query_modules_state_dict_matches_reference():
+    """backtoreality_b200.gf3d_modules mirrors G/models/modules.py:16-100: same state-dict keys and
+    shapes, and (on CPU, where the modules run the reference's own torch formulation) the same
+    outputs for the same weights."""
+    if not ref_python.available():
+        pytest.skip("reference tree not present")
+    from backtoreality_b200 import gf3d_modules as ours
+    rg = ref_python.RefStack("groupfree3d")
+    ref = rg.gf_modules
+    for name, args in (("PointsObjClsModule", (288,)), ("PositionEmbeddingLearned", (3, 288)),
+                       ("PositionEmbeddingLearned", (6, 64))):
+        torch.manual_seed(0)
+        a = getattr(ref, name)(*args)
+        torch.manual_seed(0)
+        b = getattr(ours, name)(*args)
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb)
+        for k in sa:
+            assert sa[k].shape == sb[k].shape and torch.equal(sa[k], sb[k]), k
+        a.eval(); b.eval()
+        x = torch.randn(2, 288, 50) if name == "PointsObjClsModule" else torch.randn(2, 50, args[0])
+        assert torch.allclose(a(x), b(x), atol=1e-6)
