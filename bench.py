@@ -758,7 +758,13 @@ def run_b2r(a):
             upd //= 2                                           # per launch: one of the two forwards
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6
-        out["fps"] = {"kernel": "fps_cluster_kernel", "bound": "serial fp32 chain (not hbm/tensor)",
+        out["fps"] = {"kernel": "fps_bucket_kernel (SA1: Morton-sorted buckets + bounding-box skip test, "
+                                "indices bit-identical) + fps_small_kernel (later levels), csrc/fps_bucket.cu; "
+                                "timed standalone at the lowest-latency cluster width (inside the pipelined "
+                                "step SA1 runs on %d-CTA clusters beside the step)" % a.fps_cluster,
+                      "bound": "serial fp32 chain (not hbm/tensor)",
+                      "note": "algorithmic point-updates (every point, every iteration) / time: the skip test "
+                              "executes far fewer",
                       "launches_per_step": per_step, "ms_per_step_all_levels": ms_step,
                       "sa1_ms_per_batch": sa1_ms, "sa1_ms_per_scene": sa1_ms / a.batch,
                       "sa1_point_updates_per_s": upd / (sa1_ms * 1e-3),
@@ -784,6 +790,27 @@ def run_b2r(a):
                     log("leg %s printed no result: %s" % (leg, r.stderr[-400:]))
             except Exception as e:
                 log("leg %s failed: %s: %s" % (leg, type(e).__name__, e))
+        # the precision trade of the fused SA backward as a measurement: the SAME step with the SA
+        # blocks and the FP / head MLPs on the unfused path (libb2r movers + cuDNN, TF32 forward
+        # AND backward -- the reference's own arithmetic), same graph capture and pipelining
+        log("timing leg unfused_tf32 in a subprocess ...")
+        try:
+            cmd = [sys.executable, os.path.abspath(__file__), "--workload", a.workload, "--batch", str(a.batch),
+                   "--npoints", str(a.npoints), "--steps", "10", "--warmup", "3", "--no-cpu-baseline"]
+            env = dict(os.environ, B2R_FUSED="0", B2R_DENSE="0")
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if line:
+                res = json.loads(line[-1])
+                out["unfused_tf32_arm"] = {
+                    "value": res["value"], "unit": UNIT, "ms_per_step": res["ms_per_step"],
+                    "what": "B2R_FUSED=0 B2R_DENSE=0: SA blocks and FP / head MLPs through libb2r's "
+                            "unfused kernels + cuDNN (TF32 operands forward and backward, FP32 "
+                            "accumulate); the product arm's fused SA backward uses BF16 operands"}
+            else:
+                log("leg unfused_tf32 printed no result: %s" % r.stderr[-400:])
+        except Exception as e:
+            log("leg unfused_tf32 failed: %s: %s" % (type(e).__name__, e))
     emit(out)
     if world > 1:
         # Leave without tearing NCCL down: destroying a process group whose collectives live

@@ -1,5 +1,5 @@
 """ncu launch list (scripts/gpu_launch_list.sh -> gpurun_out/launches.csv) -> per-kernel shares of
-ONE eager step:  python scripts/launch_summary.py gpurun_out/launches.csv > profiles/r01/launches_step_summary.txt
+ONE eager step:  python scripts/launch_summary.py gpurun_out/launches.csv > profiles/r02/launches_step_summary.txt
 The capture window holds about 3 steps; a step is delimited by SA1's FPS launch (the widest
 fps_cluster_kernel instantiation)."""
 import csv
@@ -16,7 +16,8 @@ for r in rows[1:]:
         name = re.sub(r"\(.*", "", r[ix["Kernel Name"]]).replace("void ", "")
         name = re.sub(r"\(anonymous namespace\)::|<?unnamed>::", "", name)
         launches.append((name, v))
-marks = [i for i, (n, _) in enumerate(launches) if n.startswith("b2r::fps_cluster_kernel")]
+marks = [i for i, (n, _) in enumerate(launches)
+         if n.startswith("b2r::fps_cluster_kernel") or n.startswith("b2r::fps_bucket_kernel")]
 # SA1's FPS is the longest FPS launch of every step
 big = max(launches[i][1] for i in marks)
 starts = [i for i in marks if launches[i][1] > 0.7 * big]

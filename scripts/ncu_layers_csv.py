@@ -2,7 +2,7 @@
 a small text table on stdout + profiles/roofline_traffic.json (mean DRAM bytes per launch of the
 b2r_sa_layer_fwd / b2r_sa_layer_bwd entry points; the thin first-layer kernels of
 csrc/mlp_thin.cu are launches of those entry points too):
-    python scripts/ncu_layers_csv.py gpurun_out/ncu_all_layers.csv > profiles/r01/ncu_sa_layers_all_blocks.txt
+    python scripts/ncu_layers_csv.py gpurun_out/ncu_all_layers.csv > profiles/r02/ncu_sa_layers_all_blocks.txt
 """
 import csv
 import json
@@ -43,5 +43,5 @@ for op, v in traffic.items():
         out[op] = {"dram_bytes_per_launch": sum(v) / len(v), "launches": len(v),
                    "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the %d launches of "
                              "this entry point in one step (scripts/gpu_ncu_all.sh, "
-                             "profiles/r01/ncu_sa_layers_all_blocks.txt)" % len(v)}
+                             "profiles/r02/ncu_sa_layers_all_blocks.txt)" % len(v)}
 json.dump(out, open(os.path.join(ROOT, "profiles", "roofline_traffic.json"), "w"), indent=1)
