@@ -77,7 +77,9 @@ class RefStack:
             if flavour == "groupfree3d":
                 # query sampling between backbone and decoder; the file does
                 # sys.path.append + `import pointnet2_utils`, served by the alias above
-                self.gf_modules = _load(tag + "gf_modules", os.path.join(root, "models", "modules.py"))
+                # (absent from the vendored copy under baseline/_ref the GPU tests use)
+                gfm = os.path.join(root, "models", "modules.py")
+                self.gf_modules = _load(tag + "gf_modules", gfm) if os.path.isfile(gfm) else None
             if flavour == "votenet":
                 self.voting_module = _load(tag + "voting_module",
                                            os.path.join(root, "models", "voting_module.py"))
