@@ -3,7 +3,7 @@
 //
 // Replaces furthest_point_sampling_kernel (reference _ext_src/src/sampling_gpu.cu:74-178) like
 // fps.cu does, with the same bit-exact result, but attacks the two things
-// that bound fps.cu's dependent iteration (profiles/r02/fps_*.txt):
+// that bound fps.cu's dependent iteration (profiles/r02/fps_phase_probe.txt, lat_probe_sm100a.txt):
 //
 //   * work: after j samples a new sample can only lower the running min-distance of points closer
 //     to it than their current value, i.e. of a ~1/j fraction of the scene.  Points are therefore
@@ -792,8 +792,8 @@ extern "C" int b2r_fps_ws(const float *xyz, int B, int N, int npoint, int *idx, 
     B2R_CUDA(cudaMemsetAsync(idx, 0, sizeof(int) * (size_t)B * npoint, st));
     return B2R_OK;
   }
-  // one CTA holds the scene: no DSMEM hop to shorten and (16 buckets) little to skip -- fps.cu's
-  // warp -> CTA reduction is the shorter chain there (scripts/fps_sweep.py, profiles/r02)
+  // one CTA holds the scene: no DSMEM hop to shorten and little to skip -- the few-fat-warps
+  // kernel is the shortest chain there (scripts/fps_sweep.py, profiles/r02/fps_table_protocol.txt)
   if (N <= b2r::kSingleCtaMaxN && !b2r::g_bucket_small) {
     b2r::Plan sp;
     if (!b2r::make_plan(B, N, 0, &sp)) return b2r_fps_ex(xyz, B, N, npoint, idx, 0, stream);
