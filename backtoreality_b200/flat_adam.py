@@ -49,6 +49,31 @@ class FlatAdam:
                 p.data = view                       # the module's Parameter now lives in the flat buffer
                 self.g_views.append(self.flat_g[off:off + p.numel()].view_as(p))
 
+    # ---- overlapping the gradient all-reduce with the rest of backward (world > 1) --------------
+    def set_late(self, n_late):
+        """The first `n_late` parameters are the ones whose gradients arrive LAST in backward (the
+        first layers of the network: backward runs the forward order in reverse).  `reduce_early`
+        may then be called from a backward hook placed where everything after them is done."""
+        self.n_late = int(n_late)
+        self.off_late = self.offsets[self.n_late] if self.n_late < len(self.params) else self.numel
+        self.comm = torch.cuda.Stream(device=self.flat_p.device)
+        self._early_done = False
+
+    def reduce_early(self):
+        """pack + all-reduce the gradients of params[n_late:] on a side stream, while backward goes
+        on with the first layers.  Call when those gradients exist (tensor hook on an activation
+        between the two parameter groups).  No-op without a process group."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        early = self.params[self.n_late:]
+        if any(p.grad is None for p in early):
+            return                      # not all there (e.g. a frozen branch): step() does everything
+        torch._foreach_copy_(self.g_views[self.n_late:], [p.grad for p in early])
+        self.comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(self.flat_g[self.off_late:])
+        self._early_done = True
+
     def zero_grad(self, set_to_none=True):
         for p in self.params:
             p.grad = None
@@ -65,10 +90,25 @@ class FlatAdam:
 
     def step(self, grads=None, allreduce=True):
         """pack -> (world > 1: one NCCL sum all-reduce of the flat gradient) -> one Adam kernel"""
-        self.pack(grads)
         scale = 1.0
-        if allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat_g)
+        multi = allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if multi and getattr(self, "_early_done", False):
+            # params[n_late:] are packed and their all-reduce is in flight on the side stream
+            self._early_done = False
+            if grads is None:
+                grads = [p.grad for p in self.params]
+            late = [(v, g) for v, g in zip(self.g_views[:self.n_late], grads[:self.n_late]) if g is not None]
+            if len(late) != self.n_late:
+                self.flat_g[:self.off_late].zero_()
+            torch._foreach_copy_([v for v, _ in late], [g for _, g in late])
+            if self.off_late > 0:
+                dist.all_reduce(self.flat_g[:self.off_late])
+            torch.cuda.current_stream().wait_stream(self.comm)
+        else:
+            self.pack(grads)
+            if multi:
+                dist.all_reduce(self.flat_g)
+        if multi:
             scale = 1.0 / dist.get_world_size()     # averaged inside the Adam kernel (DDP semantics)
         with _ext._on_device(self.flat_p):
             _lib.check(_lib.lib().b2r_adam_flat_step(

@@ -152,13 +152,20 @@ def synthetic_loss(ep):
     return (ep["proposal_scores_raw"] ** 2).mean() + ((ep["vote_xyz"] - ep["seed_xyz"]) ** 2).mean()
 
 
-def workload_loss(workload, net, pc, geometry=None):
+def workload_loss(workload, net, pc, geometry=None, on_sa2_grad=None):
     """forward + synthetic loss of one step of `workload` (shared by the GPU arm and the CPU port:
-    `net` takes {"point_clouds": ..} or, gf3d, the point cloud itself)"""
+    `net` takes {"point_clouds": ..} or, gf3d, the point cloud itself).  on_sa2_grad: called in
+    backward once the gradient of SA2's output exists, i.e. when every layer after SA2 has its
+    weight gradients (N > 1: the early all-reduce bucket starts there)."""
+    def hook(ep):
+        if on_sa2_grad is not None and ep["sa2_features"].requires_grad:
+            ep["sa2_features"].register_hook(lambda g: on_sa2_grad())
+
     if workload == "votenet":
         ep = net({"point_clouds": pc, "geometry": geometry} if geometry is not None else {"point_clouds": pc})
         if "seed_xyz" not in ep:
             ep["seed_xyz"] = ep["fp2_xyz"]
+        hook(ep)
         return synthetic_loss(ep)
     if workload == "br":
         half = pc.shape[0] // 2
@@ -172,6 +179,7 @@ def workload_loss(workload, net, pc, geometry=None):
                 loss = loss + (ep["global_d_pred"] ** 2).mean() + (ep["local_d_pred"] ** 2).mean()
         return loss
     ep = net(pc, geometry=geometry) if geometry is not None else net(pc)
+    hook(ep)
     return (ep["fp2_features"] ** 2).mean()
 
 
@@ -469,11 +477,21 @@ def run_b2r(a):
     # N > 1: gradients are packed into one flat buffer for a single all-reduce per step
     # optimizer: Adam over one flat buffer (flat_adam.FlatAdam: pack + [all-reduce] + ONE kernel);
     # B2R_TORCH_ADAM=1 keeps torch.optim.Adam(fused) + FlatGradBucket (round 1's arrangement)
+    early_hook = None
     use_flat_adam = os.environ.get("B2R_TORCH_ADAM", "0") in ("0", "")
     if use_flat_adam:
         from backtoreality_b200.flat_adam import FlatAdam
         bucket = None
         opt = FlatAdam(params, lr=1e-3)
+        if world > 1 and a.workload != "br" and os.environ.get("B2R_OVERLAP", "0") not in ("0", ""):
+            # opt-in (measured at 2 GPUs: 3.490 vs 3.492 ms -- the 3.8 MB all-reduce is not what the
+            # N > 1 step waits for).  SA1's and SA2's gradients arrive last: everything else is
+            # all-reduced on a side stream while their backward runs (sa1, sa2 come first in
+            # net.parameters())
+            late = list(backbone.sa1.parameters()) + list(backbone.sa2.parameters())
+            assert all(x is y for x, y in zip(late, params)), "parameter order: sa1, sa2 first"
+            opt.set_late(len(late))
+            early_hook = opt.reduce_early
     else:
         bucket = dist_utils.FlatGradBucket(params, as_views=False) if world > 1 else None
         opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
@@ -487,7 +505,7 @@ def run_b2r(a):
     def fwd_bwd(pc, geometry=None):
         for p in params:          # autograd then ASSIGNS fresh gradients: no accumulate kernels,
             p.grad = None         # nothing to zero
-        loss = workload_loss(a.workload, net, pc, geometry)
+        loss = workload_loss(a.workload, net, pc, geometry, on_sa2_grad=early_hook)
         loss.backward()
         live["grads"] = [p.grad for p in params]
         return loss
