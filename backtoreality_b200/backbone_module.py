@@ -90,6 +90,7 @@ class Pointnet2Backbone(nn.Module):
             query = _QUERY_STREAMS[qkey] = torch.cuda.Stream(device=xyz.device)
         levels, cur = list(prev) if prev is not None else [], xyz
         assert len(levels) == first
+        fp, fp_ev = {}, None
         with torch.cuda.stream(side), torch.no_grad():
             for sa in (self.sa1, self.sa2, self.sa3, self.sa4)[first:last + 1]:
                 inds = _ext.furthest_point_sampling(cur, sa.npoint, cluster=fps_cluster)
@@ -109,6 +110,18 @@ class Pointnet2Backbone(nn.Module):
                         torch._foreach_copy_([dst[k] for k in keys], [src[k] for k in keys])
                     ev = torch.cuda.Event()
                     ev.record(query)
+                    # the FP modules' 3-NN indices and inverse-distance weights are geometry too
+                    # (fp2 interpolates sa3 -> sa2, fp1 sa4 -> sa3): on THIS stream as soon as their
+                    # two levels' centres exist, not at the tail of the FPS chain
+                    li = len(levels)
+                    if last == 3 and li == 2:
+                        fp["fp2_idx"], fp["fp2_weight"] = PointnetFPModule.interpolation_weights(
+                            levels[1]["new_xyz"], new_xyz)
+                    if last == 3 and li == 3:
+                        fp["fp1_idx"], fp["fp1_weight"] = PointnetFPModule.interpolation_weights(
+                            levels[2]["new_xyz"], new_xyz)
+                        fp_ev = torch.cuda.Event()
+                        fp_ev.record(query)
                 cur.record_stream(query)
                 new_xyz.record_stream(query)
                 for t in (inds, new_xyz, idx) + tuple(plan.values()):
@@ -117,23 +130,14 @@ class Pointnet2Backbone(nn.Module):
                                    sm_limit=(fused_sa.NUM_SMS - GEOMETRY_SMS) if sm_limit is None
                                    else sm_limit))
                 cur = new_xyz
-            if last < 3:
-                side.wait_stream(query)   # joining `side` joins the whole pre-pass
-                return levels
-            # the FP modules' 3-NN indices and inverse-distance weights are geometry too:
-            # fp1 interpolates sa4 -> sa3, fp2 sa3 -> sa2 (stored with the last level, whose
-            # event covers them)
-            sa2x, sa3x, sa4x = levels[1]["new_xyz"], levels[2]["new_xyz"], levels[3]["new_xyz"]
-            i1, w1 = PointnetFPModule.interpolation_weights(sa3x, sa4x)
-            i2, w2 = PointnetFPModule.interpolation_weights(sa2x, sa3x)
-            ev = torch.cuda.Event()
-            ev.record(side)
-            for t in (i1, w1, i2, w2):
-                t.record_stream(main)
-            levels[3].update(fp1_idx=i1, fp1_weight=w1, fp2_idx=i2, fp2_weight=w2, fp_event=ev)
-            if copy_to is not None:
-                fpk = [k for k in ("fp1_idx", "fp1_weight", "fp2_idx", "fp2_weight") if k in copy_to[3]]
-                torch._foreach_copy_([copy_to[3][k] for k in fpk], [levels[3][k] for k in fpk])
+            if last == 3:
+                for t in fp.values():
+                    t.record_stream(main)
+                levels[3].update(fp, fp_event=fp_ev)
+                if copy_to is not None:
+                    with torch.cuda.stream(query):
+                        fpk = [k for k in fp if k in copy_to[3]]
+                        torch._foreach_copy_([copy_to[3][k] for k in fpk], [fp[k] for k in fpk])
             side.wait_stream(query)       # joining `side` joins the whole pre-pass
         if sm_limit is None:
             levels[-1]["sm_limit"] = 0   # nothing runs beside sa4's MLP

@@ -24,7 +24,7 @@ import os
 
 import torch
 
-from . import _ext, _lib
+from . import _ext, _lib, step_arena
 
 _vp = ctypes.c_void_p
 
@@ -42,6 +42,8 @@ def _ceil4(c):
 
 def _vec(c, dev):
     """A per-channel coefficient vector the kernels may read up to the next multiple of 4."""
+    if c % 4 == 0:      # no padding to define: spare the fill kernel (40 of them per VoteNet step)
+        return torch.empty(c, dtype=torch.float32, device=dev)
     return torch.zeros(_ceil4(c), dtype=torch.float32, device=dev)
 
 
@@ -175,7 +177,7 @@ class _DenseMLP(torch.autograd.Function):
         # batch statistics of every layer: ONE zero-filled buffer
         stats_all, s_off = None, 0
         if training:
-            stats_all = torch.zeros(sum(2 * c.out_channels for c, b in specs if b is not None),
+            stats_all = step_arena.zeros(sum(2 * c.out_channels for c, b in specs if b is not None),
                                     dtype=torch.float64, device=dev)
         for l, (conv, bn) in enumerate(specs):
             w, bias = params[4 * l], params[4 * l + 1]
@@ -260,8 +262,8 @@ class _DenseMLP(torch.autograd.Function):
         Ct = specs[top][0].out_channels
         coef = None
         # every accumulated output from two zero-filled buffers
-        dW_all = torch.zeros(sum(c.out_channels * c.in_channels for c, _ in specs), **f32)
-        st_all = torch.zeros(sum(2 * c.out_channels for c, b in specs if b is not None),
+        dW_all = step_arena.zeros(sum(c.out_channels * c.in_channels for c, _ in specs), **f32)
+        st_all = step_arena.zeros(sum(2 * c.out_channels for c, b in specs if b is not None),
                              dtype=torch.float64, device=dev)
         w_off, s_off = [0], [0]
         for c, b_ in specs:
@@ -392,7 +394,7 @@ class _InterpCat(torch.autograd.Function):
         g = g.contiguous()
         g_known = g_skip = None
         if ctx.needs_input_grad[0]:
-            g_known = torch.zeros((B, m, C2), dtype=torch.float32, device=g.device)
+            g_known = step_arena.zeros((B, m, C2), dtype=torch.float32, device=g.device)
         if C1 and ctx.needs_input_grad[1]:
             g_skip = torch.empty((B, n, C1), dtype=torch.float32, device=g.device)
         _lib.check(_lib.lib().b2r_interp_cat_bwd(_ptr(g), g.shape[1], _ptr(idx), _ptr(weight), B, n,

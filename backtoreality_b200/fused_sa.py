@@ -34,7 +34,7 @@ import os
 
 import torch
 
-from . import _ext, _lib
+from . import _ext, _lib, step_arena
 
 _vp = ctypes.c_void_p
 
@@ -243,7 +243,7 @@ def sa_mlp_forward(xyz, new_xyz, feat_t, idx, radius, normalize_xyz, mlp_module,
     # batch statistics of every layer: ONE zero-filled buffer (one memset instead of one per layer)
     stats_all = None
     if training:
-        stats_all = torch.zeros(sum(2 * b.conv.out_channels for b in blocks), dtype=torch.float64,
+        stats_all = step_arena.zeros(sum(2 * b.conv.out_channels for b in blocks), dtype=torch.float64,
                                 device=dev)
     stats_off = 0
     zmax = zmin = amax = amin = None
@@ -362,8 +362,8 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
     Ct = weights[top].shape[0]
     mean, invstd, scale, shift = bn[top]
     # every accumulated output of the block from two zero-filled buffers (two memsets in total)
-    stats_all = torch.zeros(sum(2 * w.shape[0] for w in weights), dtype=torch.float64, device=dev)
-    dW_all = torch.zeros(sum(w.numel() for w in weights), **f32)
+    stats_all = step_arena.zeros(sum(2 * w.shape[0] for w in weights), dtype=torch.float64, device=dev)
+    dW_all = step_arena.zeros(sum(w.numel() for w in weights), **f32)
     s_off, w_off = [0], [0]
     for w in weights:
         s_off.append(s_off[-1] + 2 * w.shape[0])
@@ -406,13 +406,13 @@ def sa_mlp_backward(g_out_cm, xyz, new_xyz, feat_t, idx, radius, normalize_xyz, 
             b.xyz, b.new_xyz, b.feat_t, b.idx = _ptr(xyz), _ptr(new_xyz), _ptr(feat_t), _ptr(idx)
             b.radius, b.normalize_xyz = float(radius), 1 if normalize_xyz else 0
             if need_feat and feat_t is not None:
-                g_feat_t = torch.zeros_like(feat_t)
+                g_feat_t = step_arena.zeros_like(feat_t)
                 b.g_feat_t = _ptr(g_feat_t)
             if need_xyz:
-                g_xyz = torch.zeros_like(xyz)
+                g_xyz = step_arena.zeros_like(xyz)
                 b.g_xyz = _ptr(g_xyz)
             if need_new_xyz:
-                g_new_xyz = torch.zeros_like(new_xyz)
+                g_new_xyz = step_arena.zeros_like(new_xyz)
                 b.g_new_xyz = _ptr(g_new_xyz)
             need_dgrad = g_feat_t is not None or need_xyz or need_new_xyz
         else:

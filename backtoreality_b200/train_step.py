@@ -21,6 +21,7 @@ add `warmup` weight updates on duplicated data each time).
 import copy
 
 import torch
+from . import step_arena
 
 
 def _save_state(objs):
@@ -59,7 +60,7 @@ class CapturedTrainStep:
         saved = _save_state(self.snapshot)
         with torch.cuda.stream(side):
             for _ in range(self.warmup):
-                self.step_fn(self.static_in)
+                self._step()
                 if self.after_warmup_step is not None:
                     self.after_warmup_step()
         torch.cuda.current_stream().wait_stream(side)
@@ -71,11 +72,19 @@ class CapturedTrainStep:
         try:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, capture_error_mode=CAPTURE_ERROR_MODE):
-                loss = self.step_fn(self.static_in)
+                loss = self._step()
             self.graph, self.static_loss = g, loss
             self.launches_per_step = _ext.LAUNCHES - l0
         finally:
             _ext.TIME_OPS.update(saved_ops)
+
+    def _step(self):
+        # every zero-initialised accumulator of the step comes from one arena, cleared by ONE memset
+        step_arena.begin(self.static_in.device)
+        try:
+            return self.step_fn(self.static_in)
+        finally:
+            step_arena.end(self.static_in.device)
 
     def __call__(self, batch, non_blocking=True):
         self.static_in.copy_(batch, non_blocking=non_blocking)
@@ -197,7 +206,11 @@ class PipelinedTrainStep:
             launch_prepass()
         else:
             levels[self.start_after_level]["after_forward"] = launch_prepass
-        loss = self.step_fn(self.cur, levels)
+        step_arena.begin(self.cur.device)
+        try:
+            loss = self.step_fn(self.cur, levels)
+        finally:
+            step_arena.end(self.cur.device)
         if "nxt" not in box:       # the step never reached that level's hook
             launch_prepass()
         nxt = box["nxt"]
@@ -290,7 +303,11 @@ class PipelinedTrainStepPP(PipelinedTrainStep):
             launch_prepass()
         else:
             levels[self.start_after_level]["after_forward"] = launch_prepass
-        loss = self.step_fn(self.X[p], levels)
+        step_arena.begin(self.X[p].device)
+        try:
+            loss = self.step_fn(self.X[p], levels)
+        finally:
+            step_arena.end(self.X[p].device)
         if "nxt" not in box:
             launch_prepass()
         main.wait_stream(self.side)
@@ -432,7 +449,11 @@ class PipelinedTrainStep2(PipelinedTrainStep):
             launch_a()
         else:
             levels[self.start_after_level]["after_forward"] = launch_a
-        loss = self.step_fn(self.cur, levels)
+        step_arena.begin(self.cur.device)
+        try:
+            loss = self.step_fn(self.cur, levels)
+        finally:
+            step_arena.end(self.cur.device)
         if "a" not in box:
             launch_a()
         geo_b = box["b"]

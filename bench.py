@@ -128,7 +128,7 @@ def workload_config(a, world):
         "optimizer": ("Adam, lr 1e-3, one streaming kernel over the flat parameter buffer (flat_adam.FlatAdam)"
                       if os.environ.get("B2R_TORCH_ADAM", "0") in ("0", "")
                       else "torch.optim.Adam(fused=True, capturable=True), lr 1e-3"),
-        "l2": "256 MB buffer written between steps (flush) + 4 rotating input batches",
+        "l2": "160 MB buffer (> the 126 MB L2) written between steps (flush) + 4 rotating input batches",
         "e2e_input": "pinned host -> device on a copy stream, one step ahead (train_step.HostPrefetcher)",
         "launch": ("whole step (fwd+bwd+Adam) captured in one CUDA graph, replayed per batch" if world == 1
                    else ("fwd+bwd replayed from one CUDA graph; NCCL all-reduce + fused Adam eager"
@@ -500,7 +500,7 @@ def run_b2r(a):
     pool_n = 4
     host = [torch.from_numpy(make_batch(a, rank * pool_n + i)).pin_memory() for i in range(pool_n)]
     resident = [h.to(dev) for h in host]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)   # > the 126 MB L2
 
     def fwd_bwd(pc, geometry=None):
         for p in params:          # autograd then ASSIGNS fresh gradients: no accumulate kernels,
