@@ -55,7 +55,7 @@ class Pointnet2Backbone(nn.Module):
         return xyz, features
 
     def geometry_prepass(self, xyz, fps_cluster=0, sm_limit=None, side=None, first=0, last=3,
-                         prev=None, copy_to=None):
+                         prev=None, copy_to=None, plan_splits=1):
         """inds / new_xyz / ball-query idx of sa1..sa4 for xyz (B,N,3), issued as one chain on a
         side stream with one event per level.  Returns the list of four per-level dicts that
         `forward(..., geometry=)` and `PointnetSAModuleVotes.forward(..., geometry=)` take.
@@ -74,7 +74,10 @@ class Pointnet2Backbone(nn.Module):
         copy_to: optional list of four dicts of preallocated tensors; every level's results are
         also copied into copy_to[level][key] on the side streams as soon as they exist
         (train_step.PipelinedTrainStepPP: the static buffers of the NEXT graph, filled off the
-        critical path)."""
+        critical path).
+        plan_splits: k > 1 builds the pad-free plans per batch slice (keys "cidx#i", "ccen#i",
+        "cmeta#i"): the batch will be consumed as k separate forwards (`split_geometry`; the BR step
+        of train_Votenet_BR.py:277-289 runs the source and the target half one after the other)."""
         main = torch.cuda.current_stream()
         if side is None:
             side = _GEO_STREAMS.get(xyz.device)
@@ -102,7 +105,13 @@ class Pointnet2Backbone(nn.Module):
                     # the block's pad-free position space (fused_sa.compact_plan) is geometry too
                     plan = {}
                     if fused_sa.ENABLED and fused_sa.compact_wanted(sa.nsample):
-                        plan = fused_sa.compact_plan(idx, cur.shape[1])
+                        if plan_splits <= 1:
+                            plan = fused_sa.compact_plan(idx, cur.shape[1])
+                        else:
+                            per = idx.shape[0] // plan_splits
+                            for i in range(plan_splits):
+                                part = fused_sa.compact_plan(idx[i * per:(i + 1) * per], cur.shape[1])
+                                plan.update({"%s#%d" % (k, i): v for k, v in part.items()})
                     if copy_to is not None:
                         dst = copy_to[len(levels)]
                         keys = [k for k in dst if k in plan or k in ("inds", "new_xyz", "idx")]
@@ -142,6 +151,35 @@ class Pointnet2Backbone(nn.Module):
         if sm_limit is None:
             levels[-1]["sm_limit"] = 0   # nothing runs beside sa4's MLP
         return levels
+
+    @staticmethod
+    def split_geometry(levels, nsplit):
+        """The pre-pass of a batch that is consumed as `nsplit` consecutive forwards over equal
+        batch slices (geometry_prepass(..., plan_splits=nsplit)) -> one list of four level dicts
+        per slice.  Index tensors are leading-dimension views; the `after_forward` hook of a level
+        (train_step.PipelinedTrainStep) goes with the FIRST slice."""
+        out = []
+        for i in range(nsplit):
+            part = []
+            for lv in levels:
+                d = {}
+                for k, v in lv.items():
+                    if "#" in k:
+                        base, j = k.split("#")
+                        if int(j) == i:
+                            d[base] = v
+                    elif torch.is_tensor(v) and k in ("inds", "new_xyz", "idx", "fp1_idx", "fp1_weight",
+                                                      "fp2_idx", "fp2_weight"):
+                        per = v.shape[0] // nsplit
+                        d[k] = v[i * per:(i + 1) * per]
+                    elif k == "after_forward":
+                        if i == 0:
+                            d[k] = v
+                    else:
+                        d[k] = v
+                part.append(d)
+            out.append(part)
+        return out
 
     @staticmethod
     def _after_forward(level):

@@ -297,7 +297,13 @@ class _DenseMLP(torch.autograd.Function):
             gr = g_pm.contiguous()
             ld_g = gr.shape[1]
             if params[4 * top + 1] is not None:
-                grads[4 * top + 1] = gr[:, :Ct].sum(0)
+                # bias gradient of the plain last layer: a 14 us column reduction nothing downstream
+                # waits for -- on the weight-gradient side stream, off the critical path
+                wside.wait_stream(main)
+                with torch.cuda.stream(wside):
+                    grads[4 * top + 1] = gr[:, :Ct].sum(0)
+                gr.record_stream(wside)
+                grads[4 * top + 1].record_stream(main)
         g_x = None
         for l in range(L - 1, -1, -1):
             conv, bn = specs[l]

@@ -138,11 +138,15 @@ class PipelinedTrainStep:
 
     @classmethod
     def _keys(cls, level):
-        return cls.GEO_KEYS + tuple(k for k in cls.PLAN_KEYS + cls.FP_KEYS if k in level)
+        split_plans = tuple(k for k in level if "#" in k and k.split("#")[0] in cls.PLAN_KEYS)
+        return cls.GEO_KEYS + tuple(k for k in cls.PLAN_KEYS + cls.FP_KEYS if k in level) + split_plans
 
     def __init__(self, backbone, step_fn, first_batch, warmup=3, fps_cluster=4, sm_caps=None,
-                 after_warmup_step=None, start_after_level=1, snapshot=None):
+                 after_warmup_step=None, start_after_level=1, snapshot=None, plan_splits=1):
         self.backbone = backbone
+        # > 1: the batch is consumed as that many consecutive forwards over equal slices
+        # (Pointnet2Backbone.split_geometry), e.g. the source and target halves of the BR step
+        self.plan_splits = int(plan_splits)
         self.step_fn = step_fn
         self.snapshot = snapshot
         self.after_warmup_step = after_warmup_step
@@ -178,7 +182,8 @@ class PipelinedTrainStep:
         now, eagerly."""
         self.cur.copy_(batch)
         xyz = self._xyz(self.cur)     # stays referenced until the side stream has been joined
-        levels = self.backbone.geometry_prepass(xyz, side=self.side)
+        levels = self.backbone.geometry_prepass(xyz, side=self.side,
+                                                plan_splits=getattr(self, "plan_splits", 1))
         torch.cuda.current_stream().wait_stream(self.side)
         fresh = [{k: lv[k] for k in self._keys(lv)} for lv in levels]
         if self.geo_cur is None:
@@ -199,7 +204,8 @@ class PipelinedTrainStep:
 
         def launch_prepass():
             box["nxt"] = self.backbone.geometry_prepass(xyz_next, fps_cluster=self.fps_cluster,
-                                                        sm_limit=0, side=self.side)
+                                                        sm_limit=0, side=self.side,
+                                                        plan_splits=self.plan_splits)
 
         levels = self._levels(self.geo_cur)
         if self.start_after_level is None:

@@ -78,9 +78,9 @@ def parse():
     ap.add_argument("--trace", default="",
                     help="after timing, trace 3 steps with torch.profiler (CUPTI) and write a per-kernel "
                          "summary + stream-occupancy analysis of one step to this file")
-    ap.add_argument("--prepass-after", type=int, default=1,
+    ap.add_argument("--prepass-after", type=int, default=None,
                     help="pipelined step: start the next batch's pre-pass after this SA level's forward "
-                         "(-1: with the step)")
+                         "(-1: with the step; default 1, br: -1 -- its step holds two forwards)")
     ap.add_argument("--sm-caps", default="",
                     help="pipelined step: persistent-grid caps 'fwd:bwd' of sa1,sa2,sa3,sa4,vote-agg "
                          "(comma separated, 0 = every SM); default: see PipelinedTrainStep")
@@ -91,6 +91,8 @@ def parse():
         a.npoints = 50000 if a.workload == "gf3d" else 40000
     if a.cpu_scenes <= 0:
         a.cpu_scenes = a.batch
+    if a.prepass_after is None:
+        a.prepass_after = -1 if a.workload == "br" else 1
     return a
 
 
@@ -136,7 +138,7 @@ def workload_config(a, world):
                          else "whole step (fwd+bwd + gradient pack + NCCL all-reduce + Adam) captured in one "
                               "CUDA graph per rank, replayed per batch")),
         "pipeline": ("none: FPS / ball query of a batch run inside its own step (geometry stream)"
-                     if a.no_pipeline or a.no_graph or a.workload == "br"
+                     if a.no_pipeline or a.no_graph
                      else "geometry pre-pass (FPS, centre gather, ball query, pad-free plans of sa1..sa4) of "
                           "batch i+1 runs beside the step of batch i in the same graph (%d-CTA FPS clusters, "
                           "started after SA level %d's forward; depth %d); every timed step = one pre-pass + "
@@ -170,8 +172,12 @@ def workload_loss(workload, net, pc, geometry=None, on_sa2_grad=None):
     if workload == "br":
         half = pc.shape[0] // 2
         loss = 0.0
-        for part in (pc[:half], pc[half:]):      # source forward, then target forward
-            ep = net({"point_clouds": part})
+        geo = [None, None]
+        if geometry is not None:                  # pre-pass of all 16 scenes, consumed half by half
+            from backtoreality_b200.backbone_module import Pointnet2Backbone
+            geo = Pointnet2Backbone.split_geometry(geometry, 2)
+        for part, g in zip((pc[:half], pc[half:]), geo):      # source forward, then target forward
+            ep = net({"point_clouds": part, "geometry": g} if g is not None else {"point_clouds": part})
             if "seed_xyz" not in ep:
                 ep["seed_xyz"] = ep["fp2_xyz"]
             loss = loss + synthetic_loss(ep)
@@ -576,8 +582,8 @@ def run_b2r(a):
     # B2R_EAGER_COLLECTIVE=1: round 1's arrangement (only forward+backward replayed; pack, NCCL
     # all-reduce and Adam launched eagerly after every replay)
     capture_all = world == 1 or os.environ.get("B2R_EAGER_COLLECTIVE", "0") in ("0", "")
-    # br runs two forwards per step: its geometry stays inside the step (geometry stream)
-    pipelined = not (a.no_graph or a.no_pipeline) and a.workload != "br"
+    # br runs two forwards per step: one pre-pass over its 16 scenes, pad-free plans per half
+    pipelined = not (a.no_graph or a.no_pipeline)
     for attempt in ((0, 1) if not a.no_graph else ()):
         try:
             from backtoreality_b200.train_step import (CapturedTrainStep, PipelinedTrainStep,
@@ -591,11 +597,11 @@ def run_b2r(a):
                 # the vote-aggregation block has no pre-pass level of its own: give its kernels the
                 # caps of the levels around it (forward: beside SA1's FPS; backward: it runs first)
                 start = None if a.prepass_after < 0 else a.prepass_after
-                caps, head_cap = PipelinedTrainStep.default_caps(a.batch, a.fps_cluster, start)
+                caps, head_cap = PipelinedTrainStep.default_caps(scenes_per_step(a), a.fps_cluster, start)
                 if a.sm_caps:
                     caps = [tuple(int(v) for v in c.split(":")) for c in a.sm_caps.split(",")]
                     caps, head_cap = caps[:4], caps[4]
-                if a.workload == "votenet":
+                if a.workload in ("votenet", "br"):
                     net.pnet.vote_aggregation.sm_limit = head_cap
                 if a.pipeline_depth == 2:
                     graphed = PipelinedTrainStep2(backbone, step if capture_all else fwd_bwd,
@@ -605,9 +611,9 @@ def run_b2r(a):
                                                   start_after_level=start)
                 else:
                     graphed = Pipe(backbone, step if capture_all else fwd_bwd,
-                                                 resident[0], fps_cluster=a.fps_cluster, sm_caps=caps,
-                                                 after_warmup_step=None if capture_all else finish,
-                                                 start_after_level=start)
+                                   resident[0], fps_cluster=a.fps_cluster, sm_caps=caps,
+                                   after_warmup_step=None if capture_all else finish,
+                                   start_after_level=start, plan_splits=2 if a.workload == "br" else 1)
             else:
                 graphed = CapturedTrainStep(step if capture_all else fwd_bwd, resident[0],
                                             after_warmup_step=None if capture_all else finish)

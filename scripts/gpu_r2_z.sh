@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT"; mkdir -p gpurun_out
+: > gpurun_out/sweep_z.log
+for pa in 1 0 -1; do for fc in 4 5 6; do
+timeout 300 python bench.py --no-cpu-baseline --steps 30 --warmup 5 --prepass-after $pa --fps-cluster $fc > gpurun_out/_b.json 2> gpurun_out/_b.err
+python -c "
+import json; d=json.load(open('gpurun_out/_b.json')); print('prepass_after $pa fps_cluster $fc: %.3f ms  %.1f scenes/s  e2e %.1f' % (d['ms_per_step'], d['value'], d['e2e']['value']))" | tee -a gpurun_out/sweep_z.log
+done; done

@@ -823,3 +823,33 @@ def test_gf3d_query_sampling_golden(cuda):
     proj = torch.nn.Conv1d(288, 288, 1).to(cuda)
     want = proj(feat.detach())
     assert rel_l2(m.project_pm(proj, feat.detach()).detach().cpu().numpy(), want.detach().cpu().numpy()) < 5e-3
+
+
+def test_split_geometry_equals_separate_prepasses(cuda):
+    """geometry_prepass(plan_splits=2) + split_geometry (the BR step: one pre-pass over source +
+    target scenes, consumed as two forwards) gives each half exactly the geometry -- indices AND
+    pad-free plans -- of a pre-pass over that half alone, and the same forward output."""
+    from backtoreality_b200.backbone_module import Pointnet2Backbone
+    torch.manual_seed(2)
+    net = Pointnet2Backbone(input_feature_dim=1).to(cuda).train()
+    pc = torch.from_numpy(scenes.batch(500, 4, 12000, C=1, kind="room", dup=0.2)).to(cuda)
+    xyz = pc[..., :3].contiguous()
+    both = net.geometry_prepass(xyz, plan_splits=2)
+    torch.cuda.synchronize()
+    halves = Pointnet2Backbone.split_geometry(both, 2)
+    for i, part in enumerate((pc[:2], pc[2:])):
+        alone = net.geometry_prepass(part[..., :3].contiguous())
+        torch.cuda.synchronize()
+        for lv_s, lv_a in zip(halves[i], alone):
+            for k in ("inds", "new_xyz", "idx"):
+                assert torch.equal(lv_s[k], lv_a[k]), (i, k)
+            if "cmeta" in lv_a:
+                n = int(lv_a["cmeta"][8])
+                assert n == int(lv_s["cmeta"][8])
+                assert torch.equal(lv_s["cidx"][:n], lv_a["cidx"][:n]) and torch.equal(lv_s["ccen"][:n], lv_a["ccen"][:n])
+        for k in ("fp1_idx", "fp1_weight", "fp2_idx", "fp2_weight"):
+            assert torch.equal(halves[i][3][k], alone[3][k]), k
+        with torch.no_grad():
+            a = net(part, geometry=halves[i])["fp2_features"]
+            b = net(part, geometry=alone)["fp2_features"]
+        assert torch.equal(a, b)
