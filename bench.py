@@ -73,8 +73,9 @@ def parse():
     ap.add_argument("--pipeline-depth", type=int, default=1, choices=[1, 2],
                     help="pipelined step: 1 = whole geometry pre-pass of batch i+1 beside step i; 2 = SA1 "
                          "geometry of batch i+2 and the later levels' of batch i+1 beside step i")
-    ap.add_argument("--fps-cluster", type=int, default=4,
-                    help="pipelined step: CTAs per scene of the next batch's FPS")
+    ap.add_argument("--fps-cluster", type=int, default=None,
+                    help="pipelined step: CTAs per scene of the next batch's FPS (default 4; gf3d, with "
+                         "4 scenes per GPU: 10)")
     ap.add_argument("--trace", default="",
                     help="after timing, trace 3 steps with torch.profiler (CUPTI) and write a per-kernel "
                          "summary + stream-occupancy analysis of one step to this file")
@@ -91,8 +92,12 @@ def parse():
         a.npoints = 50000 if a.workload == "gf3d" else 40000
     if a.cpu_scenes <= 0:
         a.cpu_scenes = a.batch
+    # measured optima (profiles/r02/sweep_*.log): the pre-pass must end with the step, on as few SMs
+    # as that allows
     if a.prepass_after is None:
-        a.prepass_after = -1 if a.workload == "br" else 1
+        a.prepass_after = {"br": -1, "gf3d": 0}.get(a.workload, 1)
+    if a.fps_cluster is None:
+        a.fps_cluster = 10 if a.workload == "gf3d" else 4
     return a
 
 
