@@ -32,7 +32,8 @@ def begin(device, min_bytes=48 << 20):
     if not ENABLED:
         return
     a = _ARENAS.get(device)
-    if a is None or (a.want > a.buf.numel() and not torch.cuda.is_current_stream_capturing()):
+    capturing = torch.device(device).type == "cuda" and torch.cuda.is_current_stream_capturing()
+    if a is None or (a.want > a.buf.numel() and not capturing):
         a = _ARENAS[device] = _Arena(device, max(min_bytes, int((a.want if a else 0) * 1.25)))
     else:
         a.buf.zero_()
