@@ -246,6 +246,9 @@ def _plan_pays(entries, targets, per_source, rows):
     profiles/r02/movers_roofline.log)."""
     if DETERMINISTIC:
         return True
+    if (per_source == 3 and targets <= 4096) or targets <= 1024:
+        # multi-channel gather: 4 rows per CTA share one walk over the lists
+        return rows >= 512 and entries >= targets
     tiles = -(-(entries // per_source) // 16384)
     return entries >= 2 * tiles * targets and rows >= 96
 

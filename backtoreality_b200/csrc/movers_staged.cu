@@ -17,6 +17,8 @@
 //     list from shared memory in a fixed order and writes grad_features[b,c,:] coalesced.  No
 //     atomics, no memset, run-to-run bit-identical (the reference's atomicAdd order is
 //     unspecified, group_points_gpu.cu:48-69, interpolate_gpu.cu:121-148: any order conforms).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b2r {
@@ -24,6 +26,9 @@ namespace {
 
 constexpr int kStageThreads = 512;
 constexpr int kSmemBudget = 200 * 1024;
+constexpr int kMcMaxTargets = 4096;   // multi-channel gather: targets per row it keeps in registers
+constexpr int kMcTile = 4096;         // ... and sources per staged tile
+constexpr int kMcMaxRows = 8;         // ... and (b,c) rows per CTA (template CC: 4 or 8)
 
 // ------------------------------------------------------------------------- group forward --
 // out[b,c,e] = f[b,c,idx[b,e]];  grid (tiles of e, C chunks, B); smem: one source row
@@ -108,6 +113,10 @@ __global__ void __launch_bounds__(kIpT)
 // adds into target idx[e] in [0,N).  Sources are processed in tiles of TS positions (one smem
 // stage); key(e) = tile * N + target.  plan = { int start[B][T*N + 1]; int pos[B][E];
 // float wperm[B][E] (weighted only); int cursor[B][T*N] (scratch) }.
+// Measured on B200 (profiles/r02/movers_roofline.log): interpolation (3 entries per source: the list
+// walk dominates) gains from sharing it between rows at every size; grouping only for short rows.
+inline bool use_mc(int N, int K) { return K == 3 ? N <= kMcMaxTargets : N <= 1024; }
+
 struct PlanDims {
   long long E;
   int N, K, S, TS, T;
@@ -119,7 +128,9 @@ PlanDims plan_dims(int B, long long E, int N, int K, bool weighted) {
   PlanDims d;
   d.E = E; d.N = N; d.K = K;
   d.S = (int)(E / K);
-  d.TS = 16384;                       // 64 KB of staged gradients per CTA: three CTAs per SM
+  // multi-channel gather (4 rows of 4096 staged sources share one walk over the lists, sums in
+  // registers) where it measured faster, else one row of 16384 sources per CTA
+  d.TS = use_mc(N, K) ? kMcTile : 16384;
   d.T = d.S > 0 ? (d.S + d.TS - 1) / d.TS : 1;
   d.TN = (long long)d.T * N;
   size_t o = 0;
@@ -272,6 +283,74 @@ __global__ void __launch_bounds__(kStageThreads)
   }
 }
 
+// Multi-channel variant for rows of <= 4096 targets (every level of the detectors but SA1): a CTA
+// owns kMcRows consecutive channel rows of one scene.  The walk over a target's list -- the
+// uncoalesced part: one lane per list -- is done ONCE for all rows (8x less index traffic and LSU
+// pressure per byte of gradient), sums stay in registers across the source tiles (KT targets per
+// thread), and the rows are written once at the end.  Same fixed summation order as above.
+template <int K, bool WEIGHTED, int KT, int kMcRows>
+__global__ void __launch_bounds__(kStageThreads)
+    scatter_gather_mc_kernel(const float *__restrict__ g, const int *__restrict__ start,
+                             const int *__restrict__ pos, const float *__restrict__ wperm, int C, int N,
+                             long long E, int S, int T, float *__restrict__ gf) {
+  extern __shared__ __align__(16) float s_g[];   // [kMcRows][kMcTile]
+  const int tid = threadIdx.x, b = blockIdx.y, c0 = blockIdx.x * kMcRows;
+  const int nr = min(kMcRows, C - c0);
+  const float *rows = g + ((size_t)b * C + c0) * S;
+  const long long TN = (long long)T * N;
+  start += (size_t)b * (TN + 1);
+  pos += (size_t)b * E;
+  if (WEIGHTED) wperm += (size_t)b * E;
+  const bool vec = ((S & 3) == 0) && ((reinterpret_cast<uintptr_t>(rows) & 15) == 0);
+  float acc[KT][kMcRows];
+#pragma unroll
+  for (int k = 0; k < KT; ++k)
+#pragma unroll
+    for (int r = 0; r < kMcRows; ++r) acc[k][r] = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const int base = t * kMcTile, len = min(kMcTile, S - base);
+    for (int r = 0; r < nr; ++r) {
+      const float *src = rows + (size_t)r * S + base;
+      float *dst = s_g + r * kMcTile;
+      if (vec) {
+        for (int i = tid * 4; i < len; i += kStageThreads * 4)
+          *reinterpret_cast<float4 *>(dst + i) = __ldcs(reinterpret_cast<const float4 *>(src + i));
+      } else {
+        for (int i = tid; i < len; i += kStageThreads) dst[i] = __ldcs(src + i);
+      }
+    }
+    __syncthreads();
+    const int *st = start + (size_t)t * N;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      const int n = tid + k * kStageThreads;
+      if (n < N) {
+        const int s0 = st[n], s1 = st[n + 1];
+        for (int q = s0; q < s1; ++q) {
+          const int p = pos[q] / K - base;
+          float w = 1.f;
+          if (WEIGHTED) w = wperm[q];
+#pragma unroll
+          for (int r = 0; r < kMcRows; ++r) {
+            float v = s_g[r * kMcTile + p];      // rows >= nr hold stale data: never stored
+            if (WEIGHTED) v = __fmul_rn(v, w);
+            acc[k][r] += v;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    const int n = tid + k * kStageThreads;
+    if (n < N)
+#pragma unroll
+      for (int r = 0; r < kMcRows; ++r)
+        if (r < nr) gf[((size_t)b * C + c0 + r) * N + n] = acc[k][r];
+  }
+}
+
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -403,6 +482,28 @@ int launch_gather_g(const PlanDims &d, const float *g, const void *plan, int B, 
   return B2R_OK;
 }
 
+template <int K, bool WEIGHTED, int KT, int kMcRows>
+int launch_gather_mc(const PlanDims &d, const float *g, const void *plan, int B, int C, int N,
+                     long long E, float *gf, cudaStream_t st) {
+  const char *base = static_cast<const char *>(plan);
+  const int *start = reinterpret_cast<const int *>(base);
+  const int *pos = reinterpret_cast<const int *>(base + d.off_pos);
+  const float *wperm = WEIGHTED ? reinterpret_cast<const float *>(base + d.off_w) : nullptr;
+  auto kern = scatter_gather_mc_kernel<K, WEIGHTED, KT, kMcRows>;
+  constexpr int smem = kMcRows * kMcTile * 4;
+  static bool attr_done[64] = {};
+  int dev = 0;
+  B2R_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
+  dim3 grid((unsigned)((C + kMcRows - 1) / kMcRows), (unsigned)B);
+  kern<<<grid, kStageThreads, smem, st>>>(g, start, pos, wperm, C, N, E, d.S, d.T, gf);
+  B2R_CHECK_LAUNCH();
+  return B2R_OK;
+}
+
 // One lane per target.  (Measured, profiles/r02/movers_roofline.log: 8- and 32-lane groups with a
 // shuffle tree read pos / weight coalesced but leave 8-32x fewer independent chains in flight;
 // at the detectors' shapes they were 1.5-2x SLOWER than one lane per target.)
@@ -410,6 +511,15 @@ template <int K, bool WEIGHTED>
 int launch_gather(const float *g, const void *plan, int B, int C, int N, long long E, float *gf,
                   cudaStream_t st) {
   const PlanDims d = plan_dims(B, E, N, K, WEIGHTED);
+  if (use_mc(N, K)) {
+    // rows per CTA: 4 keep three CTAs resident per SM (8 rows, one CTA per SM, measured 25-40 %
+    // slower although they halve the index traffic again)
+    const int kt = N <= 512 ? 1 : N <= 1024 ? 2 : N <= 2048 ? 4 : 8;
+    if (kt == 1) return launch_gather_mc<K, WEIGHTED, 1, 4>(d, g, plan, B, C, N, E, gf, st);
+    if (kt == 2) return launch_gather_mc<K, WEIGHTED, 2, 4>(d, g, plan, B, C, N, E, gf, st);
+    if (kt == 4) return launch_gather_mc<K, WEIGHTED, 4, 4>(d, g, plan, B, C, N, E, gf, st);
+    return launch_gather_mc<K, WEIGHTED, 8, 4>(d, g, plan, B, C, N, E, gf, st);
+  }
   return launch_gather_g<K, WEIGHTED, 1>(d, g, plan, B, C, N, E, gf, st);
 }
 }  // namespace

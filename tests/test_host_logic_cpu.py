@@ -61,6 +61,8 @@ def test_scatter_plan_dispatch_rule():
     assert not _ext._plan_pays(2048 * 64, 40000, 1, 8 * 4)
     # too few rows to fill the GPU
     assert not _ext._plan_pays(1024 * 32, 2048, 1, 16)
+    # more than 4096 targets with dense lists: the one-row-per-CTA plan kernel
+    assert _ext._plan_pays(3 * 100000, 8192, 3, 8 * 64)
 
 
 def test_flat_adam_refuses_cpu_parameters():
