@@ -577,15 +577,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
         const int ncen = ((base_s + NT - 1) >> shift_t) + 1;
         float *my_dy = s_dy + (size_t)s * kRC * a.Cout_pad;
         int *my_as = s_as + (size_t)s * kRC * a.Cout_pad;
-        for (int ml = 0; ml < MTl; ++ml) {
-          const int co = ml * 128 + q * 32 + lane;
-          if (co < a.Cout)
-            for (int c = 0; c < ncen; ++c) {
-              long long cg = centre0 + c;
+        // global centre of the tile's c-th centre (its first in-tile position), dead padding = -1:
+        // lane c fetches it ONCE for the warp (ncen <= NT/8 + 1 <= 17) and the loop below takes it
+        // by shuffle -- a dependent global load per centre and thread in front of every cp.async
+        // pair was 15 % of this kernel's stall samples (profiles/r02/ncu_stalls_sa1_bwd.txt)
+        int cg_lane = -1;
+        if constexpr (CMP) {
+          if (lane < ncen) cg_lane = __ldg(a.ccen + pos0 + (lane == 0 ? 0 : lane * ns_t - base_s));
+        }
+        for (int c = 0; c < ncen; ++c) {
+          long long cg = centre0 + c;
+          if constexpr (CMP) cg = __shfl_sync(0xffffffffu, cg_lane, c);
+          for (int ml = 0; ml < MTl; ++ml) {
+            const int co = ml * 128 + q * 32 + lane;
+            if (co < a.Cout) {
               if constexpr (CMP) {
-                // global centre of the tile's c-th centre (its first in-tile position); dead
-                // padding routes nothing
-                cg = __ldg(a.ccen + pos0 + (c == 0 ? 0 : c * ns_t - base_s));
                 if (cg < 0) {
                   my_dy[c * a.Cout_pad + co] = 0.f;
                   my_as[c * a.Cout_pad + co] = -1;
@@ -602,6 +608,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
                            "l"(a.asel + o)
                            : "memory");
             }
+          }
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
