@@ -239,7 +239,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
   }
 
   if (tid == 0) {
-    for (int i = 0; i < 13; ++i) mbar_init(bar(i), 1);
+    // full (0,1) and d2_free (10,11) are completed by ONE arrival per warp of the role -- a named
+    // barrier + single arrival made every warp of the role wait for its slowest sibling once per
+    // tile (stall_barrier 13-22 % of the samples, profiles/r02/ncu_stalls_sa1_bwd.txt)
+    for (int i = 0; i < 13; ++i)
+      mbar_init(bar(i), (i == 0 || i == 1) ? (uint32_t)(kProdThreads / 32)
+                        : (i == 10 || i == 11) ? (uint32_t)EW : 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == EW) tmem_alloc(smem_u32(s_tmem), kTmemCols);
@@ -483,8 +488,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
         }
       }
       fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-      bar_prod();
-      if (ptid == 0) mbar_arrive(bar(0 + s));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(0 + s));
     }
   } else if (warp == EW) {
     // =============================== MMA ISSUE (one thread) =====================================
@@ -686,6 +691,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
       }
       tc_fence_before();
       fence_async_smem();
+      // A full role barrier here, not per-warp arrivals: the two warps of a quadrant refill the SAME
+      // route entries of stage s right below (fetch_route), so neither may start before both have
+      // read them (compute-sanitizer racecheck flags exactly that when this is a per-warp arrival)
       bar_epi();
       if (tid == 0) mbar_arrive(bar(6 + s));
       fetch_route(k + 2, tile + 2 * grid);   // stage s is free again: this thread's reads are done
@@ -795,8 +803,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) sa_layer_bwd_kernel(const BwdA
         }
       }
       tc_fence_before();
-      bar_epi();   // every epilogue thread is done with D1/D2[s] (and, gather layers, s_idx)
-      if (tid == 0) mbar_arrive(bar(10 + s));
+      __syncwarp();   // every thread of this warp is done with D1/D2[s] (and, gather layers, s_idx)
+      if (lane == 0) mbar_arrive(bar(10 + s));
     }
 
     if (a.do_dgrad && kMode == 1 && a.stats_prev != nullptr) {

@@ -14,11 +14,13 @@ run() {   # run <tool> <tag> <pytest args...>
 SEL_MLP="dense_layer_store_and_stats or gather_layer_matches or pool_epilogue or dense_layer_backward or gather_layer_backward or thin_first_layer or compact_dense_layer or compact_plan"
 run memcheck mlp tests/test_mlp_gpu.py -k "$SEL_MLP or fused_block_single_scene or compact_block"
 run memcheck dense tests/test_dense_gpu.py
-run memcheck ops tests/test_ops_gpu.py -k "fps_small or fps_odd or fps_hole or fps_forced or ball_query_grid or ball_query_ragged or three_nn or group or gather or interp"
+run memcheck ops tests/test_ops_gpu.py -k "fps_small or fps_odd or fps_hole or fps_forced or fps_bucket or fps_legacy or ball_query_grid or ball_query_ragged or three_nn or group or gather or interp or scatter"
+run memcheck adam tests/test_modules_gpu.py -k "flat_adam"
 run synccheck mlp tests/test_mlp_gpu.py -k "$SEL_MLP"
 run synccheck dense tests/test_dense_gpu.py -k "dense_forward or dense_backward"
-run synccheck ops tests/test_ops_gpu.py -k "fps_small_levels or fps_forced_cluster or fps_hole"
+run synccheck ops tests/test_ops_gpu.py -k "fps_small_levels or fps_forced_cluster or fps_hole or fps_bucket or fps_cluster_hint or scatter"
 run racecheck mlp tests/test_mlp_gpu.py -k "dense_layer_store_and_stats or pool_epilogue or compact_dense_layer or thin_first_layer_forward"
+run racecheck mlpbwd tests/test_mlp_gpu.py -k "dense_layer_backward or gather_layer_backward"
 run racecheck dense tests/test_dense_gpu.py -k "dense_forward"
-run racecheck ops tests/test_ops_gpu.py -k "fps_small_levels or fps_forced_cluster or ball_query_ragged"
+run racecheck ops tests/test_ops_gpu.py -k "fps_small_levels or fps_forced_cluster or fps_bucket or ball_query_ragged or scatter_plan_cache"
 grep -h -A12 -E "Race reported|Invalid|Barrier error|Error:" gpurun_out/sanitize_*.log | head -80
