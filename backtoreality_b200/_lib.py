@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2r.so")
+# B2R_LIB: another build of the same C ABI (A/B timing of kernel variants); default: the in-tree build
+LIB_PATH = os.environ.get("B2R_LIB") or os.path.join(_HERE, "libb2r.so")
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
