@@ -103,10 +103,26 @@ class _on_device:
 FPS_LEGACY = os.environ.get("B2R_FPS_LEGACY", "0") not in ("0", "")
 
 
-def furthest_point_sampling(points, nsamples, cluster=0):
+def fps_presort(points):
+    """The spatial sort of furthest_point_sampling (include/b2r.h: b2r_fps_sort) run ahead of time:
+    returns the workspace to pass as `presorted=`.  Depends on the coordinates only."""
+    _chk_contig(points, "points")
+    _chk_float(points, "points")
+    _chk_cuda(points, [])
+    B, N = points.size(0), points.size(1)
+    l = _lib.lib()
+    nbytes = int(l.b2r_fps_workspace_bytes(B, N))
+    ws = torch.empty((max(nbytes, 4),), dtype=torch.uint8, device=points.device)
+    with _on_device(points):
+        _lib.check(l.b2r_fps_sort(points.data_ptr(), B, N, ws.data_ptr(), nbytes, _stream()), "fps_presort")
+    return ws
+
+
+def furthest_point_sampling(points, nsamples, cluster=0, presorted=None):
     """(B,N,3) f32 -> (B,nsamples) i32.  Replaces sampling.cpp:70-91.  `cluster` (not in the
     reference's signature, default 0 = lowest latency) caps the CTAs one scene holds; the
-    indices do not depend on it (include/b2r.h: b2r_fps_ws / b2r_fps_ex)."""
+    indices do not depend on it (include/b2r.h: b2r_fps_ws / b2r_fps_ex).  presorted: the
+    workspace `fps_presort(points)` returned for the SAME points (skips the sort)."""
     _chk_contig(points, "points")
     _chk_float(points, "points")
     _chk_cuda(points, [])
@@ -119,9 +135,15 @@ def furthest_point_sampling(points, nsamples, cluster=0):
                                     int(cluster), _stream()), "furthest_point_sampling")
         else:
             nbytes = int(l.b2r_fps_workspace_bytes(B, N))
-            ws = torch.empty((max(nbytes, 4),), dtype=torch.uint8, device=points.device)
-            _lib.check(l.b2r_fps_ws(points.data_ptr(), B, N, int(nsamples), out.data_ptr(),
-                                    int(cluster), ws.data_ptr(), nbytes, _stream()),
+            fn = l.b2r_fps_ws
+            if presorted is not None:
+                ws, fn = presorted, l.b2r_fps_ws_presorted
+                if ws.numel() < nbytes:
+                    raise RuntimeError("furthest_point_sampling: presorted workspace too small")
+            else:
+                ws = torch.empty((max(nbytes, 4),), dtype=torch.uint8, device=points.device)
+            _lib.check(fn(points.data_ptr(), B, N, int(nsamples), out.data_ptr(),
+                          int(cluster), ws.data_ptr(), nbytes, _stream()),
                        "furthest_point_sampling")
     return out
 

@@ -27,6 +27,8 @@ SIGNATURES = {
     "b2r_fps_plan": [_i, _i, _ip, _ip, _ip, _ip],
     "b2r_fps_workspace_bytes": [_i, _i],
     "b2r_fps_ws": [_vp, _i, _i, _i, _vp, _i, _vp, ctypes.c_longlong, _vp],
+    "b2r_fps_sort": [_vp, _i, _i, _vp, ctypes.c_longlong, _vp],
+    "b2r_fps_ws_presorted": [_vp, _i, _i, _i, _vp, _i, _vp, ctypes.c_longlong, _vp],
     "b2r_gather_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "b2r_gather_bwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "b2r_ball_query": [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp],

@@ -55,7 +55,7 @@ class Pointnet2Backbone(nn.Module):
         return xyz, features
 
     def geometry_prepass(self, xyz, fps_cluster=0, sm_limit=None, side=None, first=0, last=3,
-                         prev=None, copy_to=None, plan_splits=1):
+                         prev=None, copy_to=None, plan_splits=1, presorted=None):
         """inds / new_xyz / ball-query idx of sa1..sa4 for xyz (B,N,3), issued as one chain on a
         side stream with one event per level.  Returns the list of four per-level dicts that
         `forward(..., geometry=)` and `PointnetSAModuleVotes.forward(..., geometry=)` take.
@@ -75,6 +75,8 @@ class Pointnet2Backbone(nn.Module):
         also copied into copy_to[level][key] on the side streams as soon as they exist
         (train_step.PipelinedTrainStepPP: the static buffers of the NEXT graph, filled off the
         critical path).
+        presorted: `_ext.fps_presort(xyz)` of the same xyz, when the caller ran the first level's
+        spatial sort ahead of time (it depends on the coordinates only).
         plan_splits: k > 1 builds the pad-free plans per batch slice (keys "cidx#i", "ccen#i",
         "cmeta#i"): the batch will be consumed as k separate forwards (`split_geometry`; the BR step
         of train_Votenet_BR.py:277-289 runs the source and the target half one after the other)."""
@@ -96,7 +98,8 @@ class Pointnet2Backbone(nn.Module):
         fp, fp_ev = {}, None
         with torch.cuda.stream(side), torch.no_grad():
             for sa in (self.sa1, self.sa2, self.sa3, self.sa4)[first:last + 1]:
-                inds = _ext.furthest_point_sampling(cur, sa.npoint, cluster=fps_cluster)
+                inds = _ext.furthest_point_sampling(cur, sa.npoint, cluster=fps_cluster,
+                                                    presorted=presorted if cur is xyz else None)
                 new_xyz = pointnet2_utils.gather_operation(
                     cur.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
                 query.wait_stream(side)

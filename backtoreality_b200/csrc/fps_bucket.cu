@@ -778,8 +778,53 @@ extern "C" long long b2r_fps_workspace_bytes(int B, int N) {
   return (long long)B * N * (long long)sizeof(int);
 }
 
+namespace {
+int fps_sort_launch(const float *xyz, int B, int N, int bits, int *perm, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  B2R_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    B2R_CUDA(cudaFuncSetAttribute(b2r::fps_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (1 << 15) * (int)sizeof(int)));
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
+  b2r::fps_sort_kernel<<<B, 1024, (size_t)(1 << (3 * bits)) * sizeof(int), st>>>(xyz, N, bits, perm);
+  B2R_CHECK_LAUNCH();
+  return B2R_OK;
+}
+int fps_ws_impl(const float *xyz, int B, int N, int npoint, int *idx, int cluster_hint, void *workspace,
+                long long workspace_bytes, bool presorted, void *stream);
+}  // namespace
+
+extern "C" int b2r_fps_sort(const float *xyz, int B, int N, void *workspace, long long workspace_bytes,
+                            void *stream) {
+  B2R_REQUIRE(B >= 0 && N >= 0, "b2r_fps_sort: negative size");
+  if (B == 0 || N <= b2r::kSingleCtaMaxN) return B2R_OK;   // single-CTA scenes are not sorted
+  B2R_REQUIRE(xyz != nullptr && workspace != nullptr && workspace_bytes >= b2r_fps_workspace_bytes(B, N),
+              "b2r_fps_sort: null pointer or workspace of %lld bytes, %lld needed", workspace_bytes,
+              b2r_fps_workspace_bytes(B, N));
+  B2R_REQUIRE(B <= 65535, "b2r_fps_sort: B too large");
+  b2r::Plan pl;
+  if (!b2r::make_plan(B, N, 0, &pl)) {
+    b2r::set_error("b2r_fps_sort: N=%d exceeds the register-resident capacity", N);
+    return B2R_ERR_UNSUPPORTED;
+  }
+  return fps_sort_launch(xyz, B, N, pl.bits, static_cast<int *>(workspace), static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int b2r_fps_ws(const float *xyz, int B, int N, int npoint, int *idx, int cluster_hint,
                           void *workspace, long long workspace_bytes, void *stream) {
+  return fps_ws_impl(xyz, B, N, npoint, idx, cluster_hint, workspace, workspace_bytes, false, stream);
+}
+
+extern "C" int b2r_fps_ws_presorted(const float *xyz, int B, int N, int npoint, int *idx, int cluster_hint,
+                                    void *workspace, long long workspace_bytes, void *stream) {
+  return fps_ws_impl(xyz, B, N, npoint, idx, cluster_hint, workspace, workspace_bytes, true, stream);
+}
+
+namespace {
+int fps_ws_impl(const float *xyz, int B, int N, int npoint, int *idx, int cluster_hint, void *workspace,
+                long long workspace_bytes, bool presorted, void *stream) {
   B2R_REQUIRE(B >= 0 && N >= 0 && npoint >= 0, "b2r_fps_ws: negative size (B=%d N=%d npoint=%d)", B,
               N, npoint);
   B2R_REQUIRE(cluster_hint >= 0 && cluster_hint <= 16, "b2r_fps_ws: cluster_hint=%d not in [0,16]",
@@ -821,18 +866,9 @@ extern "C" int b2r_fps_ws(const float *xyz, int B, int N, int npoint, int *idx, 
     return B2R_ERR_UNSUPPORTED;
   }
   int *perm = static_cast<int *>(workspace);
-  {
-    static bool attr_done[64] = {};
-    int dev = 0;
-    B2R_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-      B2R_CUDA(cudaFuncSetAttribute(b2r::fps_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (1 << 15) * (int)sizeof(int)));
-      if (dev >= 0 && dev < 64) attr_done[dev] = true;
-    }
-    b2r::fps_sort_kernel<<<B, 1024, (size_t)(1 << (3 * pl.bits)) * sizeof(int), st>>>(xyz, N, pl.bits,
-                                                                                    perm);
-    B2R_CHECK_LAUNCH();
+  if (!presorted) {
+    const int rc = fps_sort_launch(xyz, B, N, pl.bits, perm, st);
+    if (rc != B2R_OK) return rc;
   }
   cudaError_t e = cudaSuccess;
   for (int attempt = 0; attempt < 2; ++attempt) {
@@ -859,3 +895,4 @@ extern "C" int b2r_fps_ws(const float *xyz, int B, int N, int npoint, int *idx, 
   }
   return B2R_OK;
 }
+}  // namespace

@@ -201,11 +201,15 @@ class PipelinedTrainStep:
         # step's own activations while FPS is still reading it
         xyz_next = self._xyz(self.next)
         box = {}
+        # the spatial sort of SA1's FPS depends on the coordinates alone: it runs NOW, on the side
+        # stream, so that only the sampling itself sits on the pre-pass's dependency chain
+        presorted = self._presort(xyz_next)
 
         def launch_prepass():
             box["nxt"] = self.backbone.geometry_prepass(xyz_next, fps_cluster=self.fps_cluster,
                                                         sm_limit=0, side=self.side,
-                                                        plan_splits=self.plan_splits)
+                                                        plan_splits=self.plan_splits,
+                                                        presorted=presorted)
 
         levels = self._levels(self.geo_cur)
         if self.start_after_level is None:
@@ -230,6 +234,16 @@ class PipelinedTrainStep:
                 srcs.append(src[k])
         torch._foreach_copy_(dsts + [self.cur], srcs + [self.next])
         return loss
+
+    def _presort(self, xyz_next):
+        from . import _ext
+        if _ext.FPS_LEGACY or self.start_after_level is None:
+            return None       # legacy kernel: no sort; pre-pass from the step's start: nothing to gain
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side), torch.no_grad():
+            ws = _ext.fps_presort(xyz_next)
+        ws.record_stream(torch.cuda.current_stream())
+        return ws
 
     def recapture(self):
         from . import _ext
@@ -299,10 +313,12 @@ class PipelinedTrainStepPP(PipelinedTrainStep):
         main = torch.cuda.current_stream()
         xyz_next = self._xyz(self.X[1 - p])   # referenced until the side stream has been joined
         box = {}
+        presorted = self._presort(xyz_next)
 
         def launch_prepass():
             box["nxt"] = self.backbone.geometry_prepass(xyz_next, fps_cluster=self.fps_cluster,
-                                                        sm_limit=0, side=self.side, copy_to=self.G[1 - p])
+                                                        sm_limit=0, side=self.side, copy_to=self.G[1 - p],
+                                                        presorted=presorted)
 
         levels = self._levels(self.G[p])
         if self.start_after_level is None:

@@ -86,6 +86,13 @@ B2R_API int b2r_fps_ex(const float *xyz, int B, int N, int npoint, int *idx, int
 B2R_API long long b2r_fps_workspace_bytes(int B, int N);
 B2R_API int b2r_fps_ws(const float *xyz, int B, int N, int npoint, int *idx, int cluster_hint,
                        void *workspace, long long workspace_bytes, void *stream);
+/* The two halves of b2r_fps_ws separately: the sort depends on xyz alone, so a caller that knows its
+ * next batch early (the pipelined training step) can run it ahead of time and keep only the
+ * sampling itself on its dependency chain.  b2r_fps_sort is a no-op for scenes of <= 4096 points. */
+B2R_API int b2r_fps_sort(const float *xyz, int B, int N, void *workspace, long long workspace_bytes,
+                         void *stream);
+B2R_API int b2r_fps_ws_presorted(const float *xyz, int B, int N, int npoint, int *idx, int cluster_hint,
+                                 void *workspace, long long workspace_bytes, void *stream);
 
 /* Launch geometry b2r_fps would use for (B,N): cluster size, threads per CTA, points per thread
  * and dynamic shared memory bytes.  Any out pointer may be NULL. */

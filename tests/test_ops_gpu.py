@@ -420,3 +420,15 @@ def test_nn_distance_matches_reference_formulation(cuda, B, N, M, kw):
     assert float((i1 != j1).float().mean()) < 1e-3 and float((i2 != j2).float().mean()) < 1e-3
     assert rel_l2(g1.cpu().numpy(), q1.grad.cpu().numpy()) < 1e-4
     assert rel_l2(g2.cpu().numpy(), q2.grad.cpu().numpy()) < 1e-4
+
+
+def test_fps_presorted_equals_one_call(cuda):
+    """b2r_fps_sort + b2r_fps_ws_presorted (the sort run ahead of time by the pipelined step) give
+    the indices of the single call; single-CTA scenes ignore the workspace."""
+    from backtoreality_b200 import _ext
+    for N, npnt in ((40000, 700), (3000, 200)):
+        xyz = _t(scenes.batch(33, 2, N, C=0, kind="room", dup=0.2)[..., :3], cuda)
+        ws = _ext.fps_presort(xyz)
+        a = _ext.furthest_point_sampling(xyz, npnt, cluster=4, presorted=ws)
+        b = _ext.furthest_point_sampling(xyz, npnt)
+        assert torch.equal(a, b)
