@@ -87,12 +87,146 @@ def query_and_group(xyz, new_xyz, features, radius, nsample, normalize_xyz=True,
     return grouped_features, idx
 
 
+def round_tf32(t):
+    """`cvt.rna.tf32.f32` (round to nearest, ties away from zero, 10 mantissa bits) of finite fp32
+    values: what every forward operand of the product's tensor-core layers goes through
+    (csrc/mlp_common.cuh to_tf32)."""
+    bits = t.detach().contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1fff).view(torch.float32)
+
+
+def round_bf16(t):
+    """`__float2bfloat16_rn` (round to nearest even): the operands of the fused SA backward."""
+    return t.detach().bfloat16().float()
+
+
+_ROUND = {"fp32": lambda t: t.detach(), "tf32": round_tf32, "bf16": round_bf16}
+
+
+class _RoundedConv1x1(Function):
+    """A 1x1 convolution whose operands are rounded the way the product's kernels round them
+    (forward: x and W; backward: grad_out, W and x), products and sums exact (fp64).  With it the
+    port is the product's arithmetic up to summation order, so the fused path can be held to a
+    tight bound at backbone scale instead of "no worse than cuDNN TF32" (tests/
+    test_modules_gpu.py::test_backbone_40k_vs_operand_rounding_emulation)."""
+
+    @staticmethod
+    def forward(ctx, x, w, fwd, bwd):
+        ctx.save_for_backward(x, w)
+        ctx.bwd = bwd
+        r = _ROUND[fwd]
+        return torch.einsum("oc,bcns->bons", r(w)[:, :, 0, 0].double(), r(x).double()).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        r = _ROUND[ctx.bwd]
+        gd = r(g).double()
+        dx = torch.einsum("oc,bons->bcns", r(w)[:, :, 0, 0].double(), gd).float()
+        dw = torch.einsum("bons,bcns->oc", gd, r(x).double()).float()[:, :, None, None]
+        return dx, dw, None, None
+
+
+def _bc(v):
+    return v[None, :, None, None]
+
+
+class _TopConvBN(Function):
+    """The pooled TOP layer of a fused SA block in training mode: 1x1 convolution + BatchNorm as
+    one function, because the product's backward does not keep this layer's z -- it recomputes it
+    on the tensor cores from the BF16 operands (csrc/mlp_bwd.cu, "top" variant) and uses THAT z in
+    the x_hat term of the BatchNorm backward, while the two BatchNorm sums (= the gradients of
+    gamma and beta) come from the forward's pooled values.  Everything else as _RoundedConv1x1."""
+
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, eps, fwd, bwd):
+        r = _ROUND[fwd]
+        z = torch.einsum("oc,bcns->bons", r(w)[:, :, 0, 0].double(), r(x).double()).float()
+        mean = z.mean((0, 2, 3))
+        var = z.var((0, 2, 3), unbiased=False)
+        invstd = torch.rsqrt(var + eps)
+        ctx.save_for_backward(x, w, gamma, mean, invstd, z)
+        ctx.bwd = bwd
+        ctx.mark_non_differentiable(mean, var)
+        return (z - _bc(mean)) * _bc(invstd * gamma) + _bc(beta), mean, var
+
+    @staticmethod
+    def backward(ctx, dy, _gm, _gv):
+        x, w, gamma, mean, invstd, z = (t.double() for t in ctx.saved_tensors)
+        r = _ROUND[ctx.bwd]
+        xb, wb = r(x.float()).double(), r(w.float())[:, :, 0, 0].double()
+        n = z.numel() // z.shape[1]
+        dy = dy.double()
+        s1 = dy.sum((0, 2, 3))
+        s2 = (dy * (z - _bc(mean)) * _bc(invstd)).sum((0, 2, 3))
+        z_re = torch.einsum("oc,bcns->bons", wb, xb).float().double()   # fp32 accumulators
+        xhat = (z_re - _bc(mean)) * _bc(invstd)
+        dz = _bc(gamma * invstd) * (dy - _bc(s1) / n - xhat * _bc(s2) / n)
+        dz = r(dz.float()).double()
+        dx = torch.einsum("oc,bons->bcns", wb, dz).float()
+        dw = torch.einsum("bons,bcns->oc", dz, xb).float()[:, :, None, None]
+        return dx, dw, s2.float(), s1.float(), None, None, None
+
+
+class _Conv1x1(nn.Conv2d):
+    """nn.Conv2d (same parameters / state-dict keys) with an optional operand-rounding mode:
+    `operands = (forward, backward)`, each one of "fp32" | "tf32" | "bf16"; None = plain conv.
+    `top_bn` (set by emulate_product_operands on an SA block's last layer) = the BatchNorm2d that
+    follows; in training mode conv + BN then run as _TopConvBN and that module passes through."""
+    operands = None
+    top_bn = None
+
+    def forward(self, x):
+        if self.operands is None:
+            return super().forward(x)
+        bn = self.top_bn
+        if bn is not None and bn.training:
+            y, mean, var = _TopConvBN.apply(x, self.weight, bn.weight, bn.bias, bn.eps,
+                                            *self.operands)
+            with torch.no_grad():
+                n = x.numel() // x.shape[1]
+                m = bn.momentum
+                bn.running_mean.mul_(1 - m).add_(m * mean)
+                bn.running_var.mul_(1 - m).add_(m * var * n / max(n - 1, 1))
+                bn.num_batches_tracked += 1
+            return y
+        y = _RoundedConv1x1.apply(x, self.weight, *self.operands)
+        return y if self.bias is None else y + self.bias.view(1, -1, 1, 1)
+
+
+def emulate_product_operands(backbone, on=True):
+    """Switch a `Backbone` to the operand precisions of the product's kernels:
+    fused SA layers TF32 forward / BF16 backward (csrc/mlp.cu, mlp_bwd.cu); a first SA layer with
+    <= 8 input channels TF32-rounded operands forward, fp32 backward (csrc/mlp_thin.cu); FP-module
+    layers TF32 in both directions (csrc/dense.cu)."""
+    for name, m in backbone.named_modules():
+        if isinstance(m, SAModuleVotes):
+            top = m.mlp_module[len(m.mlp_module) - 1]
+            bn = top.bn.bn if hasattr(top, "bn") else None
+            top.conv.__dict__["top_bn"] = bn if on else None   # not registered as a submodule
+            if bn is not None:
+                bn.__dict__.pop("forward", None)
+                if on:   # conv + BN run inside _TopConvBN while training
+                    bn.forward = (lambda t, bn=bn:
+                                  t if bn.training else nn.BatchNorm2d.forward(bn, t))
+        if not isinstance(m, _Conv1x1):
+            continue
+        if not on:
+            m.operands = None
+        elif ".mlp_module." in "." + name:
+            thin = name.endswith("layer0.conv") and m.in_channels <= 8
+            m.operands = ("tf32", "fp32") if thin else ("tf32", "bf16")
+        else:
+            m.operands = ("tf32", "tf32")
+    return backbone
+
+
 def shared_mlp(channels, bn=True):
     """Same nesting/names as pytorch_utils.SharedMLP: layer{i}.conv, layer{i}.bn.bn."""
     seq = nn.Sequential()
     for i in range(len(channels) - 1):
         blk = nn.Sequential()
-        conv = nn.Conv2d(channels[i], channels[i + 1], kernel_size=(1, 1), bias=not bn)
+        conv = _Conv1x1(channels[i], channels[i + 1], kernel_size=(1, 1), bias=not bn)
         nn.init.kaiming_normal_(conv.weight)
         blk.add_module("conv", conv)
         if bn:

@@ -103,3 +103,61 @@ def test_new_module_parameter_layouts_match_the_reference_checksums():
     pnet = ProposalModule(4, 2, 4, g["msa"], 32, "seed_fps")
     assert abs(weight_checksum(vgen) + weight_checksum(pnet) - float(g["wsum"])) < 1e-6 * float(g["wsum"])
     assert pnet.conv3.out_channels == 2 + 3 + 2 * 2 + 4 * 4 + 4
+
+
+def test_operand_rounding_emulation_of_the_port():
+    """cpu_modules.emulate_product_operands (the checker of the GPU emulation tests): rounding
+    helpers are bit-exact models of cvt.rna.tf32 / bf16 RNE; with "fp32" operands the emulated
+    convolutions and the fused top conv + BatchNorm function reproduce the plain port (forward,
+    every gradient, running statistics); state-dict keys do not change; switching off restores
+    the plain modules."""
+    import struct
+    from backtoreality_b200 import scenes
+
+    def f32(bits):
+        return struct.unpack("<f", struct.pack("<I", bits))[0]
+
+    x = torch.tensor([f32(0x3F800FFF), f32(0x3F801000), f32(0x3F801001), f32(0xBF801000), 0.0])
+    assert [hex(v) for v in cpu_modules.round_tf32(x).view(torch.int32).tolist()] == \
+        [hex(v) for v in torch.tensor([0x3F800000, 0x3F802000, 0x3F802000, 0xBF802000 - (1 << 32), 0],
+                                      dtype=torch.int64).to(torch.int32).tolist()]   # ties away from zero
+    y = torch.tensor([f32(0x3F808000), f32(0x3F818000), f32(0x3F808001)])
+    assert cpu_modules.round_bf16(y).view(torch.int32).tolist() == [0x3F800000, 0x3F820000, 0x3F810000]
+
+    torch.manual_seed(11)
+    port = cpu_modules.SAModuleVotes(npoint=128, radius=0.4, nsample=16, mlp=[8, 16, 16, 32],
+                                     normalize_xyz=True).train()
+    keys = list(port.state_dict().keys())
+    pc = torch.from_numpy(scenes.batch(31, 2, 1024, C=0))[..., :3].contiguous()
+    feats = torch.randn(2, 8, 1024)
+    w = None
+
+    def run():
+        nonlocal w
+        port.zero_grad()
+        port.mlp_module.layer2.bn.bn.reset_running_stats()
+        f = feats.clone().requires_grad_(True)
+        _, out, _ = port(pc, f)
+        if w is None:
+            w = torch.randn(out.shape, generator=torch.Generator().manual_seed(1))
+        (out * w).sum().backward()
+        g = {n: p.grad.clone() for n, p in port.named_parameters()}
+        g["input"] = f.grad.clone()
+        return out.detach().clone(), g, port.mlp_module.layer2.bn.bn.running_var.clone()
+
+    y0, g0, rv0 = run()
+    cpu_modules.emulate_product_operands(port)
+    assert list(port.state_dict().keys()) == keys
+    assert port.mlp_module.layer0.conv.operands == ("tf32", "bf16")
+    y_e, g_e, _ = run()
+    assert 1e-5 < rel_l2(y_e, y0) < 5e-3            # TF32 operands are visible ...
+    for m in port.modules():
+        if isinstance(m, cpu_modules._Conv1x1):
+            m.operands = ("fp32", "fp32")
+    y1, g1, rv1 = run()                             # ... exact operands are not
+    assert rel_l2(y1, y0) < 1e-6 and rel_l2(rv1, rv0) < 1e-6
+    for n in g0:
+        assert rel_l2(g1[n], g0[n]) < 2e-5, n
+    cpu_modules.emulate_product_operands(port, False)
+    y2, g2, _ = run()
+    assert torch.equal(y2, y0) and all(torch.equal(g2[n], g0[n]) for n in g0)
